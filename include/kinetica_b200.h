@@ -1,0 +1,132 @@
+/* kinetica_b200.h — C ABI of libkinetica_b200.so
+ *
+ * B200-native (sm_100a) replacement for the kinetic-solve hot path of Kinetica.jl
+ * v0.7.2.  The reference has no FFI for this path: everything below
+ * `solve_network(method, sd, rd)` is Julia calling Julia (Catalyst / ModelingToolkit /
+ * OrdinaryDiffEq).  Each entry point therefore names the reference code it replaces
+ * (file:line under the reference checkout); the Julia-side `ccall` bindings are in
+ * julia/KineticaB200.jl and INTEGRATION.md.
+ *
+ * Conventions
+ *   - all functions return int32 status, 0 = OK; kb2_last_error(h) describes the last failure
+ *   - indices are int64 and 0-based (the Julia shim subtracts 1)
+ *   - reals are FP64
+ *   - host arrays belong to the caller and are only read/written during the call
+ *   - ensemble arrays are species-major x member-minor: x[i*B + b]
+ *   - one handle = one GPU = one stream; a handle is not re-entrant
+ */
+#ifndef KINETICA_B200_H
+#define KINETICA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kb2_ctx *kb2_handle;
+
+/* per-member status words written by kb2_solve (reference: sol.retcode, and the
+ * ErrorException("ODE solution failed.") of src/solving/solve_utils.jl:405-411) */
+enum {
+    KB2_OK = 0,
+    KB2_MAXITERS = 1,      /* reference maxiters, src/solving/methods.jl:165 */
+    KB2_DTMIN = 2,         /* reference dtmin = eps(tspan[end]), src/solving/methods.jl:164 */
+    KB2_UNFINISHED = 5
+};
+
+/* condition-profile kinds understood by the device (reference src/conditions/*.jl) */
+enum {
+    KB2_PROFILE_STATIC = 0,          /* static.jl:7-9              params: [value] */
+    KB2_PROFILE_NULL = 1,            /* direct_variable.jl:49-92 / gradient_variable.jl:70-114   [X_start] */
+    KB2_PROFILE_LINEAR_DIRECT = 2,   /* direct_variable.jl:98-155   [rate, X_start, X_end, t_end] */
+    KB2_PROFILE_LINEAR_GRADIENT = 3, /* gradient_variable.jl:120-175 [rate, X_start, X_end, t_end] */
+    KB2_PROFILE_DOUBLE_RAMP = 4      /* gradient_variable.jl:181-310 [X_start, rate1, rate2, t_startr1,
+                                        t_endr1, t_startr2, t_endr2, t_blend] */
+};
+#define KB2_PROFILE_NPARAMS 16
+
+/* stop flags */
+#define KB2_STOP_RATE 1   /* discrete rate update: CompleteRateUpdateAffect, solve_utils.jl:445-450 */
+#define KB2_STOP_SAVE 2   /* saveat point, methods.jl:166 */
+
+/* ---- lifetime ---- */
+int32_t kb2_create(int32_t device, kb2_handle *out);
+int32_t kb2_destroy(kb2_handle h);
+const char *kb2_last_error(kb2_handle h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t kb2_launch_count(kb2_handle h);
+
+/* ---- network: replaces make_rs (solve_utils.jl:318-334) + Catalyst/MTK codegen of f and J.
+ * Input schema = RxData id/stoichiometry arrays flattened to CSR (network.jl:193-203). ---- */
+int32_t kb2_set_network(kb2_handle h, int64_t S, int64_t R,
+                        const int64_t *reac_ptr, const int64_t *reac_idx, const int64_t *reac_nu,
+                        const int64_t *prod_ptr, const int64_t *prod_idx, const int64_t *prod_nu);
+
+/* ---- symbolic analysis: replaces MTK `jac=true, sparse=true` pattern detection
+ * (methods.jl:157-158) and KLU's symbolic phase.  ordering: 0 = minimum degree,
+ * 1 = natural, 2 = caller-supplied via kb2_set_ordering. ---- */
+int32_t kb2_set_ordering(kb2_handle h, const int64_t *perm);
+int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, int64_t *nnzLU, int64_t *n_fma);
+int32_t kb2_get_pattern(kb2_handle h, int64_t *colptr, int64_t *rowval);          /* CSC of P_J */
+int32_t kb2_get_ordering(kb2_handle h, int64_t *perm);
+int32_t kb2_get_lu_pattern(kb2_handle h, int64_t *rowptr, int64_t *colidx, int64_t *diagpos);
+
+/* ---- calculators: PrecalculatedArrheniusCalculator (calculator.jl:164-238);
+ * k = A*T^n*exp(-Ea/(R*T))*N_A*t_mult, harmonic cap with k_max unless k_max is NaN;
+ * n may be NULL (= the reference formula, which has no T^n term). ---- */
+int32_t kb2_set_arrhenius(kb2_handle h, const double *A, const double *Ea, const double *n,
+                          double k_max, double t_mult);
+/* any other calculator: host-precomputed table k[s*R + r] for the rate-update stops, in stop
+ * order (calculate_discrete_rates, solve_utils.jl:91-109); k_init[R] = calc(initial conditions)
+ * (methods.jl:668).  Shared by all members. */
+int32_t kb2_set_rate_table(kb2_handle h, int64_t n_rate_stops, const double *k_table,
+                           const double *k_init);
+
+/* ---- conditions: per-member profile of the :T condition (ConditionSet, condition_set.jl:1-58) ---- */
+int32_t kb2_set_profiles(kb2_handle h, int64_t B, const int32_t *kind, const double *params);
+/* optional override: condition value per member at every stop, T[b*nstops + s] (NaN = use the
+ * profile) — the reference reads the interpolated profile solution, solve_utils.jl:101-104 */
+int32_t kb2_set_T_table(kb2_handle h, int64_t B, int64_t nstops, const double *T);
+/* merged stop list shared by all members: sorted, last entry = tspan[2]
+ * (get_tstops condition_set.jl:172-176, tstops kwarg methods.jl:697, saveat :166) */
+int32_t kb2_set_stops(kb2_handle h, int64_t nstops, const double *stop_t, const int32_t *flags);
+
+/* ---- the solve: replaces init/solve!/adaptive_solve! (methods.jl:174-180, 705-711,
+ * solve_utils.jl:376-424) for B members at once.
+ *   u0[u0_stride*b + i]  (u0_stride = 0 broadcasts one vector; else u0_stride = S)
+ *   out_u[(s*S + i)*B + b]  s = save index;  out_umax[i*B + b] = max over saves (NULL to skip)
+ *   status[b];  stats[b*8] = {accepted, rejected, lu, rhs, 0,0,0,0} ---- */
+int32_t kb2_solve(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, double t0,
+                  double abstol, double reltol, double dtmin, int64_t maxiters,
+                  int32_t ban_negatives, int64_t Ns, double *out_u, double *out_umax,
+                  int32_t *status, int64_t *stats);
+/* the same in three phases (bench.py times `run` alone with inputs resident in HBM) */
+int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, double t0,
+                          double abstol, double reltol, double dtmin, int64_t maxiters,
+                          int32_t ban_negatives, int64_t Ns);
+int32_t kb2_solve_run(kb2_handle h, float *ms_device);
+int32_t kb2_solve_fetch(kb2_handle h, double *out_u, double *out_umax, int32_t *status, int64_t *stats);
+/* device-side results for the multi-GPU allgather: packs final concentrations and per-species
+ * maxima member-major into caller-provided DEVICE buffers final_bs[b*S+i], umax_bs[b*S+i] */
+int32_t kb2_pack_results_device(kb2_handle h, double *final_bs_dev, double *umax_bs_dev);
+
+/* ---- kernel-level entry points (parity tests + per-kernel roofline) ---- */
+int32_t kb2_eval_k(kb2_handle h, int64_t B, const double *T, double *k_out);
+int32_t kb2_eval_profile(kb2_handle h, int64_t B, int64_t nt, const double *t, double *X_out);
+int32_t kb2_eval_rhs(kb2_handle h, int64_t B, const double *u, const double *k, double *du);
+int32_t kb2_eval_jac(kb2_handle h, int64_t B, const double *u, const double *k, double *Jval);
+int32_t kb2_factor(kb2_handle h, int64_t B, const double *u, const double *k,
+                   const double *hg_inv, double *lu_out);
+int32_t kb2_trisolve(kb2_handle h, int64_t B, const double *rhs, double *x);
+/* time `iters` launches of one standalone kernel on resident data; which: 0 arrhenius, 1 rhs,
+ * 2 jacobian, 3 W-assembly+LU, 4 trisolve */
+int32_t kb2_time_kernel(kb2_handle h, int32_t which, int64_t B, int32_t iters, float *ms_avg);
+
+/* tuning: members per tile (power of two <= 32, 0 = auto) and threads per CTA (0 = auto) */
+int32_t kb2_set_tiling(kb2_handle h, int32_t members_per_tile, int32_t threads_per_cta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

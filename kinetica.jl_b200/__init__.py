@@ -1,0 +1,12 @@
+"""kinetica_b200 — B200-native kinetic-solve hot path of Kinetica.jl behind the reference's
+calculator / ODESimulationParams / ConditionSet API.  Sources live in `kinetica.jl_b200/`;
+import as `kinetica_b200`."""
+from .calculator import (AbstractKineticCalculator, DummyKineticCalculator,
+                         PrecalculatedArrheniusCalculator)
+from .conditions import (ConditionSet, DoubleRampGradientProfile, LinearDirectProfile,
+                         LinearGradientProfile, NullDirectProfile, NullGradientProfile,
+                         StaticConditionProfile, create_savepoints, tconvert)
+from .network import RxData, SpeciesData
+from .params import B200Rodas4, ODESimulationParams
+from .solve import (B200EnsembleODESolve, EnsembleSolver, ODESolveOutput, RxFilter, StaticODESolve,
+                    VariableODESolve, solve_network)

@@ -1,0 +1,260 @@
+// Host-side symbolic analysis, computed once per network and shared by every ensemble member.
+//
+// Replaces, for the B200 path, what the reference obtains from upstream packages when it builds
+// `ODEProblem(osys, u0map, tspan, pmap; jac=true, sparse=true)` (reference
+// src/solving/methods.jl:157-158, 686-687): the analytic-Jacobian sparsity pattern, plus the
+// symbolic phase of the sparse LU the chosen solver would run (docs use KLU,
+// docs/src/getting-started.md:66-70).  Mass-action semantics follow `make_rs`
+// (src/solving/solve_utils.jl:318-334) with Catalyst's non-combinatoric rate law.
+#include "kb2_internal.h"
+
+#include <algorithm>
+#include <set>
+#include <utility>
+
+namespace kb2 {
+
+std::string build_network(Network &net)
+{
+    const int64_t S = net.S, R = net.R;
+    if (S <= 0) return "network has no species";
+    if ((int64_t)net.rp.size() != R + 1 || (int64_t)net.pp.size() != R + 1) return "bad CSR pointer length";
+    net.sub_ptr.assign(1, 0); net.sub_idx.clear(); net.sub_exp.clear();
+    net.net_ptr.assign(1, 0); net.net_idx.clear(); net.net_coef.clear();
+    for (int64_t j = 0; j < R; ++j) {
+        std::vector<std::pair<int64_t, int64_t>> sub, nt;
+        auto add = [](std::vector<std::pair<int64_t, int64_t>> &v, int64_t s, int64_t n) {
+            for (auto &e : v) if (e.first == s) { e.second += n; return; }
+            v.emplace_back(s, n);
+        };
+        for (int64_t e = net.rp[j]; e < net.rp[j + 1]; ++e) {
+            if (net.ri[e] < 0 || net.ri[e] >= S) return "reactant species id out of range";
+            if (net.rn[e] <= 0) return "reactant stoichiometry must be positive";
+            add(sub, net.ri[e], net.rn[e]);
+            add(nt, net.ri[e], -net.rn[e]);
+        }
+        for (int64_t e = net.pp[j]; e < net.pp[j + 1]; ++e) {
+            if (net.pi[e] < 0 || net.pi[e] >= S) return "product species id out of range";
+            if (net.pn[e] <= 0) return "product stoichiometry must be positive";
+            add(nt, net.pi[e], net.pn[e]);
+        }
+        std::sort(sub.begin(), sub.end());
+        std::sort(nt.begin(), nt.end());
+        if (sub.size() > 3) return "more than 3 distinct reactant species in one reaction is not supported";
+        for (auto &e : sub) {
+            if (e.second > 255) return "reactant stoichiometry above 255 is not supported";
+            net.sub_idx.push_back((int32_t)e.first);
+            net.sub_exp.push_back((int32_t)e.second);
+        }
+        for (auto &e : nt)
+            if (e.second != 0) {
+                net.net_idx.push_back((int32_t)e.first);
+                net.net_coef.push_back((int32_t)e.second);
+            }
+        net.sub_ptr.push_back((int32_t)net.sub_idx.size());
+        net.net_ptr.push_back((int32_t)net.net_idx.size());
+    }
+    return "";
+}
+
+// Minimum degree on the symmetrised pattern with an explicit elimination graph.  Selection rule
+// (the contract the oracle mirrors): alive vertex with the smallest (current degree, index).
+static void min_degree(int64_t S, const std::vector<int64_t> &colptr, const std::vector<int64_t> &rowval,
+                       std::vector<int64_t> &perm)
+{
+    std::vector<std::vector<int32_t>> adj(S);
+    for (int64_t l = 0; l < S; ++l)
+        for (int64_t p = colptr[l]; p < colptr[l + 1]; ++p) {
+            int64_t i = rowval[p];
+            if (i != l) { adj[i].push_back((int32_t)l); adj[l].push_back((int32_t)i); }
+        }
+    for (auto &a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+    std::set<std::pair<int32_t, int32_t>> heap;
+    for (int64_t v = 0; v < S; ++v) heap.emplace((int32_t)adj[v].size(), (int32_t)v);
+    perm.clear();
+    std::vector<int32_t> merged;
+    while (!heap.empty()) {
+        auto it = heap.begin();
+        int32_t v = it->second;
+        heap.erase(it);
+        perm.push_back(v);
+        std::vector<int32_t> nb;
+        nb.swap(adj[v]);
+        for (int32_t a : nb) {
+            heap.erase({(int32_t)adj[a].size(), a});
+            merged.clear();
+            // adj[a] = (adj[a] U nb) \ {a, v}
+            size_t x = 0, y = 0;
+            const auto &A = adj[a];
+            while (x < A.size() || y < nb.size()) {
+                int32_t c;
+                if (y >= nb.size() || (x < A.size() && A[x] < nb[y])) c = A[x++];
+                else if (x >= A.size() || nb[y] < A[x]) c = nb[y++];
+                else { c = A[x]; ++x; ++y; }
+                if (c != a && c != v) merged.push_back(c);
+            }
+            adj[a] = merged;
+            heap.emplace((int32_t)adj[a].size(), a);
+        }
+    }
+}
+
+std::string build_symbolic(const Network &net, int ordering, Symbolic &sym)
+{
+    const int64_t S = net.S, R = net.R;
+    // ---- Jacobian pattern P_J = {(i,l): exists j, net[i,j] != 0 and nu_lj > 0}, CSC ----
+    {
+        std::vector<std::vector<int32_t>> cols(S);
+        for (int64_t j = 0; j < R; ++j)
+            for (int32_t a = net.sub_ptr[j]; a < net.sub_ptr[j + 1]; ++a)
+                for (int32_t e = net.net_ptr[j]; e < net.net_ptr[j + 1]; ++e)
+                    cols[net.sub_idx[a]].push_back(net.net_idx[e]);
+        sym.colptr.assign(S + 1, 0);
+        sym.rowval.clear();
+        for (int64_t l = 0; l < S; ++l) {
+            auto &c = cols[l];
+            std::sort(c.begin(), c.end());
+            c.erase(std::unique(c.begin(), c.end()), c.end());
+            for (int32_t i : c) sym.rowval.push_back(i);
+            sym.colptr[l + 1] = (int64_t)sym.rowval.size();
+        }
+        sym.nnzJ = (int64_t)sym.rowval.size();
+    }
+    // ---- ordering ----
+    if (ordering == 0) min_degree(S, sym.colptr, sym.rowval, sym.perm);
+    else if (ordering == 1) { sym.perm.resize(S); for (int64_t a = 0; a < S; ++a) sym.perm[a] = a; }
+    else {
+        if ((int64_t)sym.perm.size() != S) return "ordering 2 requested but kb2_set_ordering was not called";
+        std::vector<char> seen(S, 0);
+        for (int64_t a = 0; a < S; ++a) {
+            if (sym.perm[a] < 0 || sym.perm[a] >= S || seen[sym.perm[a]]) return "supplied ordering is not a permutation";
+            seen[sym.perm[a]] = 1;
+        }
+    }
+    sym.iperm.assign(S, 0);
+    for (int64_t a = 0; a < S; ++a) sym.iperm[sym.perm[a]] = a;
+    // ---- row-wise symbolic LU of P (P_J U diag) P^T without pivoting ----
+    {
+        std::vector<std::vector<int32_t>> rows(S);
+        for (int64_t a = 0; a < S; ++a) rows[a].push_back((int32_t)a);
+        for (int64_t l = 0; l < S; ++l)
+            for (int64_t p = sym.colptr[l]; p < sym.colptr[l + 1]; ++p)
+                rows[sym.iperm[sym.rowval[p]]].push_back((int32_t)sym.iperm[l]);
+        std::vector<std::vector<int32_t>> upper(S);
+        std::vector<int32_t> mark(S, -1);
+        sym.rowptr.assign(S + 1, 0);
+        sym.colidx.clear();
+        sym.diagpos.assign(S, 0);
+        sym.n_fma = 0;
+        std::vector<int32_t> pat;
+        for (int64_t i = 0; i < S; ++i) {
+            pat.clear();
+            std::set<int32_t> lower;           // pending pivots < i, ascending
+            for (int32_t c : rows[i])
+                if (mark[c] != (int32_t)i) { mark[c] = (int32_t)i; pat.push_back(c); if (c < i) lower.insert(c); }
+            while (!lower.empty()) {
+                int32_t k = *lower.begin();
+                lower.erase(lower.begin());
+                sym.n_fma += (int64_t)upper[k].size();
+                for (int32_t j : upper[k])
+                    if (mark[j] != (int32_t)i) { mark[j] = (int32_t)i; pat.push_back(j); if (j < i) lower.insert(j); }
+            }
+            std::sort(pat.begin(), pat.end());
+            for (size_t q = 0; q < pat.size(); ++q) {
+                if (pat[q] == (int32_t)i) sym.diagpos[i] = sym.rowptr[i] + (int64_t)q;
+                if (pat[q] > (int32_t)i) upper[i].push_back(pat[q]);
+                sym.colidx.push_back(pat[q]);
+            }
+            sym.rowptr[i + 1] = (int64_t)sym.colidx.size();
+        }
+        sym.nnzLU = (int64_t)sym.colidx.size();
+    }
+    if (sym.nnzLU >= (int64_t)1 << 31 || sym.n_fma >= (int64_t)1 << 32) return "factorisation too large for 32-bit tables";
+    // ---- RHS gather CSR (rows = species, entries in ascending reaction order) ----
+    {
+        std::vector<int32_t> cnt(S + 1, 0);
+        for (size_t e = 0; e < net.net_idx.size(); ++e) cnt[net.net_idx[e] + 1]++;
+        sym.rhs_ptr.assign(S + 1, 0);
+        for (int64_t i = 0; i < S; ++i) sym.rhs_ptr[i + 1] = sym.rhs_ptr[i] + cnt[i + 1];
+        sym.rhs_rxn.assign(net.net_idx.size(), 0);
+        sym.rhs_coef.assign(net.net_idx.size(), 0);
+        std::vector<int32_t> fill(sym.rhs_ptr.begin(), sym.rhs_ptr.end() - 1);
+        for (int64_t j = 0; j < R; ++j)
+            for (int32_t e = net.net_ptr[j]; e < net.net_ptr[j + 1]; ++e) {
+                int32_t pos = fill[net.net_idx[e]]++;
+                sym.rhs_rxn[pos] = (int32_t)j;
+                sym.rhs_coef[pos] = net.net_coef[e];
+            }
+    }
+    // ---- reaction descriptors ----
+    sym.rdesc.assign(4 * (size_t)std::max<int64_t>(R, 1), -1);
+    for (int64_t j = 0; j < R; ++j) {
+        int32_t ex = 0;
+        int s = 0;
+        for (int32_t a = net.sub_ptr[j]; a < net.sub_ptr[j + 1]; ++a, ++s) {
+            sym.rdesc[4 * j + s] = net.sub_idx[a];
+            ex |= net.sub_exp[a] << (8 * s);
+        }
+        sym.rdesc[4 * j + 3] = ex;
+    }
+    // ---- Jacobian terms per CSC entry ----
+    {
+        std::vector<std::vector<std::pair<int32_t, int32_t>>> terms(sym.nnzJ);
+        for (int64_t j = 0; j < R; ++j) {
+            int s = 0;
+            for (int32_t a = net.sub_ptr[j]; a < net.sub_ptr[j + 1]; ++a, ++s) {
+                int64_t l = net.sub_idx[a];
+                for (int32_t e = net.net_ptr[j]; e < net.net_ptr[j + 1]; ++e) {
+                    int64_t i = net.net_idx[e];
+                    auto b = sym.rowval.begin() + sym.colptr[l], en = sym.rowval.begin() + sym.colptr[l + 1];
+                    int64_t p = std::lower_bound(b, en, i) - sym.rowval.begin();
+                    int32_t c = net.net_coef[e] * net.sub_exp[a];
+                    terms[p].emplace_back((int32_t)j, (int32_t)(c * 4 + s));
+                }
+            }
+        }
+        sym.jt_ptr.assign(sym.nnzJ + 1, 0);
+        sym.jt_rxn.clear(); sym.jt_pack.clear();
+        for (int64_t p = 0; p < sym.nnzJ; ++p) {
+            for (auto &t : terms[p]) { sym.jt_rxn.push_back(t.first); sym.jt_pack.push_back(t.second); }
+            sym.jt_ptr[p + 1] = (int32_t)sym.jt_rxn.size();
+        }
+    }
+    // ---- LU slot tables ----
+    sym.lu_rowptr.assign(sym.rowptr.begin(), sym.rowptr.end());
+    sym.lu_colidx.assign(sym.colidx.begin(), sym.colidx.end());
+    sym.lu_diagpos.assign(sym.diagpos.begin(), sym.diagpos.end());
+    sym.slot_src.assign(sym.nnzLU, 0);
+    sym.max_rowlen = 0;
+    for (int64_t a = 0; a < S; ++a) {
+        sym.max_rowlen = std::max<int32_t>(sym.max_rowlen, (int32_t)(sym.rowptr[a + 1] - sym.rowptr[a]));
+        int64_t i = sym.perm[a];
+        for (int64_t q = sym.rowptr[a]; q < sym.rowptr[a + 1]; ++q) {
+            int64_t l = sym.perm[sym.colidx[q]];
+            auto b = sym.rowval.begin() + sym.colptr[l], en = sym.rowval.begin() + sym.colptr[l + 1];
+            auto it = std::lower_bound(b, en, i);
+            int32_t p1 = (it != en && *it == i) ? (int32_t)(it - sym.rowval.begin()) + 1 : 0;
+            sym.slot_src[q] = (p1 << 1) | (sym.colidx[q] == a ? 1 : 0);
+        }
+    }
+    // ---- elimination schedule ----
+    {
+        sym.tgt_off.assign(sym.nnzLU, 0);
+        sym.tgt.clear();
+        sym.tgt.reserve((size_t)sym.n_fma);
+        std::vector<int32_t> where(S, -1);
+        for (int64_t i = 0; i < S; ++i) {
+            for (int64_t q = sym.rowptr[i]; q < sym.rowptr[i + 1]; ++q) where[sym.colidx[q]] = (int32_t)(q - sym.rowptr[i]);
+            for (int64_t p = sym.rowptr[i]; p < sym.diagpos[i]; ++p) {
+                int64_t k = sym.colidx[p];
+                sym.tgt_off[p] = (uint32_t)sym.tgt.size();
+                for (int64_t q = sym.diagpos[k] + 1; q < sym.rowptr[k + 1]; ++q) sym.tgt.push_back(where[sym.colidx[q]]);
+            }
+        }
+        if ((int64_t)sym.tgt.size() != sym.n_fma) return "internal error: schedule size mismatch";
+    }
+    sym.ready = true;
+    return "";
+}
+
+}  // namespace kb2

@@ -1,0 +1,339 @@
+"""`solve_network` front door of the B200 path — host-side mirror of the reference's
+src/solving/methods.jl (method structs + dispatch), src/solving/solve_utils.jl (host
+pre-processing), src/solving/filters.jl and the output container of src/analysis/io.jl.
+
+The unchanged host steps of the reference run here in the same order (deepcopy, profile
+pre-solution, reaction filter, calculator setup, low-k pruning, u0 assembly); everything from
+"build the ReactionSystem" down (methods.jl:140-180 / 660-711) is replaced by one call into
+libkinetica_b200.so.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import copy
+import itertools
+from dataclasses import dataclass, field
+from typing import Any, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .calculator import AbstractKineticCalculator
+from .conditions import (ConditionSet, StaticConditionProfile, create_savepoints, isstatic, isvariable)
+from .network import RxData, SpeciesData
+from .params import ODESimulationParams
+
+STOP_RATE, STOP_SAVE = 1, 2
+RETCODES = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 5: "Unfinished"}
+
+
+# ---------------------------------------------------------------- filters (filters.jl:1-52)
+class RxFilter:
+    def __init__(self, filters=None, keep_filtered=False):
+        self.filters = [lambda sd, rd: [False] * rd.nr] if filters is None else list(filters)
+        self.keep_filtered = keep_filtered
+
+
+def get_filter_mask(rf: RxFilter, sd, rd):
+    if len(rf.filters) == 0:
+        raise RuntimeError("RxFilter has not filter functions defined.")
+    inv = ~np.asarray(rf.filters[0](sd, rd), dtype=bool)
+    for f in rf.filters[1:]:
+        inv &= ~np.asarray(f(sd, rd), dtype=bool)
+    mask = ~inv
+    return ~mask if rf.keep_filtered else mask
+
+
+# ---------------------------------------------------------------- method structs (methods.jl:7-79)
+class AbstractODESolveMethod:
+    pass
+
+
+class StaticODESolve(AbstractODESolveMethod):
+    def __init__(self, pars, conditions, calculator, filter=None):
+        if not conditions.isstatic():
+            raise ValueError("All conditions must be static to run a StaticODESolve.")
+        if not calculator.has_conditions(conditions.symbols):
+            raise ValueError("Calculator does not support all of the provided conditions.")
+        self.pars, self.conditions, self.calculator = pars, conditions, calculator
+        self.filter = filter if filter is not None else RxFilter()
+
+
+class VariableODESolve(AbstractODESolveMethod):
+    def __init__(self, pars, conditions, calculator, filter=None):
+        if not calculator.has_conditions(conditions.symbols):
+            raise ValueError("Calculator does not support all of the provided conditions.")
+        if not conditions.discrete_updates and not calculator.allows_continuous():
+            raise ValueError("Calculator does not support continuous rate updates in simulations.")
+        self.pars, self.conditions, self.calculator = pars, conditions, calculator
+        self.filter = filter if filter is not None else RxFilter()
+
+
+class B200EnsembleODESolve(AbstractODESolveMethod):
+    """New capability (the reference has no ensembles, docs/src/tutorials/ode-solution.md:190):
+    one ConditionSet per member, shared network / calculator / parameters."""
+
+    def __init__(self, pars, conditions: Sequence[ConditionSet], calculator, filter=None):
+        if len(conditions) == 0:
+            raise ValueError("An ensemble needs at least one ConditionSet.")
+        for cs in conditions:
+            if not calculator.has_conditions(cs.symbols):
+                raise ValueError("Calculator does not support all of the provided conditions.")
+            if not cs.isstatic() and not cs.discrete_updates:
+                raise ValueError("The B200 ensemble path needs discrete rate updates (ts_update) for variable conditions.")
+        self.pars, self.conditions, self.calculator = pars, list(conditions), calculator
+        self.filter = filter if filter is not None else RxFilter()
+
+
+# ---------------------------------------------------------------- host pre-processing (solve_utils.jl)
+def get_max_rates(conditions: ConditionSet, calculator):
+    """solve_utils.jl:19-54"""
+    static = conditions.get_static_conditions()
+    variable = [(s, p) for s, p in zip(conditions.symbols, conditions.profiles) if isvariable(p)]
+    if not variable:
+        return calculator(**static)
+    perms = []
+    for bits in itertools.product((0, 1), repeat=len(variable)):
+        kw = dict(static)
+        for (s, p), bit in zip(variable, bits):
+            kw[s] = p.maximum() if bit else p.minimum()
+        perms.append(calculator(**kw))
+    return perms[int(np.argmax([float(np.mean(p)) for p in perms]))]
+
+
+def get_initial_rates(conditions: ConditionSet, calculator):
+    """solve_utils.jl:62-73"""
+    return calculator(**conditions.get_initial_conditions())
+
+
+def calculate_discrete_rates(conditions: ConditionSet, calculator, nr):
+    """solve_utils.jl:91-109 -> (tstops, k[Nt, nr])"""
+    if not conditions.discrete_updates:
+        raise RuntimeError("Cannot calculate discrete rates for a continuous ConditionSet.")
+    tstops = conditions.get_tstops()
+    static = conditions.get_static_conditions()
+    vcs = conditions.get_variable_conditions()
+    rows = []
+    for ts in tstops:
+        kw = dict(static)
+        kw.update({s: sol(ts) for s, sol in vcs.items()})
+        rows.append(np.asarray(calculator(**kw), dtype=np.float64))
+    return tstops, np.array(rows).reshape(len(tstops), nr)
+
+
+def low_k_removal(max_rates, pars: ODESimulationParams):
+    """apply_low_k_cutoff! (solve_utils.jl:213-245) -> indices to remove (0-based)."""
+    if pars.low_k_cutoff == "none":
+        return np.zeros(0, dtype=np.int64)
+    cutoff = pars.reltol / pars.tspan[1] if pars.low_k_cutoff == "auto" else float(pars.low_k_cutoff)
+    return np.nonzero(np.asarray(max_rates) * pars.low_k_maxconc ** 2 < cutoff)[0].astype(np.int64)
+
+
+def make_u0(sd: SpeciesData, pars: ODESimulationParams):
+    """solve_utils.jl:262-297"""
+    if isinstance(pars.u0, dict):
+        u0 = np.zeros(sd.n)
+        for spec, conc in pars.u0.items():
+            if spec not in sd.toInt:
+                raise RuntimeError(f"Species {spec} not in SpeciesData. Check pars.u0 is correct.")
+            u0[sd.toInt[spec]] = conc
+        return u0
+    u0 = np.asarray(pars.u0, dtype=np.float64)
+    if len(u0) != sd.n:
+        if not pars.allow_short_u0:
+            raise RuntimeError("Length of supplied initial concentration vector does not match with number of species in system.")
+        full = np.zeros(sd.n)
+        full[:len(u0)] = u0
+        return full
+    return u0.copy()
+
+
+# ---------------------------------------------------------------- outputs (analysis/io.jl:3-48)
+@dataclass
+class Solution:
+    t: np.ndarray
+    u: List[np.ndarray]              # time-major, length-S inner vectors (res.sol.u)
+    retcode: str = "Success"
+    stats: Any = None
+
+    def __call__(self, tq):
+        U = np.array(self.u)
+        return np.array([np.interp(tq, self.t, U[:, i]) for i in range(U.shape[1])])
+
+
+@dataclass
+class ODESolveOutput:
+    sd: SpeciesData
+    rd: RxData
+    sol: Solution
+    sol_k: Any = None                # (tstops, k table) when rate constants were tabulated / requested
+    sol_vcs: Any = None
+    pars: Any = None
+    conditions: Any = None
+    umax: Optional[np.ndarray] = None   # per-species max over saved points (identify_next_seeds input)
+
+
+# ---------------------------------------------------------------- the device-backed solver
+def merge_stops(tstops, saveat, t0, tf):
+    ts = np.asarray(tstops, dtype=np.float64) if tstops is not None else np.zeros(0)
+    sv = np.asarray(saveat, dtype=np.float64)
+    ts = ts[(ts >= t0) & (ts <= tf)]
+    sv = sv[(sv >= t0) & (sv <= tf)]
+    allt = np.unique(np.concatenate([ts, sv, [tf]]))
+    flags = np.zeros(len(allt), dtype=np.int32)
+    flags[np.isin(allt, ts)] |= STOP_RATE
+    flags[np.isin(allt, sv)] |= STOP_SAVE
+    return allt, flags
+
+
+class EnsembleSolver:
+    """Network-level state on one GPU: symbolic factorisation + calculator tables, reusable
+    across solves (what the reference rebuilds through MTK on every solve_network call)."""
+
+    def __init__(self, sd: SpeciesData, rd: RxData, calculator, device=0, ordering=0):
+        self.sd, self.rd, self.calculator = sd, rd, calculator
+        self.h = _lib.Handle(device)
+        self.h.set_network(sd.n, *rd.flatten())
+        self.nnzJ, self.nnzLU, self.n_fma = self.h.symbolic(ordering)
+        self.dev = calculator.device_arrhenius() if hasattr(calculator, "device_arrhenius") else None
+        if self.dev is not None:
+            self.h.set_arrhenius(self.dev["A"], self.dev["Ea"], self.dev["n"], self.dev["k_max"], self.dev["t_mult"])
+
+    def close(self):
+        self.h.close()
+
+    def _conditions_to_device(self, conds: Sequence[ConditionSet], pars, stop_t, flags):
+        B = len(conds)
+        rate_stops = stop_t[(flags & STOP_RATE) != 0]
+        if self.dev is not None:
+            kinds = np.zeros(B, dtype=np.int32)
+            params = np.zeros((B, 16))
+            need_table = False
+            table = np.full((B, len(stop_t)), np.nan)
+            ridx = np.nonzero(flags & STOP_RATE)[0]
+            for b, cs in enumerate(conds):
+                prof = cs.get_profile("T")
+                kinds[b], params[b] = prof.device_desc()
+                if isvariable(prof) and len(ridx):
+                    # the reference reads the INTERPOLATED profile solution at each tstop
+                    # (solve_utils.jl:101-104); ship a table only where that differs from X(t)
+                    ref = np.interp(rate_stops, prof.sol.t, prof.sol.u)
+                    exact = np.array([prof.value_at(t) for t in rate_stops])
+                    if np.any(np.abs(ref - exact) > 1e-12 * np.maximum(np.abs(exact), 1.0)):
+                        need_table = True
+                    table[b, ridx] = ref
+            self.h.set_profiles(kinds, params)
+            self.h.set_T_table(table if need_table else None)
+            return None
+        # calculators without a device kernel: host table (single member / shared conditions)
+        if B != 1:
+            raise NotImplementedError("host-tabulated calculators are supported for single-member solves only")
+        cs = conds[0]
+        k_init = np.asarray(get_initial_rates(cs, self.calculator), dtype=np.float64)
+        if cs.isstatic() or len(rate_stops) == 0:
+            k_table = np.zeros((0, self.rd.nr))
+            sol_k = None
+        else:
+            ts, k_all = calculate_discrete_rates(cs, self.calculator, self.rd.nr)
+            k_table = k_all[np.isin(ts, rate_stops)]
+            sol_k = (ts, k_all)
+        self.h.set_rate_table(k_table, k_init)
+        self.h.set_T_table(None)
+        return sol_k
+
+    def prepare(self, conds: Sequence[ConditionSet], pars: ODESimulationParams, u0):
+        t0, tf = pars.tspan
+        si = pars.save_interval if pars.save_interval is not None else tf / 1000
+        saveat = create_savepoints(t0, tf, si)
+        tstops = None
+        if not conds[0].isstatic():
+            tstops = conds[0].get_tstops()
+            for cs in conds[1:]:
+                ts = cs.get_tstops()
+                if len(ts) != len(tstops) or np.any(ts != tstops):
+                    raise NotImplementedError("all ensemble members must share one tstops grid")
+        stop_t, flags = merge_stops(tstops, saveat, t0, tf)
+        self.h.set_stops(stop_t, flags)
+        sol_k = self._conditions_to_device(conds, pars, stop_t, flags)
+        self.save_t = stop_t[(flags & STOP_SAVE) != 0]
+        B = len(conds)
+        self.h.solve_prepare(B, u0, t0, pars.abstol, pars.reltol, float(np.spacing(tf)), pars.maxiters,
+                             pars.ban_negatives, len(self.save_t))
+        return sol_k
+
+    def run(self):
+        return self.h.solve_run()
+
+    def fetch(self, out_u=None, out_umax=None):
+        return self.h.solve_fetch(out_u, out_umax)
+
+
+def _solve_with_retry(solver: EnsembleSolver, conds, pars, u0):
+    """adaptive_solve! (solve_utils.jl:376-424): on failure tighten abstol/reltol x0.1 and restart
+    the whole solve, at most 5 attempts, never below eps."""
+    p = copy.copy(pars)
+    mintol = np.finfo(np.float64).eps
+    iters = 0
+    while True:
+        iters += 1
+        sol_k = solver.prepare(conds, p, u0)
+        solver.run()
+        out_u, umax, status, stats = solver.fetch()
+        if np.all(status == 0):
+            if pars.update_tols and p.abstol != pars.abstol:
+                pars.abstol, pars.reltol = p.abstol, p.reltol
+            return out_u, umax, status, stats, sol_k
+        if not pars.adaptive_tols or iters >= 5 or p.abstol / 10 <= mintol or p.reltol / 10 <= mintol:
+            raise RuntimeError("ODE solution failed.")       # ErrorException, solve_utils.jl:405-411
+        p.abstol /= 10
+        p.reltol /= 10
+
+
+def solve_network(method: AbstractODESolveMethod, sd: SpeciesData, rd: RxData, copy_network=True,
+                  device=0, solver: Optional[EnsembleSolver] = None):
+    """methods.jl:105-130 (static) / :330-360 (variable) + the new ensemble method.
+    Returns an `ODESolveOutput` (a list of them for `B200EnsembleODESolve`)."""
+    if copy_network:
+        sd, rd = copy.deepcopy(sd), copy.deepcopy(rd)
+    pars, calc = method.pars, method.calculator
+    ensemble = isinstance(method, B200EnsembleODESolve)
+    conds = method.conditions if ensemble else [method.conditions]
+    if copy_network:
+        calc = copy.deepcopy(calc)
+    if isinstance(method, VariableODESolve) and not method.conditions.discrete_updates:
+        raise NotImplementedError("continuous rate updates (methods.jl:363-653) are not on the B200 path yet; "
+                                  "pass ts_update to ConditionSet for discrete updates")
+    for cs in conds:
+        cs.solve_variable_conditions(pars)
+    mask = get_filter_mask(method.filter, sd, rd)
+    rids = np.nonzero(mask)[0]
+    rd.splice(rids)
+    if len(rids):
+        calc.splice(rids)
+    calc.setup_network(sd, rd)
+    # low-k pruning with ensemble-wide maximum rates (identical to the reference for one member)
+    if pars.low_k_cutoff != "none":
+        mr = None
+        for cs in conds:
+            r = np.asarray(get_max_rates(cs, calc))
+            mr = r if mr is None else np.maximum(mr, r)
+        low = low_k_removal(mr, pars)
+        rd.splice(low)
+        if len(low):
+            calc.splice(low)
+    u0 = make_u0(sd, pars)
+    own = solver is None
+    if own:
+        solver = EnsembleSolver(sd, rd, calc, device=device)
+    try:
+        out_u, umax, status, stats, sol_k = _solve_with_retry(solver, conds, pars, u0)
+        save_t = solver.save_t
+    finally:
+        if own:
+            solver.close()
+    outs = []
+    for b, cs in enumerate(conds):
+        sol = Solution(t=save_t.copy(), u=[out_u[s, :, b].copy() for s in range(out_u.shape[0])],
+                       retcode=RETCODES.get(int(status[b]), "Failure"), stats=stats[b].copy())
+        outs.append(ODESolveOutput(sd=sd, rd=rd, sol=sol, sol_k=sol_k, pars=pars, conditions=cs,
+                                   umax=umax[:, b].copy()))
+    return outs if ensemble else outs[0]
