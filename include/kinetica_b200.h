@@ -91,6 +91,11 @@ int32_t kb2_set_T_table(kb2_handle h, int64_t B, int64_t nstops, const double *T
 /* merged stop list shared by all members: sorted, last entry = tspan[2]
  * (get_tstops condition_set.jl:172-176, tstops kwarg methods.jl:697, saveat :166) */
 int32_t kb2_set_stops(kb2_handle h, int64_t nstops, const double *stop_t, const int32_t *flags);
+/* per-member stop lists (members whose ConditionSets have different tstops):
+ * stop_t[b*nstops_max + s], flags likewise, counts[b] valid entries per member; every member must
+ * carry the same save points */
+int32_t kb2_set_member_stops(kb2_handle h, int64_t B, int64_t nstops_max, const int32_t *counts,
+                             const double *stop_t, const int32_t *flags);
 
 /* ---- the solve: replaces init/solve!/adaptive_solve! (methods.jl:174-180, 705-711,
  * solve_utils.jl:376-424) for B members at once.

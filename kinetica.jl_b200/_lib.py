@@ -34,6 +34,7 @@ SIGNATURES = {
     "kb2_set_profiles": (_i32, [_H, _i64, _pi32, _pf64]),
     "kb2_set_T_table": (_i32, [_H, _i64, _i64, _pf64]),
     "kb2_set_stops": (_i32, [_H, _i64, _pf64, _pi32]),
+    "kb2_set_member_stops": (_i32, [_H, _i64, _i64, _pi32, _pf64, _pi32]),
     "kb2_solve": (_i32, [_H, _i64, _pf64, _i64, _f64, _f64, _f64, _f64, _i64, _i32, _i64, _pf64, _pf64, _pi32, _pi64]),
     "kb2_solve_prepare": (_i32, [_H, _i64, _pf64, _i64, _f64, _f64, _f64, _f64, _i64, _i32, _i64]),
     "kb2_solve_run": (_i32, [_H, C.POINTER(C.c_float)]),
@@ -180,6 +181,14 @@ class Handle:
         st = _c64(stop_t)
         fl = np.ascontiguousarray(flags, dtype=np.int32)
         self._ck(self._lib.kb2_set_stops(self._h, len(st), _f(st), fl.ctypes.data_as(_pi32)))
+
+    def set_member_stops(self, counts, stop_t, flags):
+        cnt = np.ascontiguousarray(counts, dtype=np.int32)
+        st = _c64(stop_t)
+        fl = np.ascontiguousarray(flags, dtype=np.int32)
+        assert st.shape == fl.shape == (len(cnt), st.shape[1])
+        self._ck(self._lib.kb2_set_member_stops(self._h, st.shape[0], st.shape[1], cnt.ctypes.data_as(_pi32),
+                                                _f(st), fl.ctypes.data_as(_pi32)))
 
     def set_tiling(self, members_per_tile=0, threads_per_cta=0):
         self._ck(self._lib.kb2_set_tiling(self._h, members_per_tile, threads_per_cta))

@@ -89,6 +89,9 @@ class AbstractVariableProfile(AbstractConditionProfile):
     def value_at(self, t):
         raise NotImplementedError
 
+    def values_at(self, ts):
+        return np.array([self.value_at(float(t)) for t in ts])
+
     def solve(self, pars, reset=False):
         """solve_variable_condition! (direct_variable.jl:34-43, gradient_variable.jl:35-64):
         tabulates the profile on the save grid (∪ tstops for gradient profiles)."""
@@ -99,7 +102,7 @@ class AbstractVariableProfile(AbstractConditionProfile):
         if isinstance(self, AbstractGradientProfile):
             ts = np.asarray(self.tstops, dtype=np.float64)
             t = np.sort(np.concatenate([t, ts[(ts >= pars.tspan[0]) & (ts <= pars.tspan[1])]]))
-        self.sol = _Sol(t, [self.value_at(x) for x in t])
+        self.sol = _Sol(t, self.values_at(t))
 
     def minimum(self):
         if self.sol is None:
@@ -157,6 +160,10 @@ class LinearDirectProfile(AbstractDirectProfile):
         if t <= p.t_end:
             return p.X_start + p.rate * t
         return p.X_end
+
+    def values_at(self, ts):
+        ts = np.asarray(ts, dtype=np.float64)
+        return np.where(ts <= 0.0, self.X_start, np.where(ts <= self.t_end, self.X_start + self.rate * ts, self.X_end))
 
     def create_discrete_tstops(self, ts_update):
         self._check_ts(ts_update)

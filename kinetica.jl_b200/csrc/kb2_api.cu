@@ -35,8 +35,8 @@ struct kb2_ctx {
     // conditions (host copies)
     std::vector<int32_t> pkind;
     std::vector<double> pparams, Ttab, stop_t;
-    std::vector<int32_t> stop_flags;
-    int64_t Bprof = 0, Btab = 0;
+    std::vector<int32_t> stop_flags, stop_cnt;     // stop_cnt empty = one list shared by all members
+    int64_t Bprof = 0, Btab = 0, ns_row = 0, Bstops = 0;
     // device
     std::vector<void *> net_allocs, ens_allocs;
     DevNet dn{};
@@ -307,6 +307,26 @@ extern "C" int32_t kb2_set_stops(kb2_handle h, int64_t nstops, const double *sto
     for (int64_t s = 1; s < nstops; ++s) if (!(stop_t[s] > stop_t[s - 1])) FAIL(h, "stops must be strictly increasing");
     h->stop_t.assign(stop_t, stop_t + nstops);
     h->stop_flags.assign(flags, flags + nstops);
+    h->stop_cnt.clear();
+    h->ns_row = nstops; h->Bstops = 0;
+    h->prepared = false;
+    return 0;
+}
+
+extern "C" int32_t kb2_set_member_stops(kb2_handle h, int64_t B, int64_t nstops_max, const int32_t *counts,
+                                        const double *stop_t, const int32_t *flags)
+{
+    if (!h) return 1;
+    if (B <= 0 || nstops_max <= 0) FAIL(h, "need at least one member and one stop");
+    for (int64_t b = 0; b < B; ++b) {
+        if (counts[b] <= 0 || counts[b] > nstops_max) FAIL(h, "bad per-member stop count");
+        for (int64_t s = 1; s < counts[b]; ++s)
+            if (!(stop_t[b * nstops_max + s] > stop_t[b * nstops_max + s - 1])) FAIL(h, "stops must be strictly increasing");
+    }
+    h->stop_t.assign(stop_t, stop_t + B * nstops_max);
+    h->stop_flags.assign(flags, flags + B * nstops_max);
+    h->stop_cnt.assign(counts, counts + B);
+    h->ns_row = nstops_max; h->Bstops = B;
     h->prepared = false;
     return 0;
 }
@@ -590,19 +610,41 @@ extern "C" int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, 
     if (h->calc_mode < 0) FAIL(h, "no calculator set");
     if (h->stop_t.empty()) FAIL(h, "no stops set");
     if (h->calc_mode == 0 && h->Bprof != B) FAIL(h, "kb2_set_profiles must be called with the same B");
-    if (!h->Ttab.empty() && (h->Btab != B || (int64_t)h->Ttab.size() != B * (int64_t)h->stop_t.size()))
+    const int64_t nstops = h->ns_row;
+    const bool shared = h->stop_cnt.empty();
+    if (!shared && h->Bstops != B) FAIL(h, "kb2_set_member_stops was called with a different B");
+    if (!h->Ttab.empty() && (h->Btab != B || (int64_t)h->Ttab.size() != B * nstops))
         FAIL(h, "T table does not match B x nstops");
     if (!(abstol > 0) || !(reltol > 0)) FAIL(h, "tolerances must be positive");
-    const int64_t nstops = (int64_t)h->stop_t.size();
-    int64_t nsave = 0, nrate = 0;
-    std::vector<int32_t> ridx(nstops, -1);
-    for (int64_t s = 0; s < nstops; ++s) {
-        if (h->stop_t[s] < t0) FAIL(h, "stops must not precede t0");
-        if (h->stop_flags[s] & KB2_STOP_SAVE) ++nsave;
-        if (h->stop_flags[s] & KB2_STOP_RATE) ridx[s] = (int32_t)nrate++;
+    const int64_t Bp64 = (B + 31) / 32 * 32;
+    // expand to per-member tables [b][nstops]
+    std::vector<double> st((size_t)(Bp64 * nstops), 0.0);
+    std::vector<int32_t> sf((size_t)(Bp64 * nstops), 0), ridx((size_t)(Bp64 * nstops), -1), cnt((size_t)Bp64, 0);
+    for (int64_t b = 0; b < B; ++b) {
+        const double *ts = shared ? h->stop_t.data() : h->stop_t.data() + b * nstops;
+        const int32_t *fl = shared ? h->stop_flags.data() : h->stop_flags.data() + b * nstops;
+        const int64_t n = shared ? nstops : h->stop_cnt[b];
+        int64_t nsave = 0, nrate = 0;
+        for (int64_t s = 0; s < n; ++s) {
+            if (ts[s] < t0) FAIL(h, "stops must not precede t0");
+            st[b * nstops + s] = ts[s];
+            sf[b * nstops + s] = fl[s];
+            if (fl[s] & KB2_STOP_SAVE) ++nsave;
+            if (fl[s] & KB2_STOP_RATE) ridx[b * nstops + s] = (int32_t)nrate++;
+        }
+        cnt[b] = (int32_t)n;
+        if (nsave != Ns) FAIL(h, "Ns does not match the number of save stops");
+        if (h->calc_mode == 1 && nrate != h->n_rate_stops) FAIL(h, "rate table length does not match the rate-update stops");
+        if (shared && b == 0 && B > 1) {       // replicate member 0
+            for (int64_t bb = 1; bb < B; ++bb) {
+                std::copy(st.begin(), st.begin() + nstops, st.begin() + bb * nstops);
+                std::copy(sf.begin(), sf.begin() + nstops, sf.begin() + bb * nstops);
+                std::copy(ridx.begin(), ridx.begin() + nstops, ridx.begin() + bb * nstops);
+                cnt[bb] = cnt[0];
+            }
+            break;
+        }
     }
-    if (nsave != Ns) FAIL(h, "Ns does not match the number of save stops");
-    if (h->calc_mode == 1 && nrate != h->n_rate_stops) FAIL(h, "rate table length does not match the rate-update stops");
     int rc = ensure_ensemble(h, B, Ns);
     if (rc) return rc;
     DevEns &e = h->de;
@@ -626,9 +668,10 @@ extern "C" int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, 
     }
     rc |= dev_upload(h, P, kind.data(), kind.size(), &e.pkind);
     rc |= dev_upload(h, P, par.data(), par.size(), &e.pparams);
-    rc |= dev_upload(h, P, h->stop_t.data(), (size_t)nstops, &e.stop_t);
-    rc |= dev_upload(h, P, h->stop_flags.data(), (size_t)nstops, &e.stop_flags);
-    rc |= dev_upload(h, P, ridx.data(), (size_t)nstops, &e.stop_ridx);
+    rc |= dev_upload(h, P, st.data(), st.size(), &e.stop_t);
+    rc |= dev_upload(h, P, sf.data(), sf.size(), &e.stop_flags);
+    rc |= dev_upload(h, P, ridx.data(), ridx.size(), &e.stop_ridx);
+    rc |= dev_upload(h, P, cnt.data(), cnt.size(), &e.stop_cnt);
     e.Ttab = nullptr;
     if (!h->Ttab.empty()) {
         std::vector<double> tp(Bp * nstops, NAN);

@@ -56,9 +56,9 @@ struct DevEns {
     int B, Bp;
     double *u, *ua, *rv, *y, *K[6], *k, *lu, *invd;
     // conditions
-    int nstops;
-    const double *stop_t;
-    const int *stop_flags, *stop_ridx;
+    int nstops;               // row length of the per-member stop tables
+    const double *stop_t;     // [b*nstops + s]
+    const int *stop_flags, *stop_ridx, *stop_cnt;   // [b*nstops + s], [b*nstops + s], [b]
     const double *Ttab;       // [b*nstops + s] or null
     const int *pkind;
     const double *pparams;    // [b*16]
@@ -272,14 +272,25 @@ __device__ void tile_lu(const Tile<MB> &tl, const DevNet &net, double *__restric
     }
 }
 
-// sum over the slots of one member, fixed order (deterministic); red has nslot*MB doubles
+// sum over the slots of one member in a fixed order (deterministic): shuffle tree across the
+// sub-lanes of each warp, then one pass over the per-warp partials; red has (nthreads/32)*MB doubles
+template <int MB>
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int off = 16; off >= MB; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
 template <int MB>
 __device__ __forceinline__ double tile_sum(const Tile<MB> &tl, double v, double *red)
 {
-    red[tl.slot * MB + tl.m] = v;
+    v = warp_sum<MB>(v);
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if ((threadIdx.x & 31) < MB) red[warp * MB + tl.m] = v;
     __syncthreads();
     double s = 0.0;
-    for (int q = 0; q < tl.nslot; ++q) s += red[q * MB + tl.m];
+    for (int q = 0; q < nw; ++q) s += red[q * MB + tl.m];
     __syncthreads();
     return s;
 }
@@ -290,33 +301,57 @@ __device__ void tile_trisolve(const Tile<MB> &tl, const DevNet &net, const doubl
                               const double *__restrict__ invd, const double *__restrict__ rhs,
                               double *__restrict__ y, double *__restrict__ x, double *red)
 {
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const bool wlead = (threadIdx.x & 31) < MB;
+    // rows without an L part depend on nothing: do them all at once
+    for (int i = threadIdx.x / MB; i < net.S; i += tl.nslot)
+        if (net.diagpos[i] == net.rowptr[i]) y[(size_t)i * tl.Bp + tl.b] = rhs[(size_t)net.perm[i] * tl.Bp + tl.b];
+    __syncthreads();
     for (int i = 0; i < net.S; ++i) {
         const int r0 = net.rowptr[i], dg = net.diagpos[i];
-        double part = 0.0;
-        for (int p = r0 + tl.slot; p < dg; p += tl.nslot)
-            part += lu[(size_t)p * tl.Bp + tl.b] * y[(size_t)net.colidx[p] * tl.Bp + tl.b];
         if (dg - r0 > 0) {
-            const double s = tile_sum(tl, part, red);
-            if (tl.slot == 0) y[(size_t)i * tl.Bp + tl.b] = rhs[(size_t)net.perm[i] * tl.Bp + tl.b] - s;
+            double part = 0.0;
+            for (int p = r0 + tl.slot; p < dg; p += tl.nslot)
+                part += lu[(size_t)p * tl.Bp + tl.b] * y[(size_t)net.colidx[p] * tl.Bp + tl.b];
+            part = warp_sum<MB>(part);
+            if (wlead) red[warp * MB + tl.m] = part;
             __syncthreads();
-        } else {
-            if (tl.slot == 0) y[(size_t)i * tl.Bp + tl.b] = rhs[(size_t)net.perm[i] * tl.Bp + tl.b];
+            if (tl.slot == 0) {
+                double s = 0.0;
+                for (int q = 0; q < nw; ++q) s += red[q * MB + tl.m];
+                y[(size_t)i * tl.Bp + tl.b] = rhs[(size_t)net.perm[i] * tl.Bp + tl.b] - s;
+            }
             __syncthreads();
         }
     }
-    for (int i = net.S - 1; i >= 0; --i) {
-        const int dg = net.diagpos[i], r1 = net.rowptr[i + 1];
-        double part = 0.0;
-        for (int p = dg + 1 + tl.slot; p < r1; p += tl.nslot)
-            part += lu[(size_t)p * tl.Bp + tl.b] * y[(size_t)net.colidx[p] * tl.Bp + tl.b];
-        const double s = (r1 - dg - 1 > 0) ? tile_sum(tl, part, red) : 0.0;
-        if (tl.slot == 0) {
-            const double v = (y[(size_t)i * tl.Bp + tl.b] - s) * invd[(size_t)i * tl.Bp + tl.b];
+    // rows without a U part (beyond the diagonal) only need scaling
+    for (int i = threadIdx.x / MB; i < net.S; i += tl.nslot)
+        if (net.rowptr[i + 1] - net.diagpos[i] == 1) {
+            const double v = y[(size_t)i * tl.Bp + tl.b] * invd[(size_t)i * tl.Bp + tl.b];
             y[(size_t)i * tl.Bp + tl.b] = v;
             x[(size_t)net.perm[i] * tl.Bp + tl.b] = v;
         }
-        __syncthreads();
+    __syncthreads();
+    for (int i = net.S - 1; i >= 0; --i) {
+        const int dg = net.diagpos[i], r1 = net.rowptr[i + 1];
+        if (r1 - dg - 1 > 0) {
+            double part = 0.0;
+            for (int p = dg + 1 + tl.slot; p < r1; p += tl.nslot)
+                part += lu[(size_t)p * tl.Bp + tl.b] * y[(size_t)net.colidx[p] * tl.Bp + tl.b];
+            part = warp_sum<MB>(part);
+            if (wlead) red[warp * MB + tl.m] = part;
+            __syncthreads();
+            if (tl.slot == 0) {
+                double s = 0.0;
+                for (int q = 0; q < nw; ++q) s += red[q * MB + tl.m];
+                const double v = (y[(size_t)i * tl.Bp + tl.b] - s) * invd[(size_t)i * tl.Bp + tl.b];
+                y[(size_t)i * tl.Bp + tl.b] = v;
+                x[(size_t)net.perm[i] * tl.Bp + tl.b] = v;
+            }
+            __syncthreads();
+        }
     }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -408,7 +443,7 @@ template <int MB>
 struct Ctl {
     double t[MB], h[MB], hs[MB], hold[MB], errold[MB], T[MB];
     long long iters[MB];
-    int si[MB], isave[MB], status[MB], hit[MB], active[MB], rejlast[MB], firstacc[MB], accept[MB], upd[MB], ridx[MB], sav[MB];
+    int ns[MB], si[MB], isave[MB], status[MB], hit[MB], active[MB], rejlast[MB], firstacc[MB], accept[MB], upd[MB], ridx[MB], sav[MB];
     int nacc[MB], nrej[MB], nlu[MB], nrhs[MB];
 };
 
@@ -421,18 +456,19 @@ __device__ void tile_process_stop(const Tile<MB> &tl, const DevNet &net, const D
     if (tl.slot == 0) {
         const int m = tl.m;
         c.upd[m] = 0; c.sav[m] = -1;
-        const bool due = at_start ? (c.status[m] == ST_RUNNING && c.si[m] < en.nstops && en.stop_t[c.si[m]] <= en.t0)
+        const size_t sb = (size_t)tl.b * en.nstops;
+        const bool due = at_start ? (c.status[m] == ST_RUNNING && c.si[m] < c.ns[m] && en.stop_t[sb + c.si[m]] <= en.t0)
                                   : (c.accept[m] && c.hit[m]);
         if (due) {
-            const int s = c.si[m], fl = en.stop_flags[s];
+            const int s = c.si[m], fl = en.stop_flags[sb + s];
             if (fl & 1) {
-                double T = en.Ttab ? en.Ttab[(size_t)tl.b * en.nstops + s] : nan("");
-                if (isnan(T) && net.calc_mode == 0) T = profile_eval(en.pkind[tl.b], en.pparams + (size_t)tl.b * 16, en.stop_t[s]);
-                c.T[m] = T; c.upd[m] = 1; c.ridx[m] = en.stop_ridx[s];
+                double T = en.Ttab ? en.Ttab[sb + s] : nan("");
+                if (isnan(T) && net.calc_mode == 0) T = profile_eval(en.pkind[tl.b], en.pparams + (size_t)tl.b * 16, en.stop_t[sb + s]);
+                c.T[m] = T; c.upd[m] = 1; c.ridx[m] = en.stop_ridx[sb + s];
             }
             if (fl & 2) c.sav[m] = c.isave[m]++;
             c.si[m] = s + 1;
-            if (c.si[m] >= en.nstops) c.status[m] = 0;   // reached the end of tspan
+            if (c.si[m] >= c.ns[m]) c.status[m] = 0;   // reached the end of tspan
         }
     }
     __syncthreads();
@@ -451,6 +487,47 @@ __device__ void tile_process_stop(const Tile<MB> &tl, const DevNet &net, const D
     __syncthreads();
 }
 
+// Starting step size (Hairer-Nørsett-Wanner II.4, order 4).  Called once at t0 (`initial`) and
+// again after every discrete rate update, where the RHS jumps: members flagged in c.upd get
+// h = min(h, estimate).  Uses rv, ua, y as scratch.
+template <int MB>
+__device__ void tile_hinit(const Tile<MB> &tl, const DevNet &net, const DevEns &en, Ctl<MB> &c, double *red, bool initial)
+{
+    const int m = tl.m, b = tl.b;
+    const size_t Bp = tl.Bp;
+    tile_rhs(tl, net, en.u, en.k, en.rv, 0, nullptr, nullptr);
+    __syncthreads();
+    double d0 = 0, d1 = 0;
+    for (int i = tl.slot; i < net.S; i += tl.nslot) {
+        const double ui = en.u[(size_t)i * Bp + b], fi = en.rv[(size_t)i * Bp + b];
+        const double sc = en.abstol + en.reltol * fabs(ui);
+        d0 += (ui / sc) * (ui / sc); d1 += (fi / sc) * (fi / sc);
+    }
+    d0 = sqrt(tile_sum(tl, d0, red) / net.S);
+    d1 = sqrt(tile_sum(tl, d1, red) / net.S);
+    const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    for (int i = tl.slot; i < net.S; i += tl.nslot)
+        en.ua[(size_t)i * Bp + b] = en.u[(size_t)i * Bp + b] + h0 * en.rv[(size_t)i * Bp + b];
+    __syncthreads();
+    tile_rhs(tl, net, en.ua, en.k, en.y, 0, nullptr, nullptr);
+    __syncthreads();
+    double d2 = 0;
+    for (int i = tl.slot; i < net.S; i += tl.nslot) {
+        const double sc = en.abstol + en.reltol * fabs(en.u[(size_t)i * Bp + b]);
+        const double q = (en.y[(size_t)i * Bp + b] - en.rv[(size_t)i * Bp + b]) / sc;
+        d2 += q * q;
+    }
+    d2 = sqrt(tile_sum(tl, d2, red) / net.S) / h0;
+    const double dm = fmax(d1, d2);
+    const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
+    const double hn = fmin(100.0 * h0, h1);
+    if (tl.slot == 0) {
+        if (initial) { c.h[m] = hn; c.hold[m] = hn; c.nrhs[m] += 2; }
+        else if (c.upd[m] && c.status[m] == ST_RUNNING) { c.h[m] = fmin(c.h[m], hn); c.nrhs[m] += 2; }
+    }
+    __syncthreads();
+}
+
 template <int MB>
 __device__ void solve_tile(int tile, const DevNet &net, const DevEns &en, Ctl<MB> &c, double *w, double *red)
 {
@@ -460,7 +537,8 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevEns &en, Ctl<MB
     const int b = tl.b;
     if (tl.slot == 0) {
         c.t[m] = en.t0; c.si[m] = 0; c.isave[m] = 0; c.iters[m] = 0;
-        c.status[m] = (b < en.B && en.nstops > 0) ? ST_RUNNING : 0;
+        c.ns[m] = en.stop_cnt[b];
+        c.status[m] = (b < en.B && c.ns[m] > 0) ? ST_RUNNING : 0;
         c.nacc[m] = c.nrej[m] = c.nlu[m] = c.nrhs[m] = 0;
         c.rejlast[m] = 0; c.firstacc[m] = 1; c.accept[m] = 0; c.hit[m] = 0;
         c.errold[m] = 1.0;
@@ -472,36 +550,7 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevEns &en, Ctl<MB
     tile_rates(tl, net, en.k, c.T[m], true, -1);     // k(initial conditions), methods.jl:668
     __syncthreads();
     tile_process_stop(tl, net, en, c, true);
-    // ---- starting step size (Hairer-Nørsett-Wanner II.4) ----
-    {
-        tile_rhs(tl, net, en.u, en.k, en.rv, 0, nullptr, nullptr);
-        __syncthreads();
-        double d0 = 0, d1 = 0;
-        for (int i = tl.slot; i < net.S; i += tl.nslot) {
-            const double ui = en.u[(size_t)i * Bp + b], fi = en.rv[(size_t)i * Bp + b];
-            const double sc = en.abstol + en.reltol * fabs(ui);
-            d0 += (ui / sc) * (ui / sc); d1 += (fi / sc) * (fi / sc);
-        }
-        d0 = sqrt(tile_sum(tl, d0, red) / net.S);
-        d1 = sqrt(tile_sum(tl, d1, red) / net.S);
-        const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        for (int i = tl.slot; i < net.S; i += tl.nslot)
-            en.ua[(size_t)i * Bp + b] = en.u[(size_t)i * Bp + b] + h0 * en.rv[(size_t)i * Bp + b];
-        __syncthreads();
-        tile_rhs(tl, net, en.ua, en.k, en.y, 0, nullptr, nullptr);
-        __syncthreads();
-        double d2 = 0;
-        for (int i = tl.slot; i < net.S; i += tl.nslot) {
-            const double sc = en.abstol + en.reltol * fabs(en.u[(size_t)i * Bp + b]);
-            const double q = (en.y[(size_t)i * Bp + b] - en.rv[(size_t)i * Bp + b]) / sc;
-            d2 += q * q;
-        }
-        d2 = sqrt(tile_sum(tl, d2, red) / net.S) / h0;
-        const double dm = fmax(d1, d2);
-        const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
-        if (tl.slot == 0) { c.h[m] = fmin(100.0 * h0, h1); c.hold[m] = c.h[m]; c.nrhs[m] += 2; }
-        __syncthreads();
-    }
+    tile_hinit(tl, net, en, c, red, true);
     // ---- main loop ----
     for (;;) {
         if (tl.slot == 0) {
@@ -511,7 +560,7 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevEns &en, Ctl<MB
             if (act) {
                 if (++c.iters[m] > en.maxiters) { c.status[m] = 1; act = 0; }
                 else {
-                    const double tstop = en.stop_t[c.si[m]];
+                    const double tstop = en.stop_t[(size_t)b * en.nstops + c.si[m]];
                     hs = c.h[m];
                     if (c.t[m] + 1.01 * hs >= tstop) { hs = tstop - c.t[m]; hit = 1; }
                     if (hs < en.dtmin && !hit) { c.status[m] = 2; act = 0; hs = 1.0; }
@@ -576,7 +625,7 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevEns &en, Ctl<MB
                 if (c.rejlast[m]) hnew = fmin(hnew, hs);
                 c.rejlast[m] = 0;
                 c.accept[m] = 1;
-                if (c.hit[m]) { c.t[m] = en.stop_t[c.si[m]]; c.h[m] = fmax(hnew, c.h[m]); }
+                if (c.hit[m]) { c.t[m] = en.stop_t[(size_t)b * en.nstops + c.si[m]]; c.h[m] = fmax(hnew, c.h[m]); }
                 else { c.t[m] += hs; c.h[m] = hnew; }
             } else {
                 c.nrej[m]++; c.rejlast[m] = 1; c.h[m] = hnew;
@@ -591,6 +640,7 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevEns &en, Ctl<MB
             }
         __syncthreads();
         tile_process_stop(tl, net, en, c, false);
+        if (__syncthreads_or(c.upd[m])) tile_hinit(tl, net, en, c, red, false);
     }
     if (tl.slot == 0 && b < en.B) {
         en.status[b] = c.status[m] == ST_RUNNING ? 5 : c.status[m];

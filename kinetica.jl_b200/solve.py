@@ -201,33 +201,41 @@ class EnsembleSolver:
     def close(self):
         self.h.close()
 
-    def _conditions_to_device(self, conds: Sequence[ConditionSet], pars, stop_t, flags):
+    def _conditions_to_device(self, conds: Sequence[ConditionSet], stop_t, flags):
+        """stop_t/flags: [B, ns] per-member tables (or [ns] shared)."""
         B = len(conds)
-        rate_stops = stop_t[(flags & STOP_RATE) != 0]
+        shared = stop_t.ndim == 1
         if self.dev is not None:
             kinds = np.zeros(B, dtype=np.int32)
             params = np.zeros((B, 16))
             need_table = False
-            table = np.full((B, len(stop_t)), np.nan)
-            ridx = np.nonzero(flags & STOP_RATE)[0]
+            ns = stop_t.shape[-1]
+            table = np.full((B, ns), np.nan)
             for b, cs in enumerate(conds):
                 prof = cs.get_profile("T")
                 kinds[b], params[b] = prof.device_desc()
-                if isvariable(prof) and len(ridx):
+                if isvariable(prof):
+                    st = stop_t if shared else stop_t[b]
+                    ridx = np.nonzero((flags if shared else flags[b]) & STOP_RATE)[0]
+                    if len(ridx) == 0:
+                        continue
                     # the reference reads the INTERPOLATED profile solution at each tstop
                     # (solve_utils.jl:101-104); ship a table only where that differs from X(t)
-                    ref = np.interp(rate_stops, prof.sol.t, prof.sol.u)
-                    exact = np.array([prof.value_at(t) for t in rate_stops])
+                    ref = np.interp(st[ridx], prof.sol.t, prof.sol.u)
+                    exact = prof.values_at(st[ridx])
                     if np.any(np.abs(ref - exact) > 1e-12 * np.maximum(np.abs(exact), 1.0)):
                         need_table = True
                     table[b, ridx] = ref
             self.h.set_profiles(kinds, params)
             self.h.set_T_table(table if need_table else None)
             return None
-        # calculators without a device kernel: host table (single member / shared conditions)
+        # calculators without a device kernel: host table (single member)
         if B != 1:
             raise NotImplementedError("host-tabulated calculators are supported for single-member solves only")
         cs = conds[0]
+        st = stop_t if shared else stop_t[0]
+        fl = flags if shared else flags[0]
+        rate_stops = st[(fl & STOP_RATE) != 0]
         k_init = np.asarray(get_initial_rates(cs, self.calculator), dtype=np.float64)
         if cs.isstatic() or len(rate_stops) == 0:
             k_table = np.zeros((0, self.rd.nr))
@@ -244,18 +252,38 @@ class EnsembleSolver:
         t0, tf = pars.tspan
         si = pars.save_interval if pars.save_interval is not None else tf / 1000
         saveat = create_savepoints(t0, tf, si)
-        tstops = None
-        if not conds[0].isstatic():
-            tstops = conds[0].get_tstops()
+        B = len(conds)
+        if conds[0].isstatic():
+            tstops0, same = None, all(cs.isstatic() for cs in conds)
+            if not same:
+                raise ValueError("static and variable ConditionSets cannot be mixed in one ensemble")
+        else:
+            tstops0 = conds[0].get_tstops()
+            same = True
             for cs in conds[1:]:
                 ts = cs.get_tstops()
-                if len(ts) != len(tstops) or np.any(ts != tstops):
-                    raise NotImplementedError("all ensemble members must share one tstops grid")
-        stop_t, flags = merge_stops(tstops, saveat, t0, tf)
-        self.h.set_stops(stop_t, flags)
-        sol_k = self._conditions_to_device(conds, pars, stop_t, flags)
-        self.save_t = stop_t[(flags & STOP_SAVE) != 0]
-        B = len(conds)
+                if len(ts) != len(tstops0) or np.any(ts != tstops0):
+                    same = False
+                    break
+        if same:
+            stop_t, flags = merge_stops(tstops0, saveat, t0, tf)
+            self.h.set_stops(stop_t, flags)
+            self.save_t = stop_t[(flags & STOP_SAVE) != 0]
+        else:
+            # members with their own tstops grids (e.g. t_end differing in the last bit)
+            lists = [merge_stops(cs.get_tstops(), saveat, t0, tf) for cs in conds]
+            nmax = max(len(t) for t, _ in lists)
+            stop_t = np.zeros((B, nmax))
+            flags = np.zeros((B, nmax), dtype=np.int32)
+            counts = np.zeros(B, dtype=np.int32)
+            for b, (t, f) in enumerate(lists):
+                counts[b] = len(t)
+                stop_t[b, :len(t)] = t
+                stop_t[b, len(t):] = np.inf
+                flags[b, :len(t)] = f
+            self.h.set_member_stops(counts, np.where(np.isfinite(stop_t), stop_t, 0.0), flags)
+            self.save_t = lists[0][0][(lists[0][1] & STOP_SAVE) != 0]
+        sol_k = self._conditions_to_device(conds, stop_t, flags)
         self.h.solve_prepare(B, u0, t0, pars.abstol, pars.reltol, float(np.spacing(tf)), pars.maxiters,
                              pars.ban_negatives, len(self.save_t))
         return sol_k

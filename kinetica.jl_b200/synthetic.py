@@ -18,6 +18,14 @@ from .network import RxData, SpeciesData
 N_A = 6.02214076e23  # reference src/constants.jl:5
 
 SEED_BASE = 20261018
+# Rate-parameter ranges of the synthetic CRNs.  SURVEY.md §8(d) proposed the shipped fixture's
+# ranges (log10 A in 8.7..12.3, Ea up to 4e5 J/mol, 25 % barrierless); with abundant species at
+# 0.1 mol/dm3 that gives opposing fluxes of ~1e10 mol/dm3/s whose FP64 cancellation noise
+# (~1e-6 /s) sits above abstol = 1e-10 and pins ANY integrator at h ~ 1e-5 (measured with the CPU
+# oracle: > 1e5 steps per member).  The ranges below keep the network stiff (rate constants span
+# ~1e-11..1e7, fastest time scale ~1e-6 s over a 1 s horizon) but well conditioned in FP64.
+LOG10_A = (3.0, 7.0)
+EA_MAX = 2.0e5
 
 
 def synthetic_crn(S: int, R: int, seed: int, w: float = 16.0, n_hubs: int = 8,
@@ -90,14 +98,14 @@ def synthetic_crn(S: int, R: int, seed: int, w: float = 16.0, n_hubs: int = 8,
         i, n = compress(reac)
         id_prods.append(i); st_prods.append(n)
 
-    Ea_f = rng.uniform(0.0, 4.0e5, nf)
-    Ea_r = rng.uniform(0.0, 4.0e5, nf)
+    Ea_f = rng.uniform(0.0, EA_MAX, nf)
+    Ea_r = rng.uniform(0.0, EA_MAX, nf)
     zero_sel = rng.random(nf) < 0.5        # half the pairs get one barrierless direction => 25 % zeros
     zero_dir = rng.random(nf) < 0.5
     Ea_f[zero_sel & zero_dir] = 0.0
     Ea_r[zero_sel & ~zero_dir] = 0.0
     Ea = np.concatenate([Ea_f, Ea_r])
-    A = 10.0 ** rng.uniform(8.7, 12.3, R) / N_A
+    A = 10.0 ** rng.uniform(LOG10_A[0], LOG10_A[1], R) / N_A
 
     sd = SpeciesData([f"S{i}" for i in range(S)])
     rd = RxData(id_reacs, id_prods, st_reacs, st_prods)

@@ -94,10 +94,16 @@ static void net_build(net_t *n)
 }
 static void net_free(net_t *n) { free(n->np_); free(n->ni); free(n->nn); }
 
+/* neg_guard: rate laws are evaluated on max(u, 0) — the Lipschitz extension of mass action outside
+ * the non-negative orthant used by the B200 solver (identical wherever the true solution lives). */
+static int g_neg_guard = 0;
+void ko_set_neg_guard(int on) { g_neg_guard = on; }
+static inline double gu(double x) { return (g_neg_guard && x < 0.0) ? 0.0 : x; }
+
 static double rate_of(const net_t *n, int64_t j, const double *u, const double *k)
 {
     double r = k[j];
-    for (int64_t e = n->rp[j]; e < n->rp[j + 1]; ++e) r *= ipow(u[n->ri[e]], n->rn[e]);
+    for (int64_t e = n->rp[j]; e < n->rp[j + 1]; ++e) r *= ipow(gu(u[n->ri[e]]), n->rn[e]);
     return r;
 }
 
@@ -135,9 +141,10 @@ static void jac_accumulate(const net_t *n, const double *u, const double *k, put
             for (int64_t b = n->rp[j]; b < n->rp[j + 1]; ++b)
                 if (n->ri[b] == l) { if (b < a) dup = 1; nu_l += n->rn[b]; }
             if (dup) continue;
-            double d = k[j] * (double)nu_l * ipow(u[l], nu_l - 1);
+            double d = k[j] * (double)nu_l * ipow(gu(u[l]), nu_l - 1);
+            if (g_neg_guard && u[l] < 0.0) d = 0.0;
             for (int64_t b = n->rp[j]; b < n->rp[j + 1]; ++b)
-                if (n->ri[b] != l) d *= ipow(u[n->ri[b]], n->rn[b]);
+                if (n->ri[b] != l) d *= ipow(gu(u[n->ri[b]]), n->rn[b]);
             for (int64_t e = n->np_[j]; e < n->np_[j + 1]; ++e) put(ctx, n->ni[e], l, (double)n->nn[e] * d);
         }
     }
@@ -252,6 +259,33 @@ static double wrms(int64_t S, const double *e, const double *u0, const double *u
     return sqrt(s / (double)S);
 }
 
+/* starting step size of Hairer/Nørsett/Wanner II.4 for an order-4 method; also used to restart the
+ * step size after every discrete rate update (the RHS jumps there). f, un, tmp: scratch. */
+static double hinit(const net_t *n, const double *u, const double *k, double *f, double *un, double *tmp,
+                    double abstol, double reltol)
+{
+    const int64_t S = n->S;
+    rhs_eval(n, u, k, f);
+    double d0 = 0, d1 = 0;
+    for (int64_t i = 0; i < S; ++i) {
+        double sc = abstol + reltol * fabs(u[i]);
+        d0 += (u[i] / sc) * (u[i] / sc); d1 += (f[i] / sc) * (f[i] / sc);
+    }
+    d0 = sqrt(d0 / S); d1 = sqrt(d1 / S);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    for (int64_t i = 0; i < S; ++i) un[i] = u[i] + h0 * f[i];
+    rhs_eval(n, un, k, tmp);
+    double d2 = 0;
+    for (int64_t i = 0; i < S; ++i) {
+        double sc = abstol + reltol * fabs(u[i]);
+        double q = (tmp[i] - f[i]) / sc; d2 += q * q;
+    }
+    d2 = sqrt(d2 / S) / h0;
+    double dm = fmax(d1, d2);
+    double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
+    return fmin(100.0 * h0, h1);
+}
+
 enum { ST_OK = 0, ST_MAXITERS = 1, ST_DTMIN = 2, ST_SINGULAR = 3, ST_NAN = 4 };
 
 /* Integrate every member.  Layouts: T_stop[b*nstops + s], u0[b*S + i] (u0_stride = 0 broadcasts
@@ -299,27 +333,7 @@ int64_t ko_solve_rodas4(int64_t S, int64_t R, const int64_t *rp, const int64_t *
             ++si;
         }
         /* initial step (Hairer/Nørsett/Wanner II.4 starting step, order 4) */
-        {
-            rhs_eval(&n, u, k, f); ++nrhs;
-            double d0 = 0, d1 = 0;
-            for (int64_t i = 0; i < S; ++i) {
-                double sc = abstol + reltol * fabs(u[i]);
-                d0 += (u[i] / sc) * (u[i] / sc); d1 += (f[i] / sc) * (f[i] / sc);
-            }
-            d0 = sqrt(d0 / S); d1 = sqrt(d1 / S);
-            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-            for (int64_t i = 0; i < S; ++i) un[i] = u[i] + h0 * f[i];
-            rhs_eval(&n, un, k, tmp); ++nrhs;
-            double d2 = 0;
-            for (int64_t i = 0; i < S; ++i) {
-                double sc = abstol + reltol * fabs(u[i]);
-                double q = (tmp[i] - f[i]) / sc; d2 += q * q;
-            }
-            d2 = sqrt(d2 / S) / h0;
-            double dm = fmax(d1, d2);
-            double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
-            h = fmin(100.0 * h0, h1);
-        }
+        h = hinit(&n, u, k, f, un, tmp, abstol, reltol); nrhs += 2;
         double err_old = 1.0, h_old = h;
         int rejected_last = 0, first_acc = 1;
         int64_t iters = 0;
@@ -388,10 +402,14 @@ int64_t ko_solve_rodas4(int64_t S, int64_t R, const int64_t *rp, const int64_t *
                 if (hit) {
                     t = tstop;
                     h = fmax(hnew, h);            /* keep the pre-truncation proposal */
+                    int updated = 0;
                     while (si < nstops && stop_t[si] <= t) {
-                        if (stop_flags[si] & 1) ko_arrhenius(R, A, Ea, T_stop[b * nstops + si], k_max, t_mult, k);
+                        if (stop_flags[si] & 1) { ko_arrhenius(R, A, Ea, T_stop[b * nstops + si], k_max, t_mult, k); updated = 1; }
                         if (stop_flags[si] & 2) { memcpy(out_u + (b * Ns + isave) * S, u, sizeof(double) * (size_t)S); ++isave; }
                         ++si;
+                    }
+                    if (updated && si < nstops) {   /* the RHS jumped: restart the step size */
+                        h = fmin(h, hinit(&n, u, k, f, un, tmp, abstol, reltol)); nrhs += 2;
                     }
                 } else {
                     t += hs;

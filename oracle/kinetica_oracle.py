@@ -512,33 +512,68 @@ class Network:
             self.sub.append(sorted(sub.items()))
             self.net.append(sorted((s, n) for s, n in net.items() if n != 0))
 
+    def _vec(self):
+        """numpy/scipy tables for vectorised evaluation (same arithmetic, different summation order
+        than the scalar loops below)."""
+        if getattr(self, "_v", None) is None:
+            import scipy.sparse as sp
+            idx = np.full((self.R, 3), -1, dtype=np.int64)
+            ex = np.zeros((self.R, 3), dtype=np.int64)
+            for j, sub in enumerate(self.sub):
+                assert len(sub) <= 3
+                for q, (s_, n_) in enumerate(sub):
+                    idx[j, q], ex[j, q] = s_, n_
+            rows = [s_ for j in range(self.R) for s_, _ in self.net[j]]
+            cols = [j for j in range(self.R) for _ in self.net[j]]
+            vals = [float(n_) for j in range(self.R) for _, n_ in self.net[j]]
+            N = sp.csr_matrix((vals, (rows, cols)), shape=(self.S, self.R))
+            self._v = (idx, ex, N)
+        return self._v
+
     def rates(self, u, k):
-        r = np.array(k, dtype=np.float64).copy()
-        for j in range(self.R):
-            for s, n in self.sub[j]:
-                r[j] *= u[s] ** n
-        return r
+        idx, ex, _ = self._vec()
+        u = np.asarray(u, dtype=np.float64)
+        f = np.where(idx >= 0, u[np.maximum(idx, 0)] ** ex, 1.0)
+        return np.asarray(k, dtype=np.float64) * f[:, 0] * f[:, 1] * f[:, 2]
 
     def rhs(self, u, k):
-        """du_i = sum_j net[i,j] * k_j * prod_m u_m^nu_mj, summed in ascending j."""
-        r = self.rates(u, k)
+        """du_i = sum_j net[i,j] * k_j * prod_m u_m^nu_mj."""
+        return self._vec()[2] @ self.rates(u, k)
+
+    def rhs_scalar(self, u, k):
+        """Same, scalar loops, summed in ascending j (the order the CUDA gather uses)."""
         du = np.zeros(self.S)
         for j in range(self.R):
-            for s, n in self.net[j]:
-                du[s] += n * r[j]
+            r = k[j]
+            for s_, n_ in self.sub[j]:
+                r *= u[s_] ** n_
+            for s_, n_ in self.net[j]:
+                du[s_] += n_ * r
         return du
 
+    def jac_sparse(self, u, k):
+        import scipy.sparse as sp
+        idx, ex, N = self._vec()
+        u = np.asarray(u, dtype=np.float64)
+        k = np.asarray(k, dtype=np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            f = np.where(idx >= 0, u[np.maximum(idx, 0)] ** ex, 1.0)
+            rr, cc, vv = [], [], []
+            for q in range(3):
+                has = idx[:, q] >= 0
+                e = ex[:, q]
+                dq = np.where(e >= 1, e * u[np.maximum(idx[:, q], 0)] ** np.maximum(e - 1, 0), 0.0)
+                others = np.ones(self.R)
+                for q2 in range(3):
+                    if q2 != q:
+                        others = others * f[:, q2]
+                d = k * dq * others
+                rr.append(np.nonzero(has)[0]); cc.append(idx[has, q]); vv.append(d[has])
+        D = sp.csr_matrix((np.concatenate(vv), (np.concatenate(rr), np.concatenate(cc))), shape=(self.R, self.S))
+        return (N @ D).tocsc()
+
     def jac_dense(self, u, k):
-        J = np.zeros((self.S, self.S))
-        for j in range(self.R):
-            for l, nl in self.sub[j]:
-                d = k[j] * nl * u[l] ** (nl - 1)
-                for m, nm in self.sub[j]:
-                    if m != l:
-                        d *= u[m] ** nm
-                for i, n in self.net[j]:
-                    J[i, l] += n * d
-        return J
+        return np.asarray(self.jac_sparse(u, k).todense())
 
     def pattern_csc(self):
         """P_J = {(i,l): exists j, net[i,j] != 0 and nu_lj > 0}, CSC with rows ascending
@@ -679,8 +714,7 @@ def solve_trajectory(net: Network, u0, k_table, tstops, tspan, saveat, k_init=No
             return net.rhs(y, kk)
 
         def jac(t, y, kk=kk):
-            J = net.jac_dense(y, kk)
-            return sp.csc_matrix(J) if (have_pat and net.S > 64) else J
+            return net.jac_sparse(y, kk) if (have_pat and net.S > 64) else net.jac_dense(y, kk)
 
         te = np.unique(np.append(saveat[sel], b))
         sol = solve_ivp(f, (a, b), u, method=method, jac=jac, rtol=rtol, atol=atol, t_eval=te)
