@@ -226,9 +226,7 @@ class EnsembleSolver:
                     if np.any(np.abs(ref - exact) > 1e-12 * np.maximum(np.abs(exact), 1.0)):
                         need_table = True
                     table[b, ridx] = ref
-            self.h.set_profiles(kinds, params)
-            self.h.set_T_table(table if need_table else None)
-            return None
+            return dict(kinds=kinds, params=params, table=table if need_table else None, sol_k=None)
         # calculators without a device kernel: host table (single member)
         if B != 1:
             raise NotImplementedError("host-tabulated calculators are supported for single-member solves only")
@@ -244,11 +242,32 @@ class EnsembleSolver:
             ts, k_all = calculate_discrete_rates(cs, self.calculator, self.rd.nr)
             k_table = k_all[np.isin(ts, rate_stops)]
             sol_k = (ts, k_all)
-        self.h.set_rate_table(k_table, k_init)
-        self.h.set_T_table(None)
-        return sol_k
+        return dict(k_table=k_table, k_init=k_init, sol_k=sol_k)
 
     def prepare(self, conds: Sequence[ConditionSet], pars: ODESimulationParams, u0):
+        """Host-side assembly of the stop / profile tables (cached per (conds, pars) identity: the
+        tables are rebuilt only when a different ensemble is bound), then the H2D upload."""
+        key = (id(conds), id(pars), len(conds), pars.abstol, pars.reltol)
+        if getattr(self, "_bound_key", None) != key:
+            self._bind(conds, pars)
+            self._bound_key = key
+        b = self._bound
+        if b["shared"]:
+            self.h.set_stops(b["stop_t"], b["flags"])
+        else:
+            self.h.set_member_stops(b["counts"], b["stop_t"], b["flags"])
+        if self.dev is not None:
+            self.h.set_profiles(b["kinds"], b["params"])
+            self.h.set_T_table(b["table"])
+        else:
+            self.h.set_rate_table(b["k_table"], b["k_init"])
+            self.h.set_T_table(None)
+        t0, tf = pars.tspan
+        self.h.solve_prepare(len(conds), u0, t0, pars.abstol, pars.reltol, float(np.spacing(tf)), pars.maxiters,
+                             pars.ban_negatives, len(self.save_t))
+        return b["sol_k"]
+
+    def _bind(self, conds: Sequence[ConditionSet], pars: ODESimulationParams):
         t0, tf = pars.tspan
         si = pars.save_interval if pars.save_interval is not None else tf / 1000
         saveat = create_savepoints(t0, tf, si)
@@ -265,9 +284,9 @@ class EnsembleSolver:
                 if len(ts) != len(tstops0) or np.any(ts != tstops0):
                     same = False
                     break
+        bound = {"shared": same, "counts": None}
         if same:
             stop_t, flags = merge_stops(tstops0, saveat, t0, tf)
-            self.h.set_stops(stop_t, flags)
             self.save_t = stop_t[(flags & STOP_SAVE) != 0]
         else:
             # members with their own tstops grids (e.g. t_end differing in the last bit)
@@ -281,12 +300,12 @@ class EnsembleSolver:
                 stop_t[b, :len(t)] = t
                 stop_t[b, len(t):] = np.inf
                 flags[b, :len(t)] = f
-            self.h.set_member_stops(counts, np.where(np.isfinite(stop_t), stop_t, 0.0), flags)
+            stop_t = np.where(np.isfinite(stop_t), stop_t, 0.0)
+            bound["counts"] = counts
             self.save_t = lists[0][0][(lists[0][1] & STOP_SAVE) != 0]
-        sol_k = self._conditions_to_device(conds, stop_t, flags)
-        self.h.solve_prepare(B, u0, t0, pars.abstol, pars.reltol, float(np.spacing(tf)), pars.maxiters,
-                             pars.ban_negatives, len(self.save_t))
-        return sol_k
+        bound["stop_t"], bound["flags"] = stop_t, flags
+        bound.update(self._conditions_to_device(conds, stop_t, flags))
+        self._bound = bound
 
     def run(self):
         return self.h.solve_run()
