@@ -65,12 +65,16 @@ int32_t kb2_set_network(kb2_handle h, int64_t S, int64_t R,
 
 /* ---- symbolic analysis: replaces MTK `jac=true, sparse=true` pattern detection
  * (methods.jl:157-158) and KLU's symbolic phase.  ordering: 0 = minimum degree,
- * 1 = natural, 2 = caller-supplied via kb2_set_ordering. ---- */
+ * 1 = natural, 2 = caller-supplied via kb2_set_ordering, 3 = natural with dense species last,
+ * 4 = auto (whichever of 0 and 3 gives the smaller padded panel storage). ---- */
 int32_t kb2_set_ordering(kb2_handle h, const int64_t *perm);
 int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, int64_t *nnzLU, int64_t *n_fma);
 int32_t kb2_get_pattern(kb2_handle h, int64_t *colptr, int64_t *rowval);          /* CSC of P_J */
 int32_t kb2_get_ordering(kb2_handle h, int64_t *perm);
 int32_t kb2_get_lu_pattern(kb2_handle h, int64_t *rowptr, int64_t *colidx, int64_t *diagpos);
+/* panel plan of the numeric factorisation: out[8] = {padded storage slots, panels, units,
+ * pivot steps, FMAs incl. padding, widest panel, column-map entries, block barriers per LU} */
+int32_t kb2_get_plan_stats(kb2_handle h, int64_t *out);
 
 /* ---- calculators: PrecalculatedArrheniusCalculator (calculator.jl:164-238);
  * k = A*T^n*exp(-Ea/(R*T))*N_A*t_mult, harmonic cap with k_max unless k_max is NaN;

@@ -29,6 +29,7 @@ SIGNATURES = {
     "kb2_get_pattern": (_i32, [_H, _pi64, _pi64]),
     "kb2_get_ordering": (_i32, [_H, _pi64]),
     "kb2_get_lu_pattern": (_i32, [_H, _pi64, _pi64, _pi64]),
+    "kb2_get_plan_stats": (_i32, [_H, _pi64]),
     "kb2_set_arrhenius": (_i32, [_H, _pf64, _pf64, _pf64, _f64, _f64]),
     "kb2_set_rate_table": (_i32, [_H, _i64, _pf64, _pf64]),
     "kb2_set_profiles": (_i32, [_H, _i64, _pi32, _pf64]),
@@ -145,6 +146,12 @@ class Handle:
         perm = np.zeros(self.S, dtype=np.int64)
         self._ck(self._lib.kb2_get_ordering(self._h, _i(perm)))
         return perm
+
+    def get_plan_stats(self):
+        out = np.zeros(8, dtype=np.int64)
+        self._ck(self._lib.kb2_get_plan_stats(self._h, _i(out)))
+        return dict(zip(["padded", "panels", "units", "steps", "fma_padded", "max_width", "map_entries", "barriers_per_lu"],
+                        map(int, out)))
 
     def get_lu_pattern(self):
         rowptr = np.zeros(self.S + 1, dtype=np.int64)

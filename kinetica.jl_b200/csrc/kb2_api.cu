@@ -2,7 +2,7 @@
 // memory behind the opaque handle, copies caller arrays in/out, launches the kernels of
 // kb2_kernels.cuh.  There is no CPU fallback: without a usable CUDA device every compute entry
 // point fails with a non-zero status.
-#include "kb2_kernels.cuh"
+#include "kb2_solve.cuh"
 #include "kb2_internal.h"
 #include "../../include/kinetica_b200.h"
 
@@ -40,6 +40,7 @@ struct kb2_ctx {
     // device
     std::vector<void *> net_allocs, ens_allocs;
     DevNet dn{};
+    DevPlan dp{};
     DevEns de{};
     int64_t ens_B = -1, ens_Ns = -1;
     size_t ens_fixed = 0;
@@ -129,8 +130,8 @@ extern "C" int64_t kb2_launch_count(kb2_handle h) { return h ? h->launches : 0; 
 extern "C" int32_t kb2_set_tiling(kb2_handle h, int32_t mb, int32_t nt)
 {
     if (!h) return 1;
-    if (mb != 0 && (mb < 1 || mb > 32 || (mb & (mb - 1)))) FAIL(h, "members_per_tile must be a power of two <= 32");
-    if (nt != 0 && (nt < 32 || nt > 1024 || nt % 32)) FAIL(h, "threads_per_cta must be a multiple of 32 in [32,1024]");
+    if (mb != 0 && (mb < 1 || mb > 16 || (mb & (mb - 1)))) FAIL(h, "members_per_tile must be a power of two <= 16");
+    if (nt != 0 && nt != 32 * mb) FAIL(h, "threads_per_cta is fixed at 32 * members_per_tile");
     h->mb_user = mb; h->nt_user = nt;
     return 0;
 }
@@ -189,13 +190,48 @@ static int upload_network(kb2_ctx *h)
     rc |= dev_upload(h, P, s.jt_ptr.data(), s.jt_ptr.size(), &d.jt_ptr);
     rc |= dev_upload(h, P, s.jt_rxn.data(), s.jt_rxn.size(), &d.jt_rxn);
     rc |= dev_upload(h, P, s.jt_pack.data(), s.jt_pack.size(), &d.jt_pack);
-    rc |= dev_upload(h, P, s.slot_src.data(), s.slot_src.size(), &d.slot_src);
     rc |= dev_upload(h, P, s.lu_rowptr.data(), s.lu_rowptr.size(), &d.rowptr);
     rc |= dev_upload(h, P, s.lu_colidx.data(), s.lu_colidx.size(), &d.colidx);
     rc |= dev_upload(h, P, s.lu_diagpos.data(), s.lu_diagpos.size(), &d.diagpos);
     rc |= dev_upload(h, P, perm32.data(), perm32.size(), &d.perm);
     rc |= dev_upload(h, P, s.tgt_off.data(), s.tgt_off.size(), &d.tgt_off);
     rc |= dev_upload(h, P, s.tgt.data(), s.tgt.size(), &d.tgt);
+    // panel plan: the LU value storage is the padded panel layout
+    {
+        const PanelPlan &pp = s.panels;
+        DevPlan &q = h->dp;
+        q = DevPlan{};
+        q.npanels = (int)pp.p_row0.size(); q.nunits = (int)pp.units.size(); q.padded = (int)pp.padded;
+        std::vector<int32_t> up, ux0, ux1, us0, unp, une, um0, ud;
+        for (const auto &u : pp.units) {
+            up.push_back(u.panel); ux0.push_back(u.x0); ux1.push_back(u.x1); us0.push_back(u.step0);
+            unp.push_back(u.n_pre); une.push_back(u.n_ext); um0.push_back(u.map0);
+            ud.push_back(u.diag_here ? 1 : (u.diag_before ? 2 : 0));
+        }
+        rc |= dev_upload(h, P, pp.p_row0.data(), pp.p_row0.size(), &q.p_row0);
+        rc |= dev_upload(h, P, pp.p_nrows.data(), pp.p_nrows.size(), &q.p_nrows);
+        rc |= dev_upload(h, P, pp.p_width.data(), pp.p_width.size(), &q.p_width);
+        rc |= dev_upload(h, P, pp.p_next.data(), pp.p_next.size(), &q.p_next);
+        rc |= dev_upload(h, P, pp.p_base.data(), pp.p_base.size(), &q.p_base);
+        rc |= dev_upload(h, P, pp.p_cptr.data(), pp.p_cptr.size(), &q.p_cptr);
+        rc |= dev_upload(h, P, pp.cols.data(), pp.cols.size(), &q.cols);
+        rc |= dev_upload(h, P, up.data(), up.size(), &q.u_panel);
+        rc |= dev_upload(h, P, ux0.data(), ux0.size(), &q.u_x0);
+        rc |= dev_upload(h, P, ux1.data(), ux1.size(), &q.u_x1);
+        rc |= dev_upload(h, P, us0.data(), us0.size(), &q.u_step0);
+        rc |= dev_upload(h, P, unp.data(), unp.size(), &q.u_npre);
+        rc |= dev_upload(h, P, une.data(), une.size(), &q.u_next);
+        rc |= dev_upload(h, P, um0.data(), um0.size(), &q.u_map0);
+        rc |= dev_upload(h, P, ud.data(), ud.size(), &q.u_diag);
+        rc |= dev_upload(h, P, pp.s_e.data(), pp.s_e.size(), &q.s_e);
+        rc |= dev_upload(h, P, pp.s_k.data(), pp.s_k.size(), &q.s_k);
+        rc |= dev_upload(h, P, pp.s_src.data(), pp.s_src.size(), &q.s_src);
+        rc |= dev_upload(h, P, pp.s_map.data(), pp.s_map.size(), &q.s_map);
+        rc |= dev_upload(h, P, pp.maps.data(), pp.maps.size(), &q.maps);
+        // W assembly runs over the padded storage
+        rc |= dev_upload(h, P, pp.slot_src.data(), pp.slot_src.size(), &d.slot_src);
+        d.nnzLU = (int)pp.padded;
+    }
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     h->net_on_device = true;
@@ -207,14 +243,40 @@ extern "C" int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, i
 {
     if (!h) return 1;
     if (h->net.S <= 0) FAIL(h, "set the network first");
-    std::string e = build_symbolic(h->net, ordering, h->sym);
-    if (!e.empty()) FAIL(h, e);
+    std::string e;
+    if (ordering == 4) {
+        // auto: the candidate whose padded panel storage is smallest (triangular solves stream it)
+        Symbolic a, b2;
+        e = build_symbolic(h->net, 0, a);
+        if (e.empty()) e = build_panels(a, h->net.S);
+        if (!e.empty()) FAIL(h, e);
+        e = build_symbolic(h->net, 3, b2);
+        if (e.empty()) e = build_panels(b2, h->net.S);
+        if (!e.empty()) FAIL(h, e);
+        h->sym = (b2.panels.padded < a.panels.padded) ? std::move(b2) : std::move(a);
+    } else {
+        e = build_symbolic(h->net, ordering, h->sym);
+        if (!e.empty()) FAIL(h, e);
+        e = build_panels(h->sym, h->net.S);
+        if (!e.empty()) FAIL(h, e);
+    }
     if (nnzJ) *nnzJ = h->sym.nnzJ;
     if (nnzLU) *nnzLU = h->sym.nnzLU;
     if (n_fma) *n_fma = h->sym.n_fma;
     h->prepared = false;
     h->ens_B = -1;
     return upload_network(h);
+}
+
+extern "C" int32_t kb2_get_plan_stats(kb2_handle h, int64_t *out)
+{
+    if (!h || !h->sym.ready) return 1;
+    const PanelPlan &pp = h->sym.panels;
+    out[0] = pp.padded; out[1] = (int64_t)pp.p_row0.size(); out[2] = (int64_t)pp.units.size();
+    out[3] = (int64_t)pp.s_e.size(); out[4] = pp.n_fma_padded; out[5] = pp.max_width;
+    out[6] = (int64_t)pp.maps.size(); out[7] = 0;
+    for (const auto &u : pp.units) out[7] += u.n_ext + (u.diag_here ? pp.p_nrows[u.panel] - 1 : 0);   // block barriers per LU
+    return 0;
 }
 
 extern "C" int32_t kb2_get_pattern(kb2_handle h, int64_t *colptr, int64_t *rowval)
@@ -354,7 +416,7 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
     rc |= dev_alloc(h, P, S * Bp, &e.y);
     for (int q = 0; q < 6; ++q) rc |= dev_alloc(h, P, S * Bp, &e.K[q]);
     rc |= dev_alloc(h, P, R * Bp, &e.k);
-    rc |= dev_alloc(h, P, (size_t)h->sym.nnzLU * Bp, &e.lu);
+    rc |= dev_alloc(h, P, (size_t)h->sym.panels.padded * Bp, &e.lu);
     rc |= dev_alloc(h, P, S * Bp, &e.invd);
     rc |= dev_alloc(h, P, (size_t)std::max<int64_t>(Ns, 1) * S * Bp, &e.out_u);
     rc |= dev_alloc(h, P, S * Bp, &e.out_umax);
@@ -381,20 +443,18 @@ static int down2d(kb2_ctx *h, double *dst, const double *src, size_t rows, size_
 
 static void pick_tiling(kb2_ctx *h, int64_t B, bool need_w, int *mb_out, int *nt_out, size_t *smem_out)
 {
-    const int maxrow = std::max(h->sym.max_rowlen, 1);
+    (void)need_w;
     int mb = h->mb_user;
     if (mb == 0) {
-        // as many members per tile as keeps >= ~2 tiles per SM, bounded by the LU row workspace
-        mb = 32;
-        while (mb > 1 && (B + mb - 1) / mb < 2 * (int64_t)h->sm_count) mb >>= 1;
-        if (mb > 8) mb = 8;
+        // 8 members per tile (64-byte coalesced segments, 256 threads) unless the ensemble is too
+        // small to give every SM a tile
+        mb = 8;
+        while (mb > 1 && (B + mb - 1) / mb < (int64_t)h->sm_count) mb >>= 1;
     }
-    int nt = h->nt_user ? h->nt_user : 256;
-    const size_t budget = h->smem_optin > 4096 ? h->smem_optin - 4096 : 44 * 1024;
-    while (mb > 1 && need_w && ((size_t)maxrow * mb + nt) * 8 > budget) mb >>= 1;
-    if (nt < mb) nt = 32;
+    if (mb > 16) mb = 16;
+    const int nt = 32 * mb;          // thread = (member, column lane): 32 column lanes per member
     *mb_out = mb; *nt_out = nt;
-    *smem_out = ((need_w ? (size_t)maxrow * mb : 0) + nt) * 8;
+    *smem_out = ((size_t)2 * PR * mb + (size_t)PR * mb * mb + nt) * 8;
 }
 
 #define DISPATCH_MB(mb, ...)                                          \
@@ -403,8 +463,7 @@ static void pick_tiling(kb2_ctx *h, int64_t B, bool need_w, int *mb_out, int *nt
     case 2: { constexpr int MB = 2; __VA_ARGS__; } break;             \
     case 4: { constexpr int MB = 4; __VA_ARGS__; } break;             \
     case 8: { constexpr int MB = 8; __VA_ARGS__; } break;             \
-    case 16: { constexpr int MB = 16; __VA_ARGS__; } break;           \
-    default: { constexpr int MB = 32; __VA_ARGS__; } break;           \
+    default: { constexpr int MB = 16; __VA_ARGS__; } break;           \
     }
 
 template <class K>
@@ -514,7 +573,7 @@ static int launch_factor(kb2_ctx *h, int64_t B, const double *d_hg)
     DISPATCH_MB(mb, {
         int r = set_smem(h, k_factor<MB>, smem);
         if (r) return r;
-        k_factor<MB><<<ntiles, nt, smem, h->stream>>>(h->dn, e, d_hg, ntiles);
+        k_factor<MB><<<ntiles, nt, smem, h->stream>>>(h->dn, h->dp, e, d_hg, ntiles);
     });
     h->launches++;
     CU(h, cudaGetLastError());
@@ -527,8 +586,7 @@ static int launch_trisolve(kb2_ctx *h, int64_t B)
     int mb, nt; size_t smem;
     pick_tiling(h, B, true, &mb, &nt, &smem);
     const int ntiles = e.Bp / mb;
-    smem = (size_t)nt * 8;
-    DISPATCH_MB(mb, (k_trisolve<MB><<<ntiles, nt, smem, h->stream>>>(h->dn, e, ntiles)));
+    DISPATCH_MB(mb, (k_trisolve<MB><<<ntiles, nt, smem, h->stream>>>(h->dn, h->dp, e, ntiles)));
     h->launches++;
     CU(h, cudaGetLastError());
     return 0;
@@ -546,7 +604,15 @@ extern "C" int32_t kb2_factor(kb2_handle h, int64_t B, const double *u, const do
     std::copy(hg_inv, hg_inv + B, hp.begin());
     CU(h, cudaMemcpyAsync(e.y, hp.data(), e.Bp * 8, cudaMemcpyHostToDevice, h->stream));
     if ((rc = launch_factor(h, B, e.y))) return rc;
-    if (lu_out && (rc = down2d(h, lu_out, e.lu, (size_t)h->sym.nnzLU, B, e.Bp))) return rc;
+    if (lu_out) {
+        // device storage is the padded panel layout: bring it back and gather the exact pattern
+        const PanelPlan &pp = h->sym.panels;
+        std::vector<double> tmp((size_t)pp.padded * B);
+        if ((rc = down2d(h, tmp.data(), e.lu, (size_t)pp.padded, B, e.Bp))) return rc;
+        CU(h, cudaStreamSynchronize(h->stream));
+        for (int64_t q = 0; q < h->sym.nnzLU; ++q)
+            std::copy(tmp.begin() + (size_t)pp.slot_of[q] * B, tmp.begin() + ((size_t)pp.slot_of[q] + 1) * B, lu_out + q * B);
+    }
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -705,7 +771,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve<MB>, nt, smem);
         if (per_sm < 1) FAIL(h, "solve kernel does not fit on an SM");
         const int grid = std::min(ntiles, per_sm * h->sm_count);
-        k_solve<MB><<<grid, nt, smem, h->stream>>>(h->dn, e, ntiles, h->d_counter);
+        k_solve<MB><<<grid, nt, smem, h->stream>>>(h->dn, h->dp, e, ntiles, h->d_counter);
     });
     h->launches++;
     CU(h, cudaEventRecord(h->ev1, h->stream));

@@ -17,6 +17,23 @@ struct Network {
     std::vector<int32_t> net_ptr, net_idx, net_coef;  // net stoichiometry per reaction (zeros dropped)
 };
 
+// Panel plan of the register-blocked LU / panel triangular solves (kb2_panel.cpp).
+struct PanelPlan {
+    static constexpr int PR = 8;      // rows per panel
+    static constexpr int CW = 128;    // columns per chunk (32 column lanes x 4 registers)
+    bool ready = false;
+    int64_t padded = 0, n_fma_padded = 0;
+    int32_t max_width = 0;
+    std::vector<int32_t> p_row0, p_nrows, p_width, p_next, p_base, p_cptr, cols;
+    std::vector<int32_t> row_panel, row_r;
+    std::vector<int32_t> slot_of;     // exact-pattern slot -> storage slot
+    std::vector<int32_t> slot_src;    // per storage slot: ((J entry + 1) << 1) | is_diagonal
+    std::vector<int32_t> diag_slot;   // per row
+    struct Unit { int32_t panel, x0, x1, step0, n_pre, n_ext, map0, n_maps, diag_here, diag_before; };
+    std::vector<Unit> units;
+    std::vector<int32_t> s_e, s_k, s_src, s_map, maps;
+};
+
 // Everything the kernels need that depends only on the network (shared by all members).
 struct Symbolic {
     bool ready = false;
@@ -40,11 +57,13 @@ struct Symbolic {
     std::vector<uint32_t> tgt_off;                    // per slot (only L slots meaningful)
     std::vector<int32_t> tgt;                         // n_fma entries
     int32_t max_rowlen = 0;
+    PanelPlan panels;
 };
 
 // Builds derived stoichiometry; returns "" or an error message.
 std::string build_network(Network &net);
 // ordering: 0 min degree, 1 natural, 2 user (sym.perm preset)
 std::string build_symbolic(const Network &net, int ordering, Symbolic &sym);
+std::string build_panels(Symbolic &sym, int64_t S);
 
 }  // namespace kb2

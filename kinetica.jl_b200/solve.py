@@ -189,7 +189,7 @@ class EnsembleSolver:
     """Network-level state on one GPU: symbolic factorisation + calculator tables, reusable
     across solves (what the reference rebuilds through MTK on every solve_network call)."""
 
-    def __init__(self, sd: SpeciesData, rd: RxData, calculator, device=0, ordering=0):
+    def __init__(self, sd: SpeciesData, rd: RxData, calculator, device=0, ordering=4):
         self.sd, self.rd, self.calculator = sd, rd, calculator
         self.h = _lib.Handle(device)
         self.h.set_network(sd.n, *rd.flatten())

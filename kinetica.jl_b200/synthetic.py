@@ -42,6 +42,10 @@ def synthetic_crn(S: int, R: int, seed: int, w: float = 16.0, n_hubs: int = 8,
     nf = R // 2
     seen = set()
     fwd = []
+    # every species carries an integer "mass" and every reaction balances it, so sum_i m_i u_i is a
+    # positive conservation law: concentrations stay bounded (random unbalanced A -> B + C networks
+    # are autocatalytic and blow up, which no real CRN does)
+    mass = rng.integers(1, 5, S)
     while len(fwd) < nf:
         kind = rng.random()
         c = int(rng.integers(0, S))
@@ -68,6 +72,8 @@ def synthetic_crn(S: int, R: int, seed: int, w: float = 16.0, n_hubs: int = 8,
         reac.sort()
         prod.sort()
         if reac == prod:
+            continue
+        if sum(int(mass[x]) for x in reac) != sum(int(mass[x]) for x in prod):
             continue
         key = (tuple(reac), tuple(prod))
         rkey = (tuple(prod), tuple(reac))

@@ -116,10 +116,32 @@ def test_rhs_deterministic(small):
     assert np.array_equal(a, b)            # gather CSR, no atomics: bit-identical run to run
 
 
+@pytest.mark.parametrize("S,R,ordering,B", [(96, 400, 0, 19), (420, 2100, 3, 9), (420, 2100, 0, 16), (30, 60, 1, 3)])
+def test_factor_and_trisolve_panels(built, S, R, ordering, B):
+    """Panel LU + panel triangular solves on networks whose hub rows span several column chunks
+    (S = 420: widest panel > 3 chunks), for every ordering mode and ragged member counts."""
+    from kinetica_b200 import _lib
+    from kinetica_b200.synthetic import synthetic_crn, SEED_BASE
+    from oracle import kinetica_oracle as ko
+    sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + 50 + S)
+    h = _lib.Handle(0)
+    h.set_network(S, *rd.flatten())
+    h.symbolic(ordering)
+    st = h.get_plan_stats()
+    if S == 420:
+        assert st["max_width"] > 256 and st["units"] > st["panels"]
+    net = ko.Network(S, rd.id_reacs, rd.id_prods, rd.stoic_reacs, rd.stoic_prods)
+    _factor_trisolve_check(h, net, B, seed=S)
+    h.close()
+
+
 def test_factor_and_trisolve(small):
     h, net, rd, Ea, A = small
-    rng = np.random.default_rng(4)
-    B = 19
+    _factor_trisolve_check(h, net, 19, seed=4)
+
+
+def _factor_trisolve_check(h, net, B, seed):
+    rng = np.random.default_rng(seed)
     u = rng.uniform(0, 1, (net.S, B))
     k = 10 ** rng.uniform(-3, 3, (net.R, B))
     hg = 10 ** rng.uniform(1, 4, B)
