@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -45,7 +46,7 @@ struct kb2_ctx {
     int64_t ens_B = -1, ens_Ns = -1;
     size_t ens_fixed = 0;
     int *d_counter = nullptr;
-    int mb_user = 0, nt_user = 0;
+    int mb_user = 0, nt_user = 0, variant = 0, last_ctas_per_sm = 0;
     bool prepared = false;
 };
 
@@ -131,8 +132,8 @@ extern "C" int32_t kb2_set_tiling(kb2_handle h, int32_t mb, int32_t nt)
 {
     if (!h) return 1;
     if (mb != 0 && (mb < 1 || mb > 16 || (mb & (mb - 1)))) FAIL(h, "members_per_tile must be a power of two <= 16");
-    if (nt != 0 && nt != 32 * mb) FAIL(h, "threads_per_cta is fixed at 32 * members_per_tile");
-    h->mb_user = mb; h->nt_user = nt;
+    if (nt != 0 && nt != 1) FAIL(h, "second argument selects the register-budget variant: 0 or 1");
+    h->mb_user = mb; h->variant = nt;
     return 0;
 }
 
@@ -202,11 +203,13 @@ static int upload_network(kb2_ctx *h)
         DevPlan &q = h->dp;
         q = DevPlan{};
         q.npanels = (int)pp.p_row0.size(); q.nunits = (int)pp.units.size(); q.padded = (int)pp.padded;
-        std::vector<int32_t> up, ux0, ux1, us0, unp, une, um0, ud;
+        q.dbg = getenv("KB2_DBG") ? atoi(getenv("KB2_DBG")) : 0;
+        std::vector<int32_t> up, ux0, ux1, us0, unp, une, um0, ud, ub0, unb;
         for (const auto &u : pp.units) {
             up.push_back(u.panel); ux0.push_back(u.x0); ux1.push_back(u.x1); us0.push_back(u.step0);
             unp.push_back(u.n_pre); une.push_back(u.n_ext); um0.push_back(u.map0);
             ud.push_back(u.diag_here ? 1 : (u.diag_before ? 2 : 0));
+            ub0.push_back(u.block0); unb.push_back(u.n_blocks);
         }
         rc |= dev_upload(h, P, pp.p_row0.data(), pp.p_row0.size(), &q.p_row0);
         rc |= dev_upload(h, P, pp.p_nrows.data(), pp.p_nrows.size(), &q.p_nrows);
@@ -223,11 +226,14 @@ static int upload_network(kb2_ctx *h)
         rc |= dev_upload(h, P, une.data(), une.size(), &q.u_next);
         rc |= dev_upload(h, P, um0.data(), um0.size(), &q.u_map0);
         rc |= dev_upload(h, P, ud.data(), ud.size(), &q.u_diag);
+        rc |= dev_upload(h, P, ub0.data(), ub0.size(), &q.u_block0);
+        rc |= dev_upload(h, P, unb.data(), unb.size(), &q.u_nblocks);
+        rc |= dev_upload(h, P, pp.b_info.data(), pp.b_info.size(), &q.b_info);
+        rc |= dev_upload(h, P, pp.b_idx.data(), pp.b_idx.size(), &q.b_idx);
         rc |= dev_upload(h, P, pp.s_e.data(), pp.s_e.size(), &q.s_e);
         rc |= dev_upload(h, P, pp.s_k.data(), pp.s_k.size(), &q.s_k);
-        rc |= dev_upload(h, P, pp.s_src.data(), pp.s_src.size(), &q.s_src);
-        rc |= dev_upload(h, P, pp.s_map.data(), pp.s_map.size(), &q.s_map);
-        rc |= dev_upload(h, P, pp.maps.data(), pp.maps.size(), &q.maps);
+        rc |= dev_upload(h, P, pp.s_meta.data(), pp.s_meta.size(), &q.s_meta);
+        rc |= dev_upload(h, P, pp.s_idx.data(), pp.s_idx.size(), &q.s_idx);
         // W assembly runs over the padded storage
         rc |= dev_upload(h, P, pp.slot_src.data(), pp.slot_src.size(), &d.slot_src);
         d.nnzLU = (int)pp.padded;
@@ -274,7 +280,7 @@ extern "C" int32_t kb2_get_plan_stats(kb2_handle h, int64_t *out)
     const PanelPlan &pp = h->sym.panels;
     out[0] = pp.padded; out[1] = (int64_t)pp.p_row0.size(); out[2] = (int64_t)pp.units.size();
     out[3] = (int64_t)pp.s_e.size(); out[4] = pp.n_fma_padded; out[5] = pp.max_width;
-    out[6] = (int64_t)pp.maps.size(); out[7] = 0;
+    out[6] = (int64_t)pp.s_idx.size(); out[7] = 0;
     for (const auto &u : pp.units) out[7] += u.n_ext + (u.diag_here ? pp.p_nrows[u.panel] - 1 : 0);   // block barriers per LU
     return 0;
 }
@@ -454,9 +460,18 @@ static void pick_tiling(kb2_ctx *h, int64_t B, bool need_w, int *mb_out, int *nt
     if (mb > 16) mb = 16;
     const int nt = 32 * mb;          // thread = (member, column lane): 32 column lanes per member
     *mb_out = mb; *nt_out = nt;
-    *smem_out = ((size_t)2 * PR * mb + (size_t)PR * mb * mb + nt) * 8;
+    *smem_out = (lu_smem_doubles(nt, mb) + (size_t)PR * mb * mb + nt) * 8;
 }
 
+// register-budget variants: A = 128 registers/thread (16/MB CTAs per SM), B = fewer CTAs, more registers
+#define DISPATCH_MBV(mb, variant, ...)                                                        \
+    switch (mb) {                                                                             \
+    case 1: if (variant) { constexpr int MB = 1, MINB = 12; __VA_ARGS__; } else { constexpr int MB = 1, MINB = 16; __VA_ARGS__; } break; \
+    case 2: if (variant) { constexpr int MB = 2, MINB = 6; __VA_ARGS__; } else { constexpr int MB = 2, MINB = 8; __VA_ARGS__; } break;   \
+    case 4: if (variant) { constexpr int MB = 4, MINB = 3; __VA_ARGS__; } else { constexpr int MB = 4, MINB = 4; __VA_ARGS__; } break;   \
+    case 8: if (variant) { constexpr int MB = 8, MINB = 1; __VA_ARGS__; } else { constexpr int MB = 8, MINB = 2; __VA_ARGS__; } break;   \
+    default: { constexpr int MB = 16, MINB = 1; __VA_ARGS__; } break;                         \
+    }
 #define DISPATCH_MB(mb, ...)                                          \
     switch (mb) {                                                     \
     case 1: { constexpr int MB = 1; __VA_ARGS__; } break;             \
@@ -564,16 +579,16 @@ extern "C" int32_t kb2_eval_jac(kb2_handle h, int64_t B, const double *u, const 
     return 0;
 }
 
-static int launch_factor(kb2_ctx *h, int64_t B, const double *d_hg)
+static int launch_factor(kb2_ctx *h, int64_t B, const double *d_hg, int mode = 3)
 {
     DevEns &e = h->de;
     int mb, nt; size_t smem;
     pick_tiling(h, B, true, &mb, &nt, &smem);
     const int ntiles = e.Bp / mb;
-    DISPATCH_MB(mb, {
-        int r = set_smem(h, k_factor<MB>, smem);
+    DISPATCH_MBV(mb, h->variant, {
+        int r = set_smem(h, k_factor<MB, MINB>, smem);
         if (r) return r;
-        k_factor<MB><<<ntiles, nt, smem, h->stream>>>(h->dn, h->dp, e, d_hg, ntiles);
+        k_factor<MB, MINB><<<ntiles, nt, smem, h->stream>>>(h->dn, h->dp, e, d_hg, ntiles, mode);
     });
     h->launches++;
     CU(h, cudaGetLastError());
@@ -586,7 +601,11 @@ static int launch_trisolve(kb2_ctx *h, int64_t B)
     int mb, nt; size_t smem;
     pick_tiling(h, B, true, &mb, &nt, &smem);
     const int ntiles = e.Bp / mb;
-    DISPATCH_MB(mb, (k_trisolve<MB><<<ntiles, nt, smem, h->stream>>>(h->dn, h->dp, e, ntiles)));
+    DISPATCH_MBV(mb, h->variant, {
+        int r = set_smem(h, k_trisolve<MB, MINB>, smem);
+        if (r) return r;
+        k_trisolve<MB, MINB><<<ntiles, nt, smem, h->stream>>>(h->dn, h->dp, e, ntiles);
+    });
     h->launches++;
     CU(h, cudaGetLastError());
     return 0;
@@ -640,7 +659,7 @@ extern "C" int32_t kb2_time_kernel(kb2_handle h, int32_t which, int64_t B, int32
     const int ntiles = e.Bp / mb;
     const int grid = std::min(ntiles, 8 * h->sm_count);
     // hg_inv / T source: reuse `invd`-independent scratch y filled with a benign constant
-    if (which == 0 || which == 3) {
+    if (which == 0 || which == 3 || which == 5 || which == 6) {
         std::vector<double> c(e.Bp, which == 0 ? 1000.0 : 1.0e6);
         CU(h, cudaMemcpyAsync(e.y, c.data(), e.Bp * 8, cudaMemcpyHostToDevice, h->stream));
     }
@@ -653,6 +672,8 @@ extern "C" int32_t kb2_time_kernel(kb2_handle h, int32_t which, int64_t B, int32
         case 2: DISPATCH_MB(mb, (k_jac<MB><<<grid, nt, 0, h->stream>>>(h->dn, e, e.lu, ntiles))); h->launches++; break;
         case 3: rc = launch_factor(h, B, e.y); break;
         case 4: rc = launch_trisolve(h, B); break;
+        case 5: rc = launch_factor(h, B, e.y, 1); break;   // W assembly only
+        case 6: rc = launch_factor(h, B, e.y, 2); break;   // LU only (on whatever the storage holds)
         default: FAIL(h, "unknown kernel id");
         }
         if (rc) return rc;
@@ -764,14 +785,15 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     const int ntiles = e.Bp / mb;
     CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
     CU(h, cudaEventRecord(h->ev0, h->stream));
-    DISPATCH_MB(mb, {
-        int r = set_smem(h, k_solve<MB>, smem);
+    DISPATCH_MBV(mb, h->variant, {
+        int r = set_smem(h, k_solve<MB, MINB>, smem);
         if (r) return r;
         int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve<MB>, nt, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve<MB, MINB>, nt, smem);
         if (per_sm < 1) FAIL(h, "solve kernel does not fit on an SM");
+        h->last_ctas_per_sm = per_sm;
         const int grid = std::min(ntiles, per_sm * h->sm_count);
-        k_solve<MB><<<grid, nt, smem, h->stream>>>(h->dn, h->dp, e, ntiles, h->d_counter);
+        k_solve<MB, MINB><<<grid, nt, smem, h->stream>>>(h->dn, h->dp, e, ntiles, h->d_counter);
     });
     h->launches++;
     CU(h, cudaEventRecord(h->ev1, h->stream));

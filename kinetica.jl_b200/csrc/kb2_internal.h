@@ -29,9 +29,15 @@ struct PanelPlan {
     std::vector<int32_t> slot_of;     // exact-pattern slot -> storage slot
     std::vector<int32_t> slot_src;    // per storage slot: ((J entry + 1) << 1) | is_diagonal
     std::vector<int32_t> diag_slot;   // per row
-    struct Unit { int32_t panel, x0, x1, step0, n_pre, n_ext, map0, n_maps, diag_here, diag_before; };
+    struct Unit { int32_t panel, x0, x1, step0, n_pre, n_ext, map0, n_maps, diag_here, diag_before, block0 = 0, n_blocks = 0; };
     std::vector<Unit> units;
     std::vector<int32_t> s_e, s_k, s_src, s_map, maps;
+    static constexpr int SEG = 64;    // source slots staged per step
+    static constexpr int NB = 4;      // steps per block (one barrier round)
+    std::vector<int32_t> b_info;      // [block] {first step (unit relative), steps, kind 0 pre / 1 in-chunk, owner lane}
+    std::vector<int32_t> b_idx;       // [block][32 column lanes][NB] packed byte-index words
+    std::vector<int32_t> s_meta;      // [step] {first source slot, slots, pivot column, flags}
+    std::vector<int32_t> s_idx;       // [step][32 column lanes] 4 x int8 index into the staged range (-1 none)
 };
 
 // Everything the kernels need that depends only on the network (shared by all members).

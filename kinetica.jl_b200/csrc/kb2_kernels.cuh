@@ -193,16 +193,40 @@ __device__ void tile_rhs(const Tile<MB> &tl, const DevNet &net, const double *u,
                          const double *k, double *out, int nk,
                          double *const *Kq, const double *cs)
 {
-    for (int i = tl.slot; i < net.S; i += tl.nslot) {
-        double acc = 0.0;
-        const int e1 = net.rhs_ptr[i + 1];
-        for (int e = net.rhs_ptr[i]; e < e1; ++e) {
-            const int j = net.rhs_rxn[e];
-            acc += (double)net.rhs_coef[e] * rate_of(net.rdesc[j], u, tl.Bp, tl.b, k[(size_t)j * tl.Bp + tl.b]);
+    // four species per thread at a time: their gather chains (index -> descriptor -> k, u) are
+    // independent, which gives the memory system four times as many loads in flight
+    constexpr int U = 4;
+    for (int i0 = tl.slot; i0 < net.S; i0 += U * tl.nslot) {
+        int e[U], e1[U];
+        double acc[U];
+        int len = 0;
+#pragma unroll
+        for (int v = 0; v < U; ++v) {
+            const int i = i0 + v * tl.nslot;
+            e[v] = i < net.S ? net.rhs_ptr[i] : 0;
+            e1[v] = i < net.S ? net.rhs_ptr[i + 1] : 0;
+            acc[v] = 0.0;
+            len = max(len, e1[v] - e[v]);
         }
-        const size_t o = (size_t)i * tl.Bp + tl.b;
-        for (int q = 0; q < nk; ++q) acc += cs[q] * Kq[q][o];
-        out[o] = acc;
+        for (int t = 0; t < len; ++t) {
+#pragma unroll
+            for (int v = 0; v < U; ++v) {
+                if (e[v] + t < e1[v]) {
+                    const int j = net.rhs_rxn[e[v] + t];
+                    acc[v] += (double)net.rhs_coef[e[v] + t] * rate_of(net.rdesc[j], u, tl.Bp, tl.b, k[(size_t)j * tl.Bp + tl.b]);
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < U; ++v) {
+            const int i = i0 + v * tl.nslot;
+            if (i < net.S) {
+                const size_t o = (size_t)i * tl.Bp + tl.b;
+                double a = acc[v];
+                for (int q = 0; q < nk; ++q) a += cs[q] * Kq[q][o];
+                out[o] = a;
+            }
+        }
     }
 }
 
@@ -227,17 +251,41 @@ __device__ void tile_jac_csc(const Tile<MB> &tl, const DevNet &net, const double
     for (int p = tl.slot; p < net.nnzJ; p += tl.nslot) Jval[(size_t)p * tl.Bp + tl.b] = jac_entry(tl, net, p, u, k);
 }
 
-// W = I/(h*gamma) - J assembled straight into the L\U slots (fill slots zeroed)
+// W = I/(h*gamma) - J assembled straight into the L\U slots (fill slots zeroed); four slots per
+// thread in flight
 template <int MB>
 __device__ void tile_assemble_w(const Tile<MB> &tl, const DevNet &net, const double *u,
                                 const double *k, double hg_inv, double *lu)
 {
-    for (int q = tl.slot; q < net.nnzLU; q += tl.nslot) {
-        const int src = net.slot_src[q];
-        double v = (src & 1) ? hg_inv : 0.0;
-        const int p = (src >> 1) - 1;
-        if (p >= 0) v -= jac_entry(tl, net, p, u, k);
-        lu[(size_t)q * tl.Bp + tl.b] = v;
+    constexpr int U = 4;
+    for (int q0 = tl.slot; q0 < net.nnzLU; q0 += U * tl.nslot) {
+        int t[U], t1[U];
+        double v[U];
+        int len = 0;
+#pragma unroll
+        for (int x = 0; x < U; ++x) {
+            const int q = q0 + x * tl.nslot;
+            const int src = q < net.nnzLU ? net.slot_src[q] : 0;
+            v[x] = (src & 1) ? hg_inv : 0.0;
+            const int p = (src >> 1) - 1;
+            t[x] = p >= 0 ? net.jt_ptr[p] : 0;
+            t1[x] = p >= 0 ? net.jt_ptr[p + 1] : 0;
+            len = max(len, t1[x] - t[x]);
+        }
+        for (int z = 0; z < len; ++z) {
+#pragma unroll
+            for (int x = 0; x < U; ++x) {
+                if (t[x] + z < t1[x]) {
+                    const int j = net.jt_rxn[t[x] + z], pk = net.jt_pack[t[x] + z];
+                    v[x] -= (double)(pk >> 2) * drate_of(net.rdesc[j], pk & 3, u, tl.Bp, tl.b, k[(size_t)j * tl.Bp + tl.b]);
+                }
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < U; ++x) {
+            const int q = q0 + x * tl.nslot;
+            if (q < net.nnzLU) lu[(size_t)q * tl.Bp + tl.b] = v[x];
+        }
     }
 }
 

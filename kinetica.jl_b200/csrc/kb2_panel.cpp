@@ -151,6 +151,104 @@ std::string build_panels(Symbolic &sym, int64_t S)
             pp.units.push_back(u);
         }
     }
+    // ---- per-step staging tables.  The part of the pivot row that a unit needs is one contiguous
+    // slot range of the source panel's storage; the CTA copies that range into shared memory
+    // (SEG slots per stage) and every lane looks its targets up with a byte index relative to the
+    // range start.  A pivot whose targets span more than SEG source slots is split into several
+    // steps; the follow-up steps reuse the already published multipliers.
+    {
+        const int NQ = CW / 32, SEG = PanelPlan::SEG;
+        std::vector<int32_t> ne, nk, nsrc, nmap, nflag;
+        pp.s_meta.clear(); pp.s_idx.clear();
+        for (auto &u : pp.units) {
+            const int nsteps = u.n_pre + u.n_ext;
+            const int old0 = u.step0;
+            u.step0 = (int32_t)ne.size();
+            int n_pre_new = 0, n_in_new = 0;
+            for (int z = 0; z < nsteps; ++z) {
+                const size_t st = (size_t)old0 + z;
+                const bool pre = z < u.n_pre;
+                // absolute source slot per chunk column (or -1)
+                std::vector<int32_t> off(CW, -1);
+                if (pp.s_map[st] >= 0) {
+                    const int32_t *mp = pp.maps.data() + ((size_t)u.map0 + pp.s_map[st]) * CW;
+                    const int ce = pp.s_e[st] - u.x0;
+                    for (int cl = 0; cl < CW; ++cl)
+                        if (mp[cl] >= 0 && cl > ce) off[cl] = pp.s_src[st] + mp[cl];
+                }
+                bool first = true;
+                for (;;) {
+                    int32_t lo = -1;
+                    for (int cl = 0; cl < CW; ++cl) if (off[cl] >= 0 && (lo < 0 || off[cl] < lo)) lo = off[cl];
+                    if (lo < 0 && !first) break;
+                    int32_t hi = lo;
+                    std::vector<int8_t> idx(CW, (int8_t)SEG);   // SEG = the stage's constant zero row
+                    if (lo >= 0)
+                        for (int cl = 0; cl < CW; ++cl)
+                            if (off[cl] >= 0 && off[cl] - lo < SEG) { idx[cl] = (int8_t)(off[cl] - lo); hi = std::max(hi, off[cl]); off[cl] = -1; }
+                    ne.push_back(pp.s_e[st]); nk.push_back(pp.s_k[st]);
+                    // meta: {first source slot, number of slots, pivot column, flags (1 = reuse multipliers)}
+                    pp.s_meta.push_back(lo < 0 ? 0 : lo);
+                    pp.s_meta.push_back(lo < 0 ? 0 : hi - lo + 1);
+                    pp.s_meta.push_back(pp.s_e[st]);
+                    pp.s_meta.push_back((first || pre) ? 0 : 1);   // in-chunk follow-ups reuse the published multipliers
+                    for (int cs = 0; cs < 32; ++cs) {
+                        uint32_t wd = 0;
+                        for (int q = 0; q < NQ; ++q) wd |= (uint32_t)(uint8_t)idx[cs * NQ + q] << (8 * q);
+                        pp.s_idx.push_back((int32_t)wd);
+                    }
+                    if (pre) ++n_pre_new; else ++n_in_new;
+                    first = false;
+                    if (lo < 0) break;
+                }
+            }
+            u.n_pre = n_pre_new; u.n_ext = n_in_new;
+        }
+        pp.s_e.swap(ne); pp.s_k.swap(nk);
+        pp.s_src.clear(); pp.s_map.clear(); pp.maps.clear();
+    }
+    // ---- blocks: up to NB consecutive steps share one barrier round.  In-chunk steps of one block
+    // all belong to the same owner lane (NQ consecutive pivot columns of one thread), which resolves
+    // the dependencies among its pivots before publishing their multipliers together.
+    {
+        const int NB = PanelPlan::NB, NQ = CW / 32;
+        pp.b_info.clear(); pp.b_idx.clear();
+        for (auto &u : pp.units) {
+            u.block0 = (int32_t)(pp.b_info.size() / 4);
+            const int n = u.n_pre + u.n_ext;
+            int z = 0;
+            while (z < n) {
+                const bool pre = z < u.n_pre;
+                const int lim = pre ? u.n_pre : n;
+                int cnt = 1;
+                const int owner = pre ? -1 : (pp.s_meta[4 * ((size_t)u.step0 + z) + 2] - u.x0) / NQ;
+                // multiplier buffer index of each step: new pivot -> next buffer, follow-up -> same buffer
+                int lj = 0;
+                std::vector<int> ljs{0};
+                while (z + cnt < lim && cnt < NB) {
+                    const size_t st = (size_t)u.step0 + z + cnt;
+                    const bool follow = (pp.s_meta[4 * st + 3] & 1) != 0;
+                    if (!pre && !follow && (pp.s_meta[4 * st + 2] - u.x0) / NQ != owner) break;
+                    if (!follow) ++lj;
+                    ljs.push_back(lj);
+                    ++cnt;
+                }
+                // a follow-up must stay in the block of its pivot
+                while (cnt > 1 && z + cnt < lim && (pp.s_meta[4 * ((size_t)u.step0 + z + cnt) + 3] & 1)) { --cnt; ljs.pop_back(); }
+                if (z + cnt < lim && (pp.s_meta[4 * ((size_t)u.step0 + z + cnt) + 3] & 1))
+                    return "a pivot row needs more staged segments than one block holds (unsupported pattern)";
+                for (int j = 0; j < cnt; ++j) pp.s_meta[4 * ((size_t)u.step0 + z + j) + 3] |= ljs[j] << 8;
+                int ljcode = 0;
+                for (int j = 0; j < cnt; ++j) ljcode |= ljs[j] << (8 + 2 * j);
+                pp.b_info.push_back(z); pp.b_info.push_back(cnt); pp.b_info.push_back((pre ? 0 : 1) | ljcode); pp.b_info.push_back(owner);
+                for (int cs = 0; cs < 32; ++cs)
+                    for (int j = 0; j < NB; ++j)
+                        pp.b_idx.push_back(j < cnt ? pp.s_idx[((size_t)u.step0 + z + j) * 32 + cs] : (int32_t)0x40404040);
+                z += cnt;
+            }
+            u.n_blocks = (int32_t)(pp.b_info.size() / 4) - u.block0;
+        }
+    }
     pp.ready = true;
     return "";
 }

@@ -35,21 +35,21 @@ __global__ void k_jac(DevNet net, DevEns en, double *Jval, int ntiles)
     }
 }
 
-template <int MB>
-__global__ void __launch_bounds__(32 * MB) k_factor(DevNet net, DevPlan pl, DevEns en, const double *hg_inv, int ntiles)
+template <int MB, int MINB>
+__global__ void __launch_bounds__(32 * MB, MINB) k_factor(DevNet net, DevPlan pl, DevEns en, const double *hg_inv, int ntiles, int mode)
 {
     extern __shared__ double smem[];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         Tile<MB> tl(tile, en.Bp);
-        tile_assemble_w(tl, net, en.u, en.k, hg_inv[tl.b], en.lu);
+        if (mode & 1) tile_assemble_w(tl, net, en.u, en.k, hg_inv[tl.b], en.lu);
         __syncthreads();
-        tile_lu_panels(tl, pl, en.lu, en.invd, smem);
+        if (mode & 2) tile_lu_panels(tl, pl, en.lu, en.invd, smem);
         __syncthreads();
     }
 }
 
-template <int MB>
-__global__ void __launch_bounds__(32 * MB) k_trisolve(DevNet net, DevPlan pl, DevEns en, int ntiles)
+template <int MB, int MINB>
+__global__ void __launch_bounds__(32 * MB, MINB) k_trisolve(DevNet net, DevPlan pl, DevEns en, int ntiles)
 {
     extern __shared__ double smem[];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -302,14 +302,14 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
     __syncthreads();
 }
 
-template <int MB>
-__global__ void __launch_bounds__(32 * MB) k_solve(DevNet net, DevPlan pl, DevEns en, int ntiles, int *tile_counter)
+template <int MB, int MINB>
+__global__ void __launch_bounds__(32 * MB, MINB) k_solve(DevNet net, DevPlan pl, DevEns en, int ntiles, int *tile_counter)
 {
     extern __shared__ double smem[];
     __shared__ Ctl<MB> c;
     __shared__ int s_tile;
     double *lbuf = smem;
-    double *red = smem + 2 * PR * MB;
+    double *red = smem + lu_smem_doubles(32 * MB, MB);
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1);
         __syncthreads();

@@ -154,12 +154,13 @@ def _factor_trisolve_check(h, net, B, seed):
         W = np.eye(net.S) * hg[b] - net.jac_dense(u[:, b], k[:, b])
         xr = np.linalg.solve(W, rhs[:, b])
         assert np.max(np.abs(x[:, b] - xr)) <= 1e-9 * np.max(np.abs(xr))
-        # L*U reproduces the permuted W on the pattern (and nothing outside it)
-        L = np.eye(net.S); U = np.zeros((net.S, net.S))
+        # L'*U' (Crout form: pivots on L', unit diagonal on U') reproduces the permuted W on the
+        # pattern and nothing outside it
+        L = np.zeros((net.S, net.S)); U = np.eye(net.S)
         for i in range(net.S):
             for p in range(rowptr[i], rowptr[i + 1]):
                 j = colidx[p]
-                if j < i:
+                if j <= i:
                     L[i, j] = lu[p, b]
                 else:
                     U[i, j] = lu[p, b]
