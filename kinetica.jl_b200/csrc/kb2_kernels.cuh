@@ -73,10 +73,13 @@ struct DevEns {
     int ban_neg;
 };
 
+// x^e for the small non-negative integer stoichiometries of mass action; exponents 0, 1 and 2
+// (uni/bimolecular steps, max_molecularity = 2 in the reference, network.jl:250) are branch-free selects
 __device__ __forceinline__ double pw(double x, int e)
 {
-    double r = 1.0;
-    for (; e > 0; --e) r *= x;
+    if (e <= 2) return e == 1 ? x : (e == 2 ? x * x : 1.0);
+    double r = x * x * x;
+    for (e -= 3; e > 0; --e) r *= x;
     return r;
 }
 

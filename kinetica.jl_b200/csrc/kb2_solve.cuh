@@ -174,7 +174,7 @@ __device__ void tile_hinit(const Tile<MB> &tl, const DevNet &net, const DevEns &
     const double hn = fmin(100.0 * h0, h1);
     if (tl.slot == 0) {
         if (initial) { c.h[m] = hn; c.hold[m] = hn; c.nrhs[m] += 2; }
-        else if (c.upd[m] && c.status[m] == ST_RUNNING) { c.h[m] = fmin(c.h[m], hn); c.nrhs[m] += 2; }
+        else if (c.upd[m] && c.status[m] == ST_RUNNING) { c.h[m] = fmin(c.h[m], 0.1 * hn); c.nrhs[m] += 2; }   // 0.1: see DESIGN.md §3
     }
     __syncthreads();
 }

@@ -286,6 +286,9 @@ static double hinit(const net_t *n, const double *u, const double *k, double *f,
     return fmin(100.0 * h0, h1);
 }
 
+static double g_facmin = 1.0 / 6.0, g_safe = 0.9, g_restart = 0.1;   /* restart = fraction of the fresh step estimate used after a rate update */
+void ko_set_controller(double facmin, double safe, double restart) { g_facmin = facmin; g_safe = safe; g_restart = restart; }
+
 enum { ST_OK = 0, ST_MAXITERS = 1, ST_DTMIN = 2, ST_SINGULAR = 3, ST_NAN = 4 };
 
 /* Integrate every member.  Layouts: T_stop[b*nstops + s], u0[b*S + i] (u0_stride = 0 broadcasts
@@ -379,7 +382,7 @@ int64_t ko_solve_rodas4(int64_t S, int64_t R, const int64_t *rp, const int64_t *
                     for (int64_t i = 0; i < S; ++i) if (tmp[i] < 0.0) { err = fmax(err, 1e4); break; }
             }
             /* step-size controller (RODAS: fac in [1/6, 5], safety 0.9, Gustafsson predictive) */
-            double fac = isfinite(err) ? fmax(1.0 / 6.0, fmin(5.0, pow(err, 0.25) / 0.9)) : 5.0;
+            double fac = isfinite(err) ? fmax(g_facmin, fmin(5.0, pow(err, 0.25) / g_safe)) : 5.0;
             double hnew = hs / fac;
             if (getenv("KO_DEBUG")) {
                 int64_t im = 0; double qm = 0;
@@ -389,8 +392,8 @@ int64_t ko_solve_rodas4(int64_t S, int64_t R, const int64_t *rp, const int64_t *
             if (err <= 1.0) {
                 ++nacc;
                 if (!first_acc) {
-                    double facgus = (h_old / hs) * pow(err * err / err_old, 0.25) / 0.9;
-                    facgus = fmax(1.0 / 6.0, fmin(5.0, facgus));
+                    double facgus = (h_old / hs) * pow(err * err / err_old, 0.25) / g_safe;
+                    facgus = fmax(g_facmin, fmin(5.0, facgus));
                     fac = fmax(fac, facgus);
                     hnew = hs / fac;
                 }
@@ -409,7 +412,7 @@ int64_t ko_solve_rodas4(int64_t S, int64_t R, const int64_t *rp, const int64_t *
                         ++si;
                     }
                     if (updated && si < nstops) {   /* the RHS jumped: restart the step size */
-                        h = fmin(h, hinit(&n, u, k, f, un, tmp, abstol, reltol)); nrhs += 2;
+                        h = fmin(h, g_restart * hinit(&n, u, k, f, un, tmp, abstol, reltol)); nrhs += 2;
                     }
                 } else {
                     t += hs;

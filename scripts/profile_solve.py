@@ -1,0 +1,24 @@
+"""Short fused solve for ncu: C3 network, B members, a few stops."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import kinetica_b200 as kb
+from kinetica_b200.synthetic import synthetic_crn, synthetic_u0, SEED_BASE
+S = 1000; R = 5000
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+tf = float(sys.argv[2]) if len(sys.argv) > 2 else 0.02
+maxit = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
+sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + 3)
+calc = kb.PrecalculatedArrheniusCalculator(Ea, A, k_max=1e12)
+pars = kb.ODESimulationParams(tspan=(0.0, tf), u0=synthetic_u0(S), save_interval=tf / 2, low_k_cutoff="none",
+                              solve_chunks=False, abstol=1e-8, reltol=1e-6, maxiters=maxit)
+conds = [kb.ConditionSet({"T": kb.LinearDirectProfile(rate=100.0, X_start=600.0 + 600.0 * b / (B - 1), X_end=700.0 + 600.0 * b / (B - 1))},
+                         ts_update=1e-2) for b in range(B)]
+for cs in conds:
+    cs.solve_variable_conditions(pars)
+es = kb.EnsembleSolver(sd, rd, calc)
+for rep in range(2):
+    es.prepare(conds, pars, synthetic_u0(S))
+    ms = es.run()
+    out_u, umax, status, stats = es.fetch()
+    print(f"rep{rep} run {ms:.1f} ms; attempts mean {stats[:,2].mean():.1f} max {stats[:,2].max()}; ok {np.sum(status==0)}/{B}")
