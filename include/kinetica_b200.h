@@ -72,9 +72,14 @@ int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, int64_t *nnz
 int32_t kb2_get_pattern(kb2_handle h, int64_t *colptr, int64_t *rowval);          /* CSC of P_J */
 int32_t kb2_get_ordering(kb2_handle h, int64_t *perm);
 int32_t kb2_get_lu_pattern(kb2_handle h, int64_t *rowptr, int64_t *colidx, int64_t *diagpos);
-/* panel plan of the numeric factorisation: out[8] = {padded storage slots, panels, units,
- * pivot steps, FMAs incl. padding, widest panel, column-map entries, block barriers per LU} */
+/* block plan of the numeric factorisation (replaces KLU's numeric phase bookkeeping):
+ * out[8] = {padded storage slots, panels, units (panel x column chunk), source-block tasks,
+ * FMAs incl. padding, widest panel, target-map entries, block barriers per LU (always 0)} */
 int32_t kb2_get_plan_stats(kb2_handle h, int64_t *out);
+/* raw plan tables for host-side verification; which: 0 p_row0, 1 p_nrows, 2 p_width, 3 p_next,
+ * 4 p_base, 5 p_cptr, 6 cols, 7 u_info (8 per unit), 8 t_info (4 per task), 9 map, 10 slot_of,
+ * 11 jslot, 12 diag_slot.  Returns the length (copies when cap is large enough), -1 on error. */
+int64_t kb2_get_plan_array(kb2_handle h, int32_t which, int32_t *out, int64_t cap);
 
 /* ---- calculators: PrecalculatedArrheniusCalculator (calculator.jl:164-238);
  * k = A*T^n*exp(-Ea/(R*T))*N_A*t_mult, harmonic cap with k_max unless k_max is NaN;
@@ -132,8 +137,10 @@ int32_t kb2_trisolve(kb2_handle h, int64_t B, const double *rhs, double *x);
  * 2 jacobian, 3 W-assembly+LU, 4 trisolve */
 int32_t kb2_time_kernel(kb2_handle h, int32_t which, int64_t B, int32_t iters, float *ms_avg);
 
-/* tuning: members per tile (power of two <= 32, 0 = auto) and threads per CTA (0 = auto) */
-int32_t kb2_set_tiling(kb2_handle h, int32_t members_per_tile, int32_t threads_per_cta);
+/* tuning: members per warp tile (1, 2 or 4; 0 = auto); the second argument is reserved (pass 0) */
+int32_t kb2_set_tiling(kb2_handle h, int32_t members_per_tile, int32_t reserved);
+/* members per warp tile and resident solve warps per SM of the last allocation / solve launch */
+int32_t kb2_get_launch_info(kb2_handle h, int32_t *members_per_tile, int32_t *ctas_per_sm);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,7 @@ SIGNATURES = {
     "kb2_get_ordering": (_i32, [_H, _pi64]),
     "kb2_get_lu_pattern": (_i32, [_H, _pi64, _pi64, _pi64]),
     "kb2_get_plan_stats": (_i32, [_H, _pi64]),
+    "kb2_get_plan_array": (_i64, [_H, _i32, _pi32, _i64]),
     "kb2_set_arrhenius": (_i32, [_H, _pf64, _pf64, _pf64, _f64, _f64]),
     "kb2_set_rate_table": (_i32, [_H, _i64, _pf64, _pf64]),
     "kb2_set_profiles": (_i32, [_H, _i64, _pi32, _pf64]),
@@ -49,6 +50,7 @@ SIGNATURES = {
     "kb2_trisolve": (_i32, [_H, _i64, _pf64, _pf64]),
     "kb2_time_kernel": (_i32, [_H, _i32, _i64, _i32, C.POINTER(C.c_float)]),
     "kb2_set_tiling": (_i32, [_H, _i32, _i32]),
+    "kb2_get_launch_info": (_i32, [_H, _pi32, _pi32]),
 }
 
 _lib = None
@@ -150,8 +152,30 @@ class Handle:
     def get_plan_stats(self):
         out = np.zeros(8, dtype=np.int64)
         self._ck(self._lib.kb2_get_plan_stats(self._h, _i(out)))
-        return dict(zip(["padded", "panels", "units", "steps", "fma_padded", "max_width", "map_entries", "barriers_per_lu"],
+        return dict(zip(["padded", "panels", "units", "tasks", "fma_padded", "max_width", "map_entries", "barriers_per_lu"],
                         map(int, out)))
+
+    PLAN_ARRAYS = ["p_row0", "p_nrows", "p_width", "p_next", "p_base", "p_cptr", "cols", "u_info", "t_info", "map",
+                   "slot_of", "jslot", "diag_slot"]
+
+    def get_plan(self):
+        """The raw block-plan tables (host-side verification of the factorisation schedule)."""
+        out = {}
+        for which, name in enumerate(self.PLAN_ARRAYS):
+            n = int(self._lib.kb2_get_plan_array(self._h, which, None, 0))
+            if n < 0:
+                raise Kb2Error("plan table %s unavailable" % name)
+            a = np.zeros(max(n, 1), dtype=np.int32)
+            self._lib.kb2_get_plan_array(self._h, which, a.ctypes.data_as(_pi32), n)
+            out[name] = a[:n]
+        out["u_info"] = out["u_info"].reshape(-1, 8)
+        out["t_info"] = out["t_info"].reshape(-1, 4)
+        return out
+
+    def get_launch_info(self):
+        a, b = _i32(), _i32()
+        self._ck(self._lib.kb2_get_launch_info(self._h, C.byref(a), C.byref(b)))
+        return {"members_per_tile": a.value, "ctas_per_sm": b.value}
 
     def get_lu_pattern(self):
         rowptr = np.zeros(self.S + 1, dtype=np.int64)
@@ -197,8 +221,8 @@ class Handle:
         self._ck(self._lib.kb2_set_member_stops(self._h, st.shape[0], st.shape[1], cnt.ctypes.data_as(_pi32),
                                                 _f(st), fl.ctypes.data_as(_pi32)))
 
-    def set_tiling(self, members_per_tile=0, threads_per_cta=0):
-        self._ck(self._lib.kb2_set_tiling(self._h, members_per_tile, threads_per_cta))
+    def set_tiling(self, members_per_tile=0, reserved=0):
+        self._ck(self._lib.kb2_set_tiling(self._h, members_per_tile, reserved))
 
     # ---- solve ----
     def solve_prepare(self, B, u0, t0, abstol, reltol, dtmin, maxiters, ban_negatives, Ns):

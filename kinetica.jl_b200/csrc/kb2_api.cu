@@ -46,7 +46,11 @@ struct kb2_ctx {
     int64_t ens_B = -1, ens_Ns = -1;
     size_t ens_fixed = 0;
     int *d_counter = nullptr;
-    int mb_user = 0, nt_user = 0, variant = 0, last_ctas_per_sm = 0;
+    int mb_user = 0, last_ctas_per_sm = 0;
+    int ens_mb = 0;               // members per warp tile of the current ensemble allocation
+    double *stage = nullptr;      // device staging for layout conversion (caller rows <-> tiles)
+    size_t stage_cap = 0;
+    double *scal = nullptr;       // [Bp] per-member scalars of the kernel-level entry points
     bool prepared = false;
 };
 
@@ -117,6 +121,7 @@ extern "C" int32_t kb2_destroy(kb2_handle h)
     cudaStreamSynchronize(h->stream);
     free_pool(h->net_allocs);
     free_pool(h->ens_allocs);
+    cudaFree(h->stage);
     cudaFree(h->d_counter);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
@@ -128,12 +133,14 @@ extern "C" int32_t kb2_destroy(kb2_handle h)
 extern "C" const char *kb2_last_error(kb2_handle h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" int64_t kb2_launch_count(kb2_handle h) { return h ? h->launches : 0; }
 
-extern "C" int32_t kb2_set_tiling(kb2_handle h, int32_t mb, int32_t nt)
+extern "C" int32_t kb2_set_tiling(kb2_handle h, int32_t mb, int32_t reserved)
 {
     if (!h) return 1;
-    if (mb != 0 && (mb < 1 || mb > 16 || (mb & (mb - 1)))) FAIL(h, "members_per_tile must be a power of two <= 16");
-    if (nt != 0 && nt != 1) FAIL(h, "second argument selects the register-budget variant: 0 or 1");
-    h->mb_user = mb; h->variant = nt;
+    (void)reserved;
+    if (mb != 0 && mb != 1 && mb != 2 && mb != 4) FAIL(h, "members_per_tile must be 0 (auto), 1, 2 or 4");
+    h->mb_user = mb;
+    h->ens_B = -1;            // the tile size is baked into the device layout
+    h->prepared = false;
     return 0;
 }
 
@@ -175,10 +182,10 @@ static int upload_network(kb2_ctx *h)
     CU(h, cudaSetDevice(h->device));
     free_pool(h->net_allocs);
     const Symbolic &s = h->sym;
+    const PanelPlan &pp = s.panels;
     DevNet &d = h->dn;
     d = DevNet{};
-    d.S = (int)h->net.S; d.R = (int)h->net.R; d.nnzJ = (int)s.nnzJ; d.nnzLU = (int)s.nnzLU;
-    d.max_rowlen = s.max_rowlen;
+    d.S = (int)h->net.S; d.R = (int)h->net.R; d.nnzJ = (int)s.nnzJ;
     int rc = 0;
     auto &P = h->net_allocs;
     const int32_t *rd = nullptr;
@@ -191,26 +198,18 @@ static int upload_network(kb2_ctx *h)
     rc |= dev_upload(h, P, s.jt_ptr.data(), s.jt_ptr.size(), &d.jt_ptr);
     rc |= dev_upload(h, P, s.jt_rxn.data(), s.jt_rxn.size(), &d.jt_rxn);
     rc |= dev_upload(h, P, s.jt_pack.data(), s.jt_pack.size(), &d.jt_pack);
-    rc |= dev_upload(h, P, s.lu_rowptr.data(), s.lu_rowptr.size(), &d.rowptr);
-    rc |= dev_upload(h, P, s.lu_colidx.data(), s.lu_colidx.size(), &d.colidx);
-    rc |= dev_upload(h, P, s.lu_diagpos.data(), s.lu_diagpos.size(), &d.diagpos);
+    rc |= dev_upload(h, P, s.rhs_order.data(), s.rhs_order.size(), &d.rhs_order);
+    rc |= dev_upload(h, P, s.j_order.data(), s.j_order.size(), &d.j_order);
+    d.rhs_nlong = s.rhs_nlong; d.j_nlong = s.j_nlong;
+    rc |= dev_upload(h, P, pp.jslot.data(), pp.jslot.size(), &d.jslot);
+    rc |= dev_upload(h, P, pp.diag_slot.data(), pp.diag_slot.size(), &d.diag_slot);
     rc |= dev_upload(h, P, perm32.data(), perm32.size(), &d.perm);
-    rc |= dev_upload(h, P, s.tgt_off.data(), s.tgt_off.size(), &d.tgt_off);
-    rc |= dev_upload(h, P, s.tgt.data(), s.tgt.size(), &d.tgt);
-    // panel plan: the LU value storage is the padded panel layout
+    // block plan: the LU value storage is the padded panel layout
     {
-        const PanelPlan &pp = s.panels;
         DevPlan &q = h->dp;
         q = DevPlan{};
-        q.npanels = (int)pp.p_row0.size(); q.nunits = (int)pp.units.size(); q.padded = (int)pp.padded;
-        q.dbg = getenv("KB2_DBG") ? atoi(getenv("KB2_DBG")) : 0;
-        std::vector<int32_t> up, ux0, ux1, us0, unp, une, um0, ud, ub0, unb;
-        for (const auto &u : pp.units) {
-            up.push_back(u.panel); ux0.push_back(u.x0); ux1.push_back(u.x1); us0.push_back(u.step0);
-            unp.push_back(u.n_pre); une.push_back(u.n_ext); um0.push_back(u.map0);
-            ud.push_back(u.diag_here ? 1 : (u.diag_before ? 2 : 0));
-            ub0.push_back(u.block0); unb.push_back(u.n_blocks);
-        }
+        q.npanels = (int)pp.p_row0.size(); q.nunits = (int)pp.n_units(); q.padded = (int)pp.padded;
+        const int32_t *ui = nullptr, *ti = nullptr;
         rc |= dev_upload(h, P, pp.p_row0.data(), pp.p_row0.size(), &q.p_row0);
         rc |= dev_upload(h, P, pp.p_nrows.data(), pp.p_nrows.size(), &q.p_nrows);
         rc |= dev_upload(h, P, pp.p_width.data(), pp.p_width.size(), &q.p_width);
@@ -218,25 +217,10 @@ static int upload_network(kb2_ctx *h)
         rc |= dev_upload(h, P, pp.p_base.data(), pp.p_base.size(), &q.p_base);
         rc |= dev_upload(h, P, pp.p_cptr.data(), pp.p_cptr.size(), &q.p_cptr);
         rc |= dev_upload(h, P, pp.cols.data(), pp.cols.size(), &q.cols);
-        rc |= dev_upload(h, P, up.data(), up.size(), &q.u_panel);
-        rc |= dev_upload(h, P, ux0.data(), ux0.size(), &q.u_x0);
-        rc |= dev_upload(h, P, ux1.data(), ux1.size(), &q.u_x1);
-        rc |= dev_upload(h, P, us0.data(), us0.size(), &q.u_step0);
-        rc |= dev_upload(h, P, unp.data(), unp.size(), &q.u_npre);
-        rc |= dev_upload(h, P, une.data(), une.size(), &q.u_next);
-        rc |= dev_upload(h, P, um0.data(), um0.size(), &q.u_map0);
-        rc |= dev_upload(h, P, ud.data(), ud.size(), &q.u_diag);
-        rc |= dev_upload(h, P, ub0.data(), ub0.size(), &q.u_block0);
-        rc |= dev_upload(h, P, unb.data(), unb.size(), &q.u_nblocks);
-        rc |= dev_upload(h, P, pp.b_info.data(), pp.b_info.size(), &q.b_info);
-        rc |= dev_upload(h, P, pp.b_idx.data(), pp.b_idx.size(), &q.b_idx);
-        rc |= dev_upload(h, P, pp.s_e.data(), pp.s_e.size(), &q.s_e);
-        rc |= dev_upload(h, P, pp.s_k.data(), pp.s_k.size(), &q.s_k);
-        rc |= dev_upload(h, P, pp.s_meta.data(), pp.s_meta.size(), &q.s_meta);
-        rc |= dev_upload(h, P, pp.s_idx.data(), pp.s_idx.size(), &q.s_idx);
-        // W assembly runs over the padded storage
-        rc |= dev_upload(h, P, pp.slot_src.data(), pp.slot_src.size(), &d.slot_src);
-        d.nnzLU = (int)pp.padded;
+        rc |= dev_upload(h, P, pp.u_info.data(), pp.u_info.size(), &ui);
+        rc |= dev_upload(h, P, pp.t_info.data(), pp.t_info.size(), &ti);
+        rc |= dev_upload(h, P, pp.map.data(), pp.map.size(), &q.map);
+        q.u_info = (const int4 *)ui; q.t_info = (const int4 *)ti;
     }
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
@@ -278,11 +262,35 @@ extern "C" int32_t kb2_get_plan_stats(kb2_handle h, int64_t *out)
 {
     if (!h || !h->sym.ready) return 1;
     const PanelPlan &pp = h->sym.panels;
-    out[0] = pp.padded; out[1] = (int64_t)pp.p_row0.size(); out[2] = (int64_t)pp.units.size();
-    out[3] = (int64_t)pp.s_e.size(); out[4] = pp.n_fma_padded; out[5] = pp.max_width;
-    out[6] = (int64_t)pp.s_idx.size(); out[7] = 0;
-    for (const auto &u : pp.units) out[7] += u.n_ext + (u.diag_here ? pp.p_nrows[u.panel] - 1 : 0);   // block barriers per LU
+    out[0] = pp.padded; out[1] = (int64_t)pp.p_row0.size(); out[2] = pp.n_units();
+    out[3] = pp.n_tasks(); out[4] = pp.n_fma_padded; out[5] = pp.max_width;
+    out[6] = (int64_t)pp.map.size(); out[7] = 0;     // no block barriers: warps never synchronise with each other
     return 0;
+}
+
+extern "C" int64_t kb2_get_plan_array(kb2_handle h, int32_t which, int32_t *out, int64_t cap)
+{
+    if (!h || !h->sym.ready) return -1;
+    const PanelPlan &pp = h->sym.panels;
+    const std::vector<int32_t> *v = nullptr;
+    switch (which) {
+    case 0: v = &pp.p_row0; break;
+    case 1: v = &pp.p_nrows; break;
+    case 2: v = &pp.p_width; break;
+    case 3: v = &pp.p_next; break;
+    case 4: v = &pp.p_base; break;
+    case 5: v = &pp.p_cptr; break;
+    case 6: v = &pp.cols; break;
+    case 7: v = &pp.u_info; break;
+    case 8: v = &pp.t_info; break;
+    case 9: v = &pp.map; break;
+    case 10: v = &pp.slot_of; break;
+    case 11: v = &pp.jslot; break;
+    case 12: v = &pp.diag_slot; break;
+    default: return -1;
+    }
+    if (out && cap >= (int64_t)v->size()) std::copy(v->begin(), v->end(), out);
+    return (int64_t)v->size();
 }
 
 extern "C" int32_t kb2_get_pattern(kb2_handle h, int64_t *colptr, int64_t *rowval)
@@ -400,6 +408,16 @@ extern "C" int32_t kb2_set_member_stops(kb2_handle h, int64_t B, int64_t nstops_
 }
 
 // ---- ensemble state -------------------------------------------------------------------------
+static int pick_mb(kb2_ctx *h, int64_t B)
+{
+    if (h->mb_user) return h->mb_user;
+    // four members per warp tile (32-byte sectors fully used) unless the ensemble is too small to
+    // give every SM a few warps
+    int mb = 4;
+    while (mb > 1 && (B + mb - 1) / mb < (int64_t)4 * h->sm_count) mb >>= 1;
+    return mb;
+}
+
 static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
 {
     if (h->device < 0) FAIL(h, "host-only handle: no CUDA device, and there is no CPU fallback");
@@ -412,74 +430,87 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
     DevEns &e = h->de;
     e = DevEns{};
     e.B = (int)B;
-    e.Bp = (int)((B + 31) / 32 * 32);
-    const size_t Bp = e.Bp, S = h->net.S, R = h->net.R;
+    e.Bp = (int)((B + 31) / 32 * 32);       // member count of the per-member tables (multiple of every tile size)
+    e.MB = pick_mb(h, B);
+    const size_t Bt = (size_t)(B + e.MB - 1) / e.MB * e.MB, S = h->net.S, R = h->net.R, Bp = e.Bp;
     auto &P = h->ens_allocs;
     int rc = 0;
-    rc |= dev_alloc(h, P, S * Bp, &e.u);
-    rc |= dev_alloc(h, P, S * Bp, &e.ua);
-    rc |= dev_alloc(h, P, S * Bp, &e.rv);
-    rc |= dev_alloc(h, P, S * Bp, &e.y);
-    for (int q = 0; q < 6; ++q) rc |= dev_alloc(h, P, S * Bp, &e.K[q]);
-    rc |= dev_alloc(h, P, R * Bp, &e.k);
-    rc |= dev_alloc(h, P, (size_t)h->sym.panels.padded * Bp, &e.lu);
-    rc |= dev_alloc(h, P, S * Bp, &e.invd);
-    rc |= dev_alloc(h, P, (size_t)std::max<int64_t>(Ns, 1) * S * Bp, &e.out_u);
-    rc |= dev_alloc(h, P, S * Bp, &e.out_umax);
+    rc |= dev_alloc(h, P, S * Bt, &e.u);
+    rc |= dev_alloc(h, P, S * Bt, &e.ua);
+    rc |= dev_alloc(h, P, S * Bt, &e.rv);
+    rc |= dev_alloc(h, P, S * Bt, &e.y);
+    for (int q = 0; q < 6; ++q) rc |= dev_alloc(h, P, S * Bt, &e.K[q]);
+    rc |= dev_alloc(h, P, R * Bt, &e.k);
+    rc |= dev_alloc(h, P, R * Bt, &e.rate);
+    rc |= dev_alloc(h, P, (size_t)h->sym.panels.padded * Bt, &e.lu);
+    rc |= dev_alloc(h, P, S * Bt, &e.invd);
+    rc |= dev_alloc(h, P, (size_t)std::max<int64_t>(Ns, 1) * S * Bt, &e.out_u);
+    rc |= dev_alloc(h, P, S * Bt, &e.out_umax);
     rc |= dev_alloc(h, P, Bp, &e.status);
     rc |= dev_alloc(h, P, Bp * 8, &e.stats);
+    rc |= dev_alloc(h, P, Bp, &h->scal);
     if (rc) { free_pool(h->ens_allocs); return rc; }
     e.Ns = (int)Ns;
-    h->ens_B = B; h->ens_Ns = Ns;
+    h->ens_B = B; h->ens_Ns = Ns; h->ens_mb = e.MB;
     h->ens_fixed = P.size();
     return 0;
 }
 
-// host [rows][B] -> device [rows][Bp]
-static int up2d(kb2_ctx *h, double *dst, const double *src, size_t rows, size_t B, size_t Bp)
-{
-    CU(h, cudaMemcpy2DAsync(dst, Bp * 8, src, B * 8, B * 8, rows, cudaMemcpyHostToDevice, h->stream));
-    return 0;
-}
-static int down2d(kb2_ctx *h, double *dst, const double *src, size_t rows, size_t B, size_t Bp)
-{
-    CU(h, cudaMemcpy2DAsync(dst, B * 8, src, Bp * 8, B * 8, rows, cudaMemcpyDeviceToHost, h->stream));
-    return 0;
-}
-
-static void pick_tiling(kb2_ctx *h, int64_t B, bool need_w, int *mb_out, int *nt_out, size_t *smem_out)
-{
-    (void)need_w;
-    int mb = h->mb_user;
-    if (mb == 0) {
-        // 8 members per tile (64-byte coalesced segments, 256 threads) unless the ensemble is too
-        // small to give every SM a tile
-        mb = 8;
-        while (mb > 1 && (B + mb - 1) / mb < (int64_t)h->sm_count) mb >>= 1;
-    }
-    if (mb > 16) mb = 16;
-    const int nt = 32 * mb;          // thread = (member, column lane): 32 column lanes per member
-    *mb_out = mb; *nt_out = nt;
-    *smem_out = (lu_smem_doubles(nt, mb) + (size_t)PR * mb * mb + nt) * 8;
-}
-
-// register-budget variants: A = 128 registers/thread (16/MB CTAs per SM), B = fewer CTAs, more registers
-#define DISPATCH_MBV(mb, variant, ...)                                                        \
-    switch (mb) {                                                                             \
-    case 1: if (variant) { constexpr int MB = 1, MINB = 12; __VA_ARGS__; } else { constexpr int MB = 1, MINB = 16; __VA_ARGS__; } break; \
-    case 2: if (variant) { constexpr int MB = 2, MINB = 6; __VA_ARGS__; } else { constexpr int MB = 2, MINB = 8; __VA_ARGS__; } break;   \
-    case 4: if (variant) { constexpr int MB = 4, MINB = 3; __VA_ARGS__; } else { constexpr int MB = 4, MINB = 4; __VA_ARGS__; } break;   \
-    case 8: if (variant) { constexpr int MB = 8, MINB = 1; __VA_ARGS__; } else { constexpr int MB = 8, MINB = 2; __VA_ARGS__; } break;   \
-    default: { constexpr int MB = 16, MINB = 1; __VA_ARGS__; } break;                         \
-    }
 #define DISPATCH_MB(mb, ...)                                          \
     switch (mb) {                                                     \
     case 1: { constexpr int MB = 1; __VA_ARGS__; } break;             \
     case 2: { constexpr int MB = 2; __VA_ARGS__; } break;             \
-    case 4: { constexpr int MB = 4; __VA_ARGS__; } break;             \
-    case 8: { constexpr int MB = 8; __VA_ARGS__; } break;             \
-    default: { constexpr int MB = 16; __VA_ARGS__; } break;           \
+    default: { constexpr int MB = 4; __VA_ARGS__; } break;            \
     }
+
+static int ensure_stage(kb2_ctx *h, size_t doubles)
+{
+    if (h->stage_cap >= doubles) return 0;
+    if (h->stage) { CU(h, cudaStreamSynchronize(h->stream)); cudaFree(h->stage); h->stage = nullptr; h->stage_cap = 0; }
+    CU(h, cudaMalloc((void **)&h->stage, std::max<size_t>(doubles, 1) * 8));
+    h->stage_cap = doubles;
+    return 0;
+}
+
+static int conv_grid(kb2_ctx *h, size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16); }
+
+// host rows [nrows][B] -> device tiles [tile][nrows][MB]
+static int up_tiles(kb2_ctx *h, double *tiles, const double *src, size_t nrows, size_t B)
+{
+    const DevEns &e = h->de;
+    int rc = ensure_stage(h, nrows * B);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(h->stage, src, nrows * B * 8, cudaMemcpyHostToDevice, h->stream));
+    const int Bt = (int)((B + e.MB - 1) / e.MB * e.MB);
+    DISPATCH_MB(e.MB, (k_rows_to_tiles<MB><<<conv_grid(h, nrows * Bt), 256, 0, h->stream>>>(h->stage, tiles, nrows, (int)B, Bt, B)));
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return 0;
+}
+
+// device tiles -> host rows [nrows][B]
+static int down_tiles(kb2_ctx *h, double *dst, const double *tiles, size_t nrows, size_t B)
+{
+    const DevEns &e = h->de;
+    int rc = ensure_stage(h, nrows * B);
+    if (rc) return rc;
+    DISPATCH_MB(e.MB, (k_tiles_to_rows<MB><<<conv_grid(h, nrows * B), 256, 0, h->stream>>>(tiles, h->stage, nrows, (int)B)));
+    h->launches++;
+    CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(dst, h->stage, nrows * B * 8, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+static int up_scal(kb2_ctx *h, const double *v, int64_t B, double fill)
+{
+    std::vector<double> p(h->de.Bp, fill);
+    std::copy(v, v + B, p.begin());
+    CU(h, cudaMemcpyAsync(h->scal, p.data(), p.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));     // p goes out of scope
+    return 0;
+}
+
+static int n_tiles(const DevEns &e) { return (e.B + e.MB - 1) / e.MB; }
 
 template <class K>
 static int set_smem(kb2_ctx *h, K kern, size_t smem)
@@ -496,17 +527,12 @@ extern "C" int32_t kb2_eval_k(kb2_handle h, int64_t B, const double *T, double *
     int rc = ensure_ensemble(h, B, 1);
     if (rc) return rc;
     DevEns &e = h->de;
-    std::vector<double> Tp(e.Bp, 300.0);
-    std::copy(T, T + B, Tp.begin());
-    CU(h, cudaMemcpyAsync(e.y, Tp.data(), e.Bp * 8, cudaMemcpyHostToDevice, h->stream));
-    int mb, nt; size_t smem;
-    pick_tiling(h, B, false, &mb, &nt, &smem);
-    const int ntiles = e.Bp / mb;
-    DISPATCH_MB(mb, (k_rates<MB><<<std::min(ntiles, 8 * h->sm_count), nt, 0, h->stream>>>(h->dn, e, e.y, ntiles)));
+    if ((rc = up_scal(h, T, B, 300.0))) return rc;
+    const int ntiles = n_tiles(e);
+    DISPATCH_MB(e.MB, (k_rates<MB><<<std::min(ntiles, 32 * h->sm_count), 32, 0, h->stream>>>(h->dn, h->dp, e, h->scal, ntiles)));
     h->launches++;
     CU(h, cudaGetLastError());
-    rc = down2d(h, k_out, e.k, h->net.R, B, e.Bp);
-    if (rc) return rc;
+    if ((rc = down_tiles(h, k_out, e.k, h->net.R, B))) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -515,6 +541,7 @@ extern "C" int32_t kb2_eval_profile(kb2_handle h, int64_t B, int64_t nt, const d
 {
     if (!h) return 1;
     if (h->Bprof != B) FAIL(h, "kb2_set_profiles must be called with the same B first");
+    if (h->device < 0) FAIL(h, "host-only handle: no CUDA device, and there is no CPU fallback");
     CU(h, cudaSetDevice(h->device));
     std::vector<void *> pool;
     const int32_t *dk; const double *dp, *dt; double *dx;
@@ -537,8 +564,8 @@ static int upload_uk(kb2_ctx *h, int64_t B, const double *u, const double *k)
 {
     DevEns &e = h->de;
     int rc = 0;
-    if (u) rc |= up2d(h, e.u, u, h->net.S, B, e.Bp);
-    if (k) rc |= up2d(h, e.k, k, h->net.R, B, e.Bp);
+    if (u) rc |= up_tiles(h, e.u, u, h->net.S, B);
+    if (k) rc |= up_tiles(h, e.k, k, h->net.R, B);
     return rc;
 }
 
@@ -549,13 +576,11 @@ extern "C" int32_t kb2_eval_rhs(kb2_handle h, int64_t B, const double *u, const 
     if (rc) return rc;
     if ((rc = upload_uk(h, B, u, k))) return rc;
     DevEns &e = h->de;
-    int mb, nt; size_t smem;
-    pick_tiling(h, B, false, &mb, &nt, &smem);
-    const int ntiles = e.Bp / mb;
-    DISPATCH_MB(mb, (k_rhs<MB><<<std::min(ntiles, 8 * h->sm_count), nt, 0, h->stream>>>(h->dn, e, ntiles)));
+    const int ntiles = n_tiles(e);
+    DISPATCH_MB(e.MB, (k_rhs<MB><<<std::min(ntiles, 32 * h->sm_count), 32, 0, h->stream>>>(h->dn, h->dp, e, ntiles)));
     h->launches++;
     CU(h, cudaGetLastError());
-    if ((rc = down2d(h, du, e.rv, h->net.S, B, e.Bp))) return rc;
+    if ((rc = down_tiles(h, du, e.rv, h->net.S, B))) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -567,45 +592,39 @@ extern "C" int32_t kb2_eval_jac(kb2_handle h, int64_t B, const double *u, const 
     if (rc) return rc;
     if ((rc = upload_uk(h, B, u, k))) return rc;
     DevEns &e = h->de;
-    int mb, nt; size_t smem;
-    pick_tiling(h, B, false, &mb, &nt, &smem);
-    const int ntiles = e.Bp / mb;
-    // nnzJ <= nnzLU: the LU value array doubles as scratch for the CSC values
-    DISPATCH_MB(mb, (k_jac<MB><<<std::min(ntiles, 8 * h->sm_count), nt, 0, h->stream>>>(h->dn, e, e.lu, ntiles)));
+    const int ntiles = n_tiles(e);
+    // nnzJ <= padded: the LU value storage of a tile doubles as scratch for its CSC values; the
+    // tile stride is the LU stride, so bring the whole storage back and keep the first nnzJ rows
+    DISPATCH_MB(e.MB, (k_jac<MB><<<std::min(ntiles, 32 * h->sm_count), 32, 0, h->stream>>>(h->dn, h->dp, e, ntiles)));
     h->launches++;
     CU(h, cudaGetLastError());
-    if ((rc = down2d(h, Jval, e.lu, (size_t)h->sym.nnzJ, B, e.Bp))) return rc;
+    std::vector<double> tmp((size_t)h->sym.panels.padded * B);
+    if ((rc = down_tiles(h, tmp.data(), e.lu, (size_t)h->sym.panels.padded, B))) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
+    std::copy(tmp.begin(), tmp.begin() + (size_t)h->sym.nnzJ * B, Jval);
     return 0;
 }
 
-static int launch_factor(kb2_ctx *h, int64_t B, const double *d_hg, int mode = 3)
+static int launch_factor(kb2_ctx *h, const double *d_hg, int mode = 3)
 {
     DevEns &e = h->de;
-    int mb, nt; size_t smem;
-    pick_tiling(h, B, true, &mb, &nt, &smem);
-    const int ntiles = e.Bp / mb;
-    DISPATCH_MBV(mb, h->variant, {
-        int r = set_smem(h, k_factor<MB, MINB>, smem);
+    const int ntiles = n_tiles(e);
+    const size_t smem = lu_smem_bytes(e.MB);
+    DISPATCH_MB(e.MB, {
+        int r = set_smem(h, k_factor<MB>, smem);
         if (r) return r;
-        k_factor<MB, MINB><<<ntiles, nt, smem, h->stream>>>(h->dn, h->dp, e, d_hg, ntiles, mode);
+        k_factor<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, d_hg, ntiles, mode);
     });
     h->launches++;
     CU(h, cudaGetLastError());
     return 0;
 }
 
-static int launch_trisolve(kb2_ctx *h, int64_t B)
+static int launch_trisolve(kb2_ctx *h)
 {
     DevEns &e = h->de;
-    int mb, nt; size_t smem;
-    pick_tiling(h, B, true, &mb, &nt, &smem);
-    const int ntiles = e.Bp / mb;
-    DISPATCH_MBV(mb, h->variant, {
-        int r = set_smem(h, k_trisolve<MB, MINB>, smem);
-        if (r) return r;
-        k_trisolve<MB, MINB><<<ntiles, nt, smem, h->stream>>>(h->dn, h->dp, e, ntiles);
-    });
+    const int ntiles = n_tiles(e);
+    DISPATCH_MB(e.MB, (k_trisolve<MB><<<std::min(ntiles, 32 * h->sm_count), 32, 0, h->stream>>>(h->dn, h->dp, e, ntiles)));
     h->launches++;
     CU(h, cudaGetLastError());
     return 0;
@@ -619,15 +638,13 @@ extern "C" int32_t kb2_factor(kb2_handle h, int64_t B, const double *u, const do
     if (rc) return rc;
     if ((rc = upload_uk(h, B, u, k))) return rc;
     DevEns &e = h->de;
-    std::vector<double> hp(e.Bp, 1.0);
-    std::copy(hg_inv, hg_inv + B, hp.begin());
-    CU(h, cudaMemcpyAsync(e.y, hp.data(), e.Bp * 8, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = launch_factor(h, B, e.y))) return rc;
+    if ((rc = up_scal(h, hg_inv, B, 1.0))) return rc;
+    if ((rc = launch_factor(h, h->scal))) return rc;
     if (lu_out) {
-        // device storage is the padded panel layout: bring it back and gather the exact pattern
+        // device storage is the padded block layout: bring it back and gather the exact pattern
         const PanelPlan &pp = h->sym.panels;
         std::vector<double> tmp((size_t)pp.padded * B);
-        if ((rc = down2d(h, tmp.data(), e.lu, (size_t)pp.padded, B, e.Bp))) return rc;
+        if ((rc = down_tiles(h, tmp.data(), e.lu, (size_t)pp.padded, B))) return rc;
         CU(h, cudaStreamSynchronize(h->stream));
         for (int64_t q = 0; q < h->sym.nnzLU; ++q)
             std::copy(tmp.begin() + (size_t)pp.slot_of[q] * B, tmp.begin() + ((size_t)pp.slot_of[q] + 1) * B, lu_out + q * B);
@@ -641,10 +658,10 @@ extern "C" int32_t kb2_trisolve(kb2_handle h, int64_t B, const double *rhs, doub
     if (!h) return 1;
     if (h->ens_B != B) FAIL(h, "kb2_trisolve must follow kb2_factor with the same B");
     DevEns &e = h->de;
-    int rc = up2d(h, e.rv, rhs, h->net.S, B, e.Bp);
+    int rc = up_tiles(h, e.rv, rhs, h->net.S, B);
     if (rc) return rc;
-    if ((rc = launch_trisolve(h, B))) return rc;
-    if ((rc = down2d(h, x, e.ua, h->net.S, B, e.Bp))) return rc;
+    if ((rc = launch_trisolve(h))) return rc;
+    if ((rc = down_tiles(h, x, e.ua, h->net.S, B))) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -654,26 +671,24 @@ extern "C" int32_t kb2_time_kernel(kb2_handle h, int32_t which, int64_t B, int32
     if (!h) return 1;
     if (h->ens_B != B) FAIL(h, "call an eval/solve entry point with this B first so data is resident");
     DevEns &e = h->de;
-    int mb, nt; size_t smem;
-    pick_tiling(h, B, false, &mb, &nt, &smem);
-    const int ntiles = e.Bp / mb;
-    const int grid = std::min(ntiles, 8 * h->sm_count);
-    // hg_inv / T source: reuse `invd`-independent scratch y filled with a benign constant
+    const int ntiles = n_tiles(e);
+    const int grid = std::min(ntiles, 32 * h->sm_count);
     if (which == 0 || which == 3 || which == 5 || which == 6) {
         std::vector<double> c(e.Bp, which == 0 ? 1000.0 : 1.0e6);
-        CU(h, cudaMemcpyAsync(e.y, c.data(), e.Bp * 8, cudaMemcpyHostToDevice, h->stream));
+        int rc = up_scal(h, c.data(), e.Bp, 1.0);
+        if (rc) return rc;
     }
     for (int it = -2; it < iters; ++it) {
         if (it == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
         int rc = 0;
         switch (which) {
-        case 0: DISPATCH_MB(mb, (k_rates<MB><<<grid, nt, 0, h->stream>>>(h->dn, e, e.y, ntiles))); h->launches++; break;
-        case 1: DISPATCH_MB(mb, (k_rhs<MB><<<grid, nt, 0, h->stream>>>(h->dn, e, ntiles))); h->launches++; break;
-        case 2: DISPATCH_MB(mb, (k_jac<MB><<<grid, nt, 0, h->stream>>>(h->dn, e, e.lu, ntiles))); h->launches++; break;
-        case 3: rc = launch_factor(h, B, e.y); break;
-        case 4: rc = launch_trisolve(h, B); break;
-        case 5: rc = launch_factor(h, B, e.y, 1); break;   // W assembly only
-        case 6: rc = launch_factor(h, B, e.y, 2); break;   // LU only (on whatever the storage holds)
+        case 0: DISPATCH_MB(e.MB, (k_rates<MB><<<grid, 32, 0, h->stream>>>(h->dn, h->dp, e, h->scal, ntiles))); h->launches++; break;
+        case 1: DISPATCH_MB(e.MB, (k_rhs<MB><<<grid, 32, 0, h->stream>>>(h->dn, h->dp, e, ntiles))); h->launches++; break;
+        case 2: DISPATCH_MB(e.MB, (k_jac<MB><<<grid, 32, 0, h->stream>>>(h->dn, h->dp, e, ntiles))); h->launches++; break;
+        case 3: rc = launch_factor(h, h->scal); break;
+        case 4: rc = launch_trisolve(h); break;
+        case 5: rc = launch_factor(h, h->scal, 1); break;   // W assembly only
+        case 6: rc = launch_factor(h, h->scal, 2); break;   // LU only (on whatever the storage holds)
         default: FAIL(h, "unknown kernel id");
         }
         if (rc) return rc;
@@ -736,12 +751,16 @@ extern "C" int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, 
     if (rc) return rc;
     DevEns &e = h->de;
     const size_t Bp = e.Bp, S = h->net.S;
-    // u0 -> [S][Bp]
+    // u0 -> tile-major [tile][S][MB]
     {
-        std::vector<double> up(S * Bp, 0.0);
-        for (size_t i = 0; i < S; ++i)
-            for (int64_t b = 0; b < B; ++b) up[i * Bp + b] = u0[(size_t)(u0_stride ? b * u0_stride : 0) + i];
-        CU(h, cudaMemcpyAsync(e.u, up.data(), S * Bp * 8, cudaMemcpyHostToDevice, h->stream));
+        const size_t MB = e.MB, Bt = (size_t)(B + e.MB - 1) / e.MB * e.MB;
+        std::vector<double> up(S * Bt, 0.0);
+        for (int64_t b = 0; b < B; ++b) {
+            const double *src = u0 + (size_t)(u0_stride ? b * u0_stride : 0);
+            double *dst = up.data() + (size_t)(b / MB) * S * MB + b % MB;
+            for (size_t i = 0; i < S; ++i) dst[i * MB] = src[i];
+        }
+        CU(h, cudaMemcpyAsync(e.u, up.data(), S * Bt * 8, cudaMemcpyHostToDevice, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
     }
     // per-solve condition tables live at the tail of the ensemble pool: drop the previous ones
@@ -780,20 +799,20 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     if (!h->prepared) FAIL(h, "kb2_solve_prepare has not succeeded");
     CU(h, cudaSetDevice(h->device));
     DevEns &e = h->de;
-    int mb, nt; size_t smem;
-    pick_tiling(h, e.B, true, &mb, &nt, &smem);
-    const int ntiles = e.Bp / mb;
+    const int ntiles = n_tiles(e);
+    const size_t smem = lu_smem_bytes(e.MB);
     CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
     CU(h, cudaEventRecord(h->ev0, h->stream));
-    DISPATCH_MBV(mb, h->variant, {
-        int r = set_smem(h, k_solve<MB, MINB>, smem);
+    DISPATCH_MB(e.MB, {
+        int r = set_smem(h, k_solve<MB>, smem);
         if (r) return r;
         int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve<MB, MINB>, nt, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve<MB>, 32, smem);
         if (per_sm < 1) FAIL(h, "solve kernel does not fit on an SM");
         h->last_ctas_per_sm = per_sm;
+        // persistent warps: every resident slot pulls tiles from an atomic counter
         const int grid = std::min(ntiles, per_sm * h->sm_count);
-        k_solve<MB, MINB><<<grid, nt, smem, h->stream>>>(h->dn, h->dp, e, ntiles, h->d_counter);
+        k_solve<MB><<<grid, 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles, h->d_counter);
     });
     h->launches++;
     CU(h, cudaEventRecord(h->ev1, h->stream));
@@ -811,11 +830,13 @@ extern "C" int32_t kb2_solve_fetch(kb2_handle h, double *out_u, double *out_umax
     if (!h) return 1;
     if (h->ens_B <= 0) FAIL(h, "nothing to fetch");
     DevEns &e = h->de;
-    const size_t B = e.B, Bp = e.Bp, S = h->net.S;
+    const size_t B = e.B, S = h->net.S;
     int rc = 0;
-    if (out_u) rc |= down2d(h, out_u, e.out_u, (size_t)e.Ns * S, B, Bp);
-    if (out_umax) rc |= down2d(h, out_umax, e.out_umax, S, B, Bp);
-    if (rc) return rc;
+    if (out_u) {
+        if ((rc = down_tiles(h, out_u, e.out_u, (size_t)e.Ns * S, B))) return rc;
+        CU(h, cudaStreamSynchronize(h->stream));      // the staging buffer is reused below
+    }
+    if (out_umax && (rc = down_tiles(h, out_umax, e.out_umax, S, B))) return rc;
     if (status) CU(h, cudaMemcpyAsync(status, e.status, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     if (stats) CU(h, cudaMemcpyAsync(stats, e.stats, B * 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -838,10 +859,18 @@ extern "C" int32_t kb2_pack_results_device(kb2_handle h, double *final_bs_dev, d
     if (h->ens_B <= 0) FAIL(h, "nothing to pack");
     DevEns &e = h->de;
     const int S = (int)h->net.S;
-    dim3 grid((e.Bp + 31) / 32, (S + 31) / 32), block(32, 8);
-    if (final_bs_dev) { k_pack_bs<<<grid, block, 0, h->stream>>>(S, e.B, e.Bp, e.u, final_bs_dev); h->launches++; }
-    if (umax_bs_dev) { k_pack_bs<<<grid, block, 0, h->stream>>>(S, e.B, e.Bp, e.out_umax, umax_bs_dev); h->launches++; }
+    const int grid = conv_grid(h, (size_t)S * e.B);
+    if (final_bs_dev) { DISPATCH_MB(e.MB, (k_pack_bs<MB><<<grid, 256, 0, h->stream>>>(S, e.B, e.u, final_bs_dev))); h->launches++; }
+    if (umax_bs_dev) { DISPATCH_MB(e.MB, (k_pack_bs<MB><<<grid, 256, 0, h->stream>>>(S, e.B, e.out_umax, umax_bs_dev))); h->launches++; }
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int32_t kb2_get_launch_info(kb2_handle h, int32_t *members_per_tile, int32_t *ctas_per_sm)
+{
+    if (!h) return 1;
+    if (members_per_tile) *members_per_tile = h->ens_mb;
+    if (ctas_per_sm) *ctas_per_sm = h->last_ctas_per_sm;
     return 0;
 }

@@ -17,27 +17,32 @@ struct Network {
     std::vector<int32_t> net_ptr, net_idx, net_coef;  // net stoichiometry per reaction (zeros dropped)
 };
 
-// Panel plan of the register-blocked LU / panel triangular solves (kb2_panel.cpp).
+// Block plan of the supernodal (block Crout) LU and the panel triangular solves (kb2_panel.cpp).
+// Rows of the permuted L\U pattern are grouped into panels of <= PR consecutive rows sharing one
+// padded column pattern; the L part of a panel is a union of COMPLETE earlier panels (source
+// blocks), so every panel-panel update is a small dense  nr x nq  times  nq x ntargets  product.
 struct PanelPlan {
     static constexpr int PR = 8;      // rows per panel
-    static constexpr int CW = 128;    // columns per chunk (32 column lanes x 4 registers)
+    static constexpr int CW = 96;     // columns of a panel held in shared memory at a time (one chunk)
     bool ready = false;
     int64_t padded = 0, n_fma_padded = 0;
     int32_t max_width = 0;
+    // per panel: first row, rows, pattern width, position of the diagonal block in the pattern,
+    // first storage slot, offset of the pattern in `cols`
     std::vector<int32_t> p_row0, p_nrows, p_width, p_next, p_base, p_cptr, cols;
     std::vector<int32_t> row_panel, row_r;
-    std::vector<int32_t> slot_of;     // exact-pattern slot -> storage slot
-    std::vector<int32_t> slot_src;    // per storage slot: ((J entry + 1) << 1) | is_diagonal
-    std::vector<int32_t> diag_slot;   // per row
-    struct Unit { int32_t panel, x0, x1, step0, n_pre, n_ext, map0, n_maps, diag_here, diag_before, block0 = 0, n_blocks = 0; };
-    std::vector<Unit> units;
-    std::vector<int32_t> s_e, s_k, s_src, s_map, maps;
-    static constexpr int SEG = 64;    // source slots staged per step
-    static constexpr int NB = 4;      // steps per block (one barrier round)
-    std::vector<int32_t> b_info;      // [block] {first step (unit relative), steps, kind 0 pre / 1 in-chunk, owner lane}
-    std::vector<int32_t> b_idx;       // [block][32 column lanes][NB] packed byte-index words
-    std::vector<int32_t> s_meta;      // [step] {first source slot, slots, pivot column, flags}
-    std::vector<int32_t> s_idx;       // [step][32 column lanes] 4 x int8 index into the staged range (-1 none)
+    std::vector<int32_t> slot_of;     // exact-pattern slot -> storage slot  p_base + c*nr + r
+    std::vector<int32_t> jslot;       // Jacobian entry (CSC order) -> storage slot
+    std::vector<int32_t> diag_slot;   // per pivot row
+    // units = (panel, column chunk [x0,x1)); 8 ints each:
+    // {panel, x0, x1, first task, tasks, diagonal mode (0 later chunk, 1 in this chunk, 2 earlier chunk), 0, 0}
+    std::vector<int32_t> u_info;
+    // tasks = source blocks applied to a unit; 4 ints each:
+    // {source panel Q, position of Q's first column in the target pattern | in-chunk << 30, targets, first map entry}
+    std::vector<int32_t> t_info;
+    std::vector<int32_t> map;         // per target: (column position in Q's pattern) | (column position in the chunk << 16)
+    int64_t n_units() const { return (int64_t)u_info.size() / 8; }
+    int64_t n_tasks() const { return (int64_t)t_info.size() / 4; }
 };
 
 // Everything the kernels need that depends only on the network (shared by all members).
@@ -52,6 +57,11 @@ struct Symbolic {
     // --- device-ready int32 tables ---
     // RHS gather CSR by species: entries (reaction, net coefficient)
     std::vector<int32_t> rhs_ptr, rhs_rxn, rhs_coef;
+    // work order of the gather loops: rows / entries sorted by length, longest first; the first
+    // n_long of them are split across the lanes of a member, the rest go one per lane
+    static constexpr int RHS_LONG = 64, JAC_LONG = 16;
+    std::vector<int32_t> rhs_order, j_order;
+    int32_t rhs_nlong = 0, j_nlong = 0;
     // reaction descriptors: up to 3 distinct reactant species + exponents packed 8 bit each
     std::vector<int32_t> rdesc;                       // 4 ints per reaction
     // Jacobian terms by J entry (CSC order): (reaction, (coef*nu_l) << 2 | reactant slot)
@@ -59,9 +69,6 @@ struct Symbolic {
     // per LU slot: ((J entry + 1) << 1) | is_diagonal
     std::vector<int32_t> slot_src;
     std::vector<int32_t> lu_rowptr, lu_colidx, lu_diagpos;
-    // elimination schedule: for L slot p (row i, pivot k): targets of U(k,:) as offsets into row i
-    std::vector<uint32_t> tgt_off;                    // per slot (only L slots meaningful)
-    std::vector<int32_t> tgt;                         // n_fma entries
     int32_t max_rowlen = 0;
     PanelPlan panels;
 };

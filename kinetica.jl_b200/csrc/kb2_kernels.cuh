@@ -1,13 +1,15 @@
 // CUDA kernels of the kinetic-solve hot path (sm_100a).
 //
-// Layout: every ensemble array is [index][Bp] — species/reaction/slot-major, member-minor —
-// so that consecutive members are consecutive in memory and every warp-level access is a
-// full-sector coalesced FP64 load/store.  A CTA owns one *tile* of MB consecutive members
-// (MB in {1,2,4,8,16,32}); its threads are laid out as (m = tid % MB, slot = tid / MB): the
-// member index is the fast axis (coalescing), `slot` strides over species / reactions / LU
-// slots.  All index tables are shared by every member, so control flow is uniform inside a
-// tile and nothing diverges.  No atomics are used on the data path (gather CSR), results are
-// deterministic run to run.
+// Execution model: ONE WARP integrates one tile of MB consecutive ensemble members (MB in
+// {1,2,4}) from t0 to the end; lane = ln * MB + m with m the member inside the tile and ln one of
+// LN = 32/MB work lanes of that member.  Warps never synchronise with each other: no block
+// barriers anywhere on the path, only __syncwarp and shuffles, and a CTA is a single warp so the
+// scheduler can keep every tile of the ensemble resident at once.
+// Layout: every per-member array is tile-major [tile][index][MB] — species / reaction / LU-slot
+// major, member minor — so the lanes of a warp that work on the same index touch one MB*8-byte
+// segment (a full 32-byte sector for MB = 4) and consecutive indices are consecutive in memory.
+// All index tables are shared by every member, control flow is uniform inside a warp.  No atomics
+// on the data path (gather CSR), results are deterministic run to run.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -38,13 +40,13 @@ __constant__ double cC[6][6] = {
      -0.6058818238834054e+01, 0}};
 
 struct DevNet {
-    int S, R, nnzJ, nnzLU, max_rowlen;
+    int S, R, nnzJ;
     const int *rhs_ptr, *rhs_rxn, *rhs_coef;
     const int4 *rdesc;
     const int *jt_ptr, *jt_rxn, *jt_pack;
-    const int *slot_src, *rowptr, *colidx, *diagpos, *perm;
-    const unsigned *tgt_off;
-    const int *tgt;
+    const int *rhs_order, *j_order;        // work orders, longest first; the first n_long are split across lanes
+    int rhs_nlong, j_nlong;
+    const int *jslot, *diag_slot, *perm;   // storage slot of every Jacobian entry / pivot; perm[a] = species at pivot a
     // calculator
     int calc_mode;            // 0 Arrhenius, 1 rate table
     const double *A, *Ea, *n; // n may be null
@@ -52,9 +54,21 @@ struct DevNet {
     const double *ktab, *kinit;
 };
 
+// Block plan of the LU / triangular solves (kb2_panel.cpp), shared by all members.
+struct DevPlan {
+    int npanels, nunits, padded;
+    const int *p_row0, *p_nrows, *p_width, *p_next, *p_base, *p_cptr, *cols;
+    const int4 *u_info;       // 2 per unit: {panel, x0, x1, task0}, {ntask, dmode, 0, 0}
+    const int4 *t_info;       // {Q, lpos | inchunk << 30, ntargets, map0}
+    const int *map;           // (column position in Q) | (column position in the chunk << 16)
+};
+
+// Ensemble state.  Every per-member array is TILE-MAJOR: [tile][index][MB] with MB members per
+// tile (species / reaction / LU-slot major, member minor inside the tile), so one warp owns one
+// contiguous block per array and every access of the warp covers whole MB*8-byte segments.
 struct DevEns {
-    int B, Bp;
-    double *u, *ua, *rv, *y, *K[6], *k, *lu, *invd;
+    int B, Bp, MB;
+    double *u, *ua, *rv, *y, *K[6], *k, *rate, *lu, *invd;
     // conditions
     int nstops;               // row length of the per-member stop tables
     const double *stop_t;     // [b*nstops + s]
@@ -64,7 +78,7 @@ struct DevEns {
     const double *pparams;    // [b*16]
     // outputs
     int Ns;
-    double *out_u, *out_umax;
+    double *out_u, *out_umax; // [tile][s][i][MB], [tile][i][MB]
     int *status;
     long long *stats;
     // controls
@@ -77,31 +91,28 @@ struct DevEns {
 // (uni/bimolecular steps, max_molecularity = 2 in the reference, network.jl:250) are branch-free selects
 __device__ __forceinline__ double pw(double x, int e)
 {
-    if (e <= 2) return e == 1 ? x : (e == 2 ? x * x : 1.0);
-    double r = x * x * x;
-    for (e -= 3; e > 0; --e) r *= x;
+    const double x2 = x * x;
+    double r = e == 1 ? x : (e == 2 ? x2 : (e == 3 ? x2 * x : 1.0));
+    if (e > 3) { r = x2 * x2; for (e -= 4; e > 0; --e) r *= x; }
     return r;
 }
 
 // rate_j = k_j * prod_m u_m^nu_mj  (Catalyst mass action, combinatoric_ratelaws=false;
-// reference src/solving/solve_utils.jl:318-334)
-__device__ __forceinline__ double rate_of(const int4 d, const double *u, size_t Bp, int b, double kj)
+// reference src/solving/solve_utils.jl:318-334).  Branch-free: an absent reactant slot reads
+// species 0 with exponent 0, so the three gathers of a reaction are always issued together.
+__device__ __forceinline__ double rate_of(const int4 d, const double *u, int MB, int m, double kj)
 {
-    double r = kj;
-    if (d.x >= 0) r *= pw(u[(size_t)d.x * Bp + b], d.w & 255);
-    if (d.y >= 0) r *= pw(u[(size_t)d.y * Bp + b], (d.w >> 8) & 255);
-    if (d.z >= 0) r *= pw(u[(size_t)d.z * Bp + b], (d.w >> 16) & 255);
-    return r;
+    const double x0 = u[max(d.x, 0) * MB + m], x1 = u[max(d.y, 0) * MB + m], x2 = u[max(d.z, 0) * MB + m];
+    return kj * pw(x0, d.x >= 0 ? (d.w & 255) : 0) * pw(x1, d.y >= 0 ? ((d.w >> 8) & 255) : 0) *
+           pw(x2, d.z >= 0 ? ((d.w >> 16) & 255) : 0);
 }
 
 // d(rate_j)/du_l / nu_l for the reactant in descriptor slot s (nu_l is folded into the term coefficient)
-__device__ __forceinline__ double drate_of(const int4 d, int s, const double *u, size_t Bp, int b, double kj)
+__device__ __forceinline__ double drate_of(const int4 d, int s, const double *u, int MB, int m, double kj)
 {
-    double r = kj;
-    if (d.x >= 0) r *= pw(u[(size_t)d.x * Bp + b], (d.w & 255) - (s == 0));
-    if (d.y >= 0) r *= pw(u[(size_t)d.y * Bp + b], ((d.w >> 8) & 255) - (s == 1));
-    if (d.z >= 0) r *= pw(u[(size_t)d.z * Bp + b], ((d.w >> 16) & 255) - (s == 2));
-    return r;
+    const double x0 = u[max(d.x, 0) * MB + m], x1 = u[max(d.y, 0) * MB + m], x2 = u[max(d.z, 0) * MB + m];
+    return kj * pw(x0, d.x >= 0 ? (d.w & 255) - (s == 0) : 0) * pw(x1, d.y >= 0 ? ((d.w >> 8) & 255) - (s == 1) : 0) *
+           pw(x2, d.z >= 0 ? ((d.w >> 16) & 255) - (s == 2) : 0);
 }
 
 // k = A*T^n*exp(-Ea/(R*T))*N_A*t_mult, optional harmonic cap — operation order of
@@ -161,248 +172,600 @@ __device__ inline double profile_eval(int kind, const double *p, double t)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tile primitives.  `b` = global member column, `slot`/`nslot` = this thread's stride lane.
+// Warp-tile primitives.
 // ---------------------------------------------------------------------------------------------
+constexpr int PR = 8;          // rows per panel (PanelPlan::PR)
+constexpr int CWMAX = 96;      // columns per chunk (PanelPlan::CW)
+constexpr unsigned FULL = 0xffffffffu;
+
 template <int MB>
-struct Tile {
-    int m, slot, nslot, b;
-    size_t Bp;
-    __device__ Tile(int tile, int Bp_) : Bp((size_t)Bp_)
+struct WTile {
+    static constexpr int LN = 32 / MB;
+    int lane, m, ln, b;
+    double *u, *ua, *rv, *y, *K[6], *k, *rate, *lu, *invd, *out_u, *out_umax;
+    __device__ WTile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en)
     {
-        m = threadIdx.x % MB;
-        slot = threadIdx.x / MB;
-        nslot = blockDim.x / MB;
+        lane = threadIdx.x & 31;
+        m = lane % MB;
+        ln = lane / MB;
         b = tile * MB + m;
+        const size_t vs = (size_t)tile * net.S * MB;
+        u = en.u + vs; ua = en.ua + vs; rv = en.rv + vs; y = en.y + vs; invd = en.invd + vs;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) K[q] = en.K[q] + vs;
+        k = en.k + (size_t)tile * net.R * MB;
+        rate = en.rate + (size_t)tile * net.R * MB;
+        lu = en.lu + (size_t)tile * pl.padded * MB;
+        out_u = en.out_u + (size_t)tile * en.Ns * net.S * MB;
+        out_umax = en.out_umax + vs;
     }
 };
 
-// K1: k[r][b] for the member's current condition value T (masked by `upd`)
+// sum over the LN lanes of each member in a fixed butterfly order (deterministic; every lane of
+// the member ends up with the same bits)
 template <int MB>
-__device__ void tile_rates(const Tile<MB> &tl, const DevNet &net, double *k, double T, bool upd, int ridx)
+__device__ __forceinline__ double member_sum(double v)
 {
-    if (!upd) return;
-    if (net.calc_mode == 0) {
-        for (int r = tl.slot; r < net.R; r += tl.nslot) k[(size_t)r * tl.Bp + tl.b] = arrhenius(net, r, T);
-    } else {
-        const double *src = ridx < 0 ? net.kinit : net.ktab + (size_t)ridx * net.R;
-        for (int r = tl.slot; r < net.R; r += tl.nslot) k[(size_t)r * tl.Bp + tl.b] = src[r];
-    }
+#pragma unroll
+    for (int off = 16; off >= MB; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+    return v;
 }
 
-// K2: du_i = sum_e coef_e * rate_{j(e)} over the gather CSR of species i (ascending reaction
-// order, no atomics).  out_i = du_i + sum_q cs[q]*Kq_i  (stage right-hand side fusion).
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
+{
+    // bulk L2 prefetch (sm_90+): one instruction pulls a whole panel towards L2
+    if (bytes >= 16) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// K1: k[r][m] for the member's current condition value T (masked by `upd`)
 template <int MB>
-__device__ void tile_rhs(const Tile<MB> &tl, const DevNet &net, const double *u,
-                         const double *k, double *out, int nk,
+__device__ void tile_rates(const WTile<MB> &tl, const DevNet &net, double T, bool upd, int ridx)
+{
+    constexpr int LN = 32 / MB;
+    if (upd) {
+        if (net.calc_mode == 0) {
+            for (int r = tl.ln; r < net.R; r += LN) tl.k[r * MB + tl.m] = arrhenius(net, r, T);
+        } else {
+            const double *src = ridx < 0 ? net.kinit : net.ktab + (size_t)ridx * net.R;
+            for (int r = tl.ln; r < net.R; r += LN) tl.k[r * MB + tl.m] = src[r];
+        }
+    }
+    __syncwarp();
+}
+
+// K2: mass-action right-hand side in two gather passes (no atomics, fixed summation order):
+//   rate_j = k_j * prod u^nu                      (lanes over reactions, coalesced k / rate)
+//   du_i   = sum_e coef_e * rate_{j(e)}           (gather CSR of species i, ascending reactions)
+// out_i = du_i + sum_q cs[q]*Kq_i  (stage right-hand side fusion)
+template <int MB>
+__device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u, double *out, int nk,
                          double *const *Kq, const double *cs)
 {
-    // four species per thread at a time: their gather chains (index -> descriptor -> k, u) are
-    // independent, which gives the memory system four times as many loads in flight
-    constexpr int U = 4;
-    for (int i0 = tl.slot; i0 < net.S; i0 += U * tl.nslot) {
-        int e[U], e1[U];
+    constexpr int LN = 32 / MB;
+    const int m = tl.m;
+    {
+        constexpr int UR = 4;
+        for (int j0 = tl.ln; j0 < net.R; j0 += UR * LN) {
+            int4 d[UR];
+            double kj[UR];
+#pragma unroll
+            for (int v = 0; v < UR; ++v) {
+                const int j = min(j0 + v * LN, net.R - 1);
+                d[v] = net.rdesc[j];
+                kj[v] = tl.k[j * MB + m];
+            }
+            double rt[UR];
+#pragma unroll
+            for (int v = 0; v < UR; ++v) rt[v] = rate_of(d[v], u, MB, m, kj[v]);
+#pragma unroll
+            for (int v = 0; v < UR; ++v)
+                if (j0 + v * LN < net.R) tl.rate[(j0 + v * LN) * MB + m] = rt[v];
+        }
+    }
+    __syncwarp();
+    // rows of hub species (hundreds of terms): the LN lanes of the member stride over the terms
+    for (int z = 0; z < net.rhs_nlong; ++z) {
+        const int i = net.rhs_order[z];
+        const int e1 = net.rhs_ptr[i + 1];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int e = net.rhs_ptr[i] + tl.ln;
+        for (; e + 3 * LN < e1; e += 4 * LN) {
+            a0 += (double)net.rhs_coef[e] * tl.rate[net.rhs_rxn[e] * MB + m];
+            a1 += (double)net.rhs_coef[e + LN] * tl.rate[net.rhs_rxn[e + LN] * MB + m];
+            a2 += (double)net.rhs_coef[e + 2 * LN] * tl.rate[net.rhs_rxn[e + 2 * LN] * MB + m];
+            a3 += (double)net.rhs_coef[e + 3 * LN] * tl.rate[net.rhs_rxn[e + 3 * LN] * MB + m];
+        }
+        for (; e < e1; e += LN) a0 += (double)net.rhs_coef[e] * tl.rate[net.rhs_rxn[e] * MB + m];
+        double a = member_sum<MB>((a0 + a1) + (a2 + a3));
+        if (tl.ln == 0) {
+            const int o = i * MB + m;
+            for (int q = 0; q < nk; ++q) a += cs[q] * Kq[q][o];
+            out[o] = a;
+        }
+    }
+    // the other rows one per lane, eight at a time (independent gather chains), in order of
+    // decreasing length so that rows walked together are about equally long
+    constexpr int U = 8;
+    for (int z0 = net.rhs_nlong + tl.ln; z0 < net.S; z0 += U * LN) {
+        int e[U], n[U], sp[U];
         double acc[U];
         int len = 0;
 #pragma unroll
         for (int v = 0; v < U; ++v) {
-            const int i = i0 + v * tl.nslot;
-            e[v] = i < net.S ? net.rhs_ptr[i] : 0;
-            e1[v] = i < net.S ? net.rhs_ptr[i + 1] : 0;
+            const int z = z0 + v * LN;
+            sp[v] = z < net.S ? net.rhs_order[z] : -1;
+            e[v] = sp[v] >= 0 ? net.rhs_ptr[sp[v]] : 0;
+            n[v] = sp[v] >= 0 ? net.rhs_ptr[sp[v] + 1] - e[v] : 0;
             acc[v] = 0.0;
-            len = max(len, e1[v] - e[v]);
+            len = max(len, n[v]);
         }
+        // branch-free: a row that has run out re-reads its last entry with a zero coefficient, so
+        // the eight index loads and then the eight gathers of a step are issued back to back
         for (int t = 0; t < len; ++t) {
+            int rx[U];
+            double cf[U], rt[U];
 #pragma unroll
             for (int v = 0; v < U; ++v) {
-                if (e[v] + t < e1[v]) {
-                    const int j = net.rhs_rxn[e[v] + t];
-                    acc[v] += (double)net.rhs_coef[e[v] + t] * rate_of(net.rdesc[j], u, tl.Bp, tl.b, k[(size_t)j * tl.Bp + tl.b]);
-                }
+                const int ee = e[v] + min(t, max(n[v] - 1, 0));
+                rx[v] = net.rhs_rxn[ee];
+                cf[v] = t < n[v] ? (double)net.rhs_coef[ee] : 0.0;
             }
+#pragma unroll
+            for (int v = 0; v < U; ++v) rt[v] = tl.rate[rx[v] * MB + m];
+#pragma unroll
+            for (int v = 0; v < U; ++v) acc[v] += cf[v] * rt[v];
         }
 #pragma unroll
         for (int v = 0; v < U; ++v) {
-            const int i = i0 + v * tl.nslot;
-            if (i < net.S) {
-                const size_t o = (size_t)i * tl.Bp + tl.b;
+            if (sp[v] >= 0) {
+                const int o = sp[v] * MB + m;
                 double a = acc[v];
                 for (int q = 0; q < nk; ++q) a += cs[q] * Kq[q][o];
                 out[o] = a;
             }
         }
     }
+    __syncwarp();
 }
 
 // K3: analytic Jacobian entry p = (i,l):  J_p = sum_t coef_t * k_j * d(prod)/du_l
 template <int MB>
-__device__ __forceinline__ double jac_entry(const Tile<MB> &tl, const DevNet &net, int p,
-                                            const double *u, const double *k)
+__device__ __forceinline__ double jac_entry(const WTile<MB> &tl, const DevNet &net, int p, const double *u)
 {
     double acc = 0.0;
     const int t1 = net.jt_ptr[p + 1];
     for (int t = net.jt_ptr[p]; t < t1; ++t) {
         const int j = net.jt_rxn[t], pk = net.jt_pack[t];
-        acc += (double)(pk >> 2) * drate_of(net.rdesc[j], pk & 3, u, tl.Bp, tl.b, k[(size_t)j * tl.Bp + tl.b]);
+        acc += (double)(pk >> 2) * drate_of(net.rdesc[j], pk & 3, u, MB, tl.m, tl.k[j * MB + tl.m]);
     }
     return acc;
 }
 
 template <int MB>
-__device__ void tile_jac_csc(const Tile<MB> &tl, const DevNet &net, const double *u,
-                             const double *k, double *Jval)
+__device__ void tile_jac_csc(const WTile<MB> &tl, const DevNet &net, const double *u, double *Jval)
 {
-    for (int p = tl.slot; p < net.nnzJ; p += tl.nslot) Jval[(size_t)p * tl.Bp + tl.b] = jac_entry(tl, net, p, u, k);
+    constexpr int LN = 32 / MB;
+    for (int p = tl.ln; p < net.nnzJ; p += LN) Jval[p * MB + tl.m] = jac_entry(tl, net, p, u);
+    __syncwarp();
 }
 
-// W = I/(h*gamma) - J assembled straight into the L\U slots (fill slots zeroed); four slots per
-// thread in flight
+// W = I/(h*gamma) - J assembled straight into the padded block storage: zero fill (coalesced
+// 16-byte stores), -J entries scattered to their slots (four entries per lane in flight), then
+// the diagonal shift.
 template <int MB>
-__device__ void tile_assemble_w(const Tile<MB> &tl, const DevNet &net, const double *u,
-                                const double *k, double hg_inv, double *lu)
+__device__ void tile_assemble_w(const WTile<MB> &tl, const DevNet &net, const DevPlan &pl, const double *u, double hg_inv)
 {
-    constexpr int U = 4;
-    for (int q0 = tl.slot; q0 < net.nnzLU; q0 += U * tl.nslot) {
-        int t[U], t1[U];
+    constexpr int LN = 32 / MB;
+    const int m = tl.m;
+    if (MB == 1) {
+        for (int i = tl.lane; i < pl.padded; i += 32) tl.lu[i] = 0.0;
+    } else {
+        double2 *z = reinterpret_cast<double2 *>(tl.lu);       // padded*MB is even: every tile is 16-byte aligned
+        const int n2 = pl.padded * MB / 2;
+        for (int i = tl.lane; i < n2; i += 32) z[i] = make_double2(0.0, 0.0);
+    }
+    __syncwarp();
+    // entries with many terms (hub columns): the lanes of the member stride over the terms
+    for (int z = 0; z < net.j_nlong; ++z) {
+        const int p = net.j_order[z];
+        const int t1 = net.jt_ptr[p + 1];
+        double a0 = 0.0, a1 = 0.0;
+        int t = net.jt_ptr[p] + tl.ln;
+        for (; t + LN < t1; t += 2 * LN) {
+            const int j0 = net.jt_rxn[t], pk0 = net.jt_pack[t], j1 = net.jt_rxn[t + LN], pk1 = net.jt_pack[t + LN];
+            a0 += (double)(pk0 >> 2) * drate_of(net.rdesc[j0], pk0 & 3, u, MB, m, tl.k[j0 * MB + m]);
+            a1 += (double)(pk1 >> 2) * drate_of(net.rdesc[j1], pk1 & 3, u, MB, m, tl.k[j1 * MB + m]);
+        }
+        for (; t < t1; t += LN) {
+            const int j0 = net.jt_rxn[t], pk0 = net.jt_pack[t];
+            a0 += (double)(pk0 >> 2) * drate_of(net.rdesc[j0], pk0 & 3, u, MB, m, tl.k[j0 * MB + m]);
+        }
+        const double a = member_sum<MB>(a0 + a1);
+        if (tl.ln == 0) tl.lu[(size_t)net.jslot[p] * MB + m] = -a;
+    }
+    // the other entries one per lane, eight in flight, longest first
+    constexpr int U = 8;
+    for (int z0 = net.j_nlong + tl.ln; z0 < net.nnzJ; z0 += U * LN) {
+        int t[U], n[U], pe[U];
         double v[U];
         int len = 0;
 #pragma unroll
         for (int x = 0; x < U; ++x) {
-            const int q = q0 + x * tl.nslot;
-            const int src = q < net.nnzLU ? net.slot_src[q] : 0;
-            v[x] = (src & 1) ? hg_inv : 0.0;
-            const int p = (src >> 1) - 1;
-            t[x] = p >= 0 ? net.jt_ptr[p] : 0;
-            t1[x] = p >= 0 ? net.jt_ptr[p + 1] : 0;
-            len = max(len, t1[x] - t[x]);
+            const int z = z0 + x * LN;
+            pe[x] = z < net.nnzJ ? net.j_order[z] : -1;
+            t[x] = pe[x] >= 0 ? net.jt_ptr[pe[x]] : 0;
+            n[x] = pe[x] >= 0 ? net.jt_ptr[pe[x] + 1] - t[x] : 0;
+            v[x] = 0.0;
+            len = max(len, n[x]);
         }
         for (int z = 0; z < len; ++z) {
+            int jj[U], pk[U];
+            int4 d[U];
+            double kj[U], dr[U];
 #pragma unroll
             for (int x = 0; x < U; ++x) {
-                if (t[x] + z < t1[x]) {
-                    const int j = net.jt_rxn[t[x] + z], pk = net.jt_pack[t[x] + z];
-                    v[x] -= (double)(pk >> 2) * drate_of(net.rdesc[j], pk & 3, u, tl.Bp, tl.b, k[(size_t)j * tl.Bp + tl.b]);
+                const int tt = t[x] + min(z, max(n[x] - 1, 0));
+                jj[x] = net.jt_rxn[tt];
+                pk[x] = z < n[x] ? net.jt_pack[tt] : (net.jt_pack[tt] & 3);     // exhausted entry: coefficient 0
+            }
+#pragma unroll
+            for (int x = 0; x < U; ++x) { d[x] = net.rdesc[jj[x]]; kj[x] = tl.k[jj[x] * MB + m]; }
+#pragma unroll
+            for (int x = 0; x < U; ++x) dr[x] = drate_of(d[x], pk[x] & 3, u, MB, m, kj[x]);
+#pragma unroll
+            for (int x = 0; x < U; ++x) v[x] -= (double)(pk[x] >> 2) * dr[x];
+        }
+#pragma unroll
+        for (int x = 0; x < U; ++x)
+            if (pe[x] >= 0) tl.lu[(size_t)net.jslot[pe[x]] * MB + m] = v[x];
+    }
+    __syncwarp();
+    for (int i = tl.ln; i < net.S; i += LN) tl.lu[(size_t)net.diag_slot[i] * MB + m] += hg_inv;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// shared memory of a factorising warp, in doubles: one staged chunk of a panel, the unit upper
+// diagonal block U'_QQ of the next in-chunk source (prefetched with cp.async) and the finished
+// L'_PQ block of a source that lies in an earlier chunk
+__host__ __device__ constexpr size_t lu_smem_doubles(int mb) { return (size_t)(CWMAX * PR + 2 * PR * PR) * mb; }
+
+// K4: block Crout LU of the padded panel storage, in place:  W = L' U'  with the pivots on L'
+// and a unit diagonal on U'; invd[i] = 1/L'_ii is kept for the substitutions.
+// A unit (panel x column chunk) is staged in shared memory Wp[c][r][m]; for every source block
+// Q in the L part:   L_PQ = X * inv(U_QQ)  (lane ln owns row ln),  then every lane updates its
+// share of the target columns, three columns per pass,
+//     w[:, j] -= L_PQ * U_Q[:, j]
+// with the 24 U' values of the pass in flight together and L_PQ broadcast from shared memory
+// (8 loads feed 24 FMAs).
+template <int MB>
+__device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
+{
+    constexpr int LN = 32 / MB, NC = 3;
+    const int m = tl.m, ln = tl.ln, lane = tl.lane;
+    double *lu = tl.lu;
+    double *Uq = Wp + CWMAX * PR * MB;       // [q][a][m]: U'_QQ of the next in-chunk source
+    double *Ls = Uq + PR * PR * MB;          // [q][r][m]: L'_PQ of a source from an earlier chunk
+    for (int un = 0; un < pl.nunits; ++un) {
+        const int4 ua = pl.u_info[2 * un], ub = pl.u_info[2 * un + 1];
+        const int P = ua.x, x0 = ua.y, x1 = ua.z, task0 = ua.w, ntask = ub.x, dmode = ub.y;
+        const int nr = pl.p_nrows[P], next = pl.p_next[P], p0 = pl.p_row0[P];
+        const int cw = x1 - x0;
+        double *gP = lu + (size_t)pl.p_base[P] * MB;
+        // pull what the NEXT unit will read towards L2 while this one is being eliminated: its
+        // own chunk and, per source block, the span of U' columns its targets touch
+        if (un + 1 < pl.nunits) {
+            const int4 na = pl.u_info[2 * un + 2], nb = pl.u_info[2 * un + 3];
+            if (lane == 31) {
+                const int nrn = pl.p_nrows[na.x];
+                const char *a = (const char *)(lu + ((size_t)pl.p_base[na.x] + (size_t)na.y * nrn) * MB);
+                const size_t nbytes = (size_t)(na.z - na.y) * nrn * MB * 8;
+                const size_t a16 = (size_t)a & ~(size_t)15;
+                prefetch_l2_bulk((const void *)a16, (unsigned)(((size_t)a + nbytes - a16) & ~(size_t)15));
+            } else {
+                for (int tk = lane; tk < nb.x; tk += 31) {
+                    const int4 ti = pl.t_info[na.w + tk];
+                    if (ti.z > 0) {
+                        const int nq = pl.p_nrows[ti.x];
+                        const int c0 = pl.map[ti.w] & 0xffff, c1 = (pl.map[ti.w + ti.z - 1] & 0xffff) + 1;
+                        const char *a = (const char *)(lu + ((size_t)pl.p_base[ti.x] + (size_t)c0 * nq) * MB);
+                        const size_t nbytes = (size_t)(c1 - c0) * nq * MB * 8;
+                        const size_t a16 = (size_t)a & ~(size_t)15;
+                        prefetch_l2_bulk((const void *)a16, (unsigned)(((size_t)a + nbytes - a16) & ~(size_t)15));
+                    }
                 }
             }
         }
-#pragma unroll
-        for (int x = 0; x < U; ++x) {
-            const int q = q0 + x * tl.nslot;
-            if (q < net.nnzLU) lu[(size_t)q * tl.Bp + tl.b] = v[x];
-        }
-    }
-}
-
-// K4: in-place sparse LU (row-wise, no pivoting) over the shared symbolic factorisation.
-// The target row lives in shared memory (w[offset][m]); for each pivot k in L(i,:) every thread
-// forms l_ik = w_k/u_kk redundantly and the updates over U(k,:) are spread across the slots.
-template <int MB>
-__device__ void tile_lu(const Tile<MB> &tl, const DevNet &net, double *lu,
-                        double *invd, double *w)
-{
-    for (int i = 0; i < net.S; ++i) {
-        const int r0 = net.rowptr[i], r1 = net.rowptr[i + 1], dg = net.diagpos[i];
-        if (dg == r0) {   // no L part: the row is already final
-            if (tl.slot == 0) invd[(size_t)i * tl.Bp + tl.b] = 1.0 / lu[(size_t)dg * tl.Bp + tl.b];
-            continue;
-        }
-        for (int o = tl.slot; o < r1 - r0; o += tl.nslot) w[o * MB + tl.m] = lu[(size_t)(r0 + o) * tl.Bp + tl.b];
-        __syncthreads();
-        for (int p = r0; p < dg; ++p) {
-            const int kk = net.colidx[p];
-            const double l = w[(p - r0) * MB + tl.m] * invd[(size_t)kk * tl.Bp + tl.b];
-            const int ub = net.diagpos[kk] + 1, nu = net.rowptr[kk + 1] - ub;
-            const int *__restrict__ tg = net.tgt + net.tgt_off[p];
-            for (int e = tl.slot; e < nu; e += tl.nslot)
-                w[tg[e] * MB + tl.m] -= l * lu[(size_t)(ub + e) * tl.Bp + tl.b];
-            if (tl.slot == 0) lu[(size_t)p * tl.Bp + tl.b] = l;
-            __syncthreads();
-        }
-        for (int o = dg - r0 + tl.slot; o < r1 - r0; o += tl.nslot) lu[(size_t)(r0 + o) * tl.Bp + tl.b] = w[o * MB + tl.m];
-        if (tl.slot == 0) invd[(size_t)i * tl.Bp + tl.b] = 1.0 / w[(dg - r0) * MB + tl.m];
-        __syncthreads();
-    }
-}
-
-// sum over the slots of one member in a fixed order (deterministic): shuffle tree across the
-// sub-lanes of each warp, then one pass over the per-warp partials; red has (nthreads/32)*MB doubles
-template <int MB>
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int off = 16; off >= MB; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
-}
-
-template <int MB>
-__device__ __forceinline__ double tile_sum(const Tile<MB> &tl, double v, double *red)
-{
-    v = warp_sum<MB>(v);
-    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if ((threadIdx.x & 31) < MB) red[warp * MB + tl.m] = v;
-    __syncthreads();
-    double s = 0.0;
-    for (int q = 0; q < nw; ++q) s += red[q * MB + tl.m];
-    __syncthreads();
-    return s;
-}
-
-// K5: forward/back substitution  W x = rhs  (rhs, x in species order; y = permuted scratch)
-template <int MB>
-__device__ void tile_trisolve(const Tile<MB> &tl, const DevNet &net, const double *lu,
-                              const double *invd, const double *rhs,
-                              double *y, double *x, double *red)
-{
-    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const bool wlead = (threadIdx.x & 31) < MB;
-    // rows without an L part depend on nothing: do them all at once
-    for (int i = threadIdx.x / MB; i < net.S; i += tl.nslot)
-        if (net.diagpos[i] == net.rowptr[i]) y[(size_t)i * tl.Bp + tl.b] = rhs[(size_t)net.perm[i] * tl.Bp + tl.b];
-    __syncthreads();
-    for (int i = 0; i < net.S; ++i) {
-        const int r0 = net.rowptr[i], dg = net.diagpos[i];
-        if (dg - r0 > 0) {
-            double part = 0.0;
-            for (int p = r0 + tl.slot; p < dg; p += tl.nslot)
-                part += lu[(size_t)p * tl.Bp + tl.b] * y[(size_t)net.colidx[p] * tl.Bp + tl.b];
-            part = warp_sum<MB>(part);
-            if (wlead) red[warp * MB + tl.m] = part;
-            __syncthreads();
-            if (tl.slot == 0) {
-                double s = 0.0;
-                for (int q = 0; q < nw; ++q) s += red[q * MB + tl.m];
-                y[(size_t)i * tl.Bp + tl.b] = rhs[(size_t)net.perm[i] * tl.Bp + tl.b] - s;
+        // stage the first in-chunk source's U'_QQ while the chunk itself is being loaded
+        auto stage_uqq = [&](int tk) {
+            for (; tk < ntask; ++tk) {
+                const int4 ti = pl.t_info[task0 + tk];
+                if (ti.y >> 30) {
+                    const int Q = ti.x, nq = pl.p_nrows[Q];
+                    const double *src = lu + ((size_t)pl.p_base[Q] + (size_t)pl.p_next[Q] * nq) * MB;
+                    for (int i = lane; i < nq * nq * MB; i += 32) cp_async8(Uq + i, src + i);
+                    break;
+                }
             }
-            __syncthreads();
-        }
-    }
-    // rows without a U part (beyond the diagonal) only need scaling
-    for (int i = threadIdx.x / MB; i < net.S; i += tl.nslot)
-        if (net.rowptr[i + 1] - net.diagpos[i] == 1) {
-            const double v = y[(size_t)i * tl.Bp + tl.b] * invd[(size_t)i * tl.Bp + tl.b];
-            y[(size_t)i * tl.Bp + tl.b] = v;
-            x[(size_t)net.perm[i] * tl.Bp + tl.b] = v;
-        }
-    __syncthreads();
-    for (int i = net.S - 1; i >= 0; --i) {
-        const int dg = net.diagpos[i], r1 = net.rowptr[i + 1];
-        if (r1 - dg - 1 > 0) {
-            double part = 0.0;
-            for (int p = dg + 1 + tl.slot; p < r1; p += tl.nslot)
-                part += lu[(size_t)p * tl.Bp + tl.b] * y[(size_t)net.colidx[p] * tl.Bp + tl.b];
-            part = warp_sum<MB>(part);
-            if (wlead) red[warp * MB + tl.m] = part;
-            __syncthreads();
-            if (tl.slot == 0) {
-                double s = 0.0;
-                for (int q = 0; q < nw; ++q) s += red[q * MB + tl.m];
-                const double v = (y[(size_t)i * tl.Bp + tl.b] - s) * invd[(size_t)i * tl.Bp + tl.b];
-                y[(size_t)i * tl.Bp + tl.b] = v;
-                x[(size_t)net.perm[i] * tl.Bp + tl.b] = v;
+            cp_async_commit();
+        };
+        stage_uqq(0);
+        {
+            // chunk -> shared memory, eight 16-byte loads per lane in flight
+            const double *src = gP + (size_t)x0 * nr * MB;
+            const int n = cw * nr * MB;
+            if (MB == 1) {
+                for (int i0 = lane; i0 < n; i0 += 32 * 8) {
+                    double v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = i0 + 32 * j < n ? src[i0 + 32 * j] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (i0 + 32 * j < n) Wp[i0 + 32 * j] = v[j];
+                }
+            } else {
+                const double2 *s2 = reinterpret_cast<const double2 *>(src);
+                double2 *d2 = reinterpret_cast<double2 *>(Wp);
+                const int n2 = n / 2;
+                for (int i0 = lane; i0 < n2; i0 += 32 * 8) {
+                    double2 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = i0 + 32 * j < n2 ? s2[i0 + 32 * j] : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (i0 + 32 * j < n2) d2[i0 + 32 * j] = v[j];
+                }
             }
-            __syncthreads();
         }
+        __syncwarp();
+        for (int tk = 0; tk < ntask; ++tk) {
+            const int4 ti = pl.t_info[task0 + tk];
+            const int Q = ti.x, lpos = ti.y & 0x3fffffff, inch = ti.y >> 30, ntg = ti.z, map0 = ti.w;
+            const int nq = pl.p_nrows[Q];
+            const double *gQ = lu + (size_t)pl.p_base[Q] * MB;
+            const double *ls;                    // L'_PQ as [q][r][m] in shared memory
+            if (inch) {
+                cp_async_wait_all();
+                __syncwarp();
+                if (ln < nr) {
+                    double X[PR];
+                    double *xp = Wp + ((lpos - x0) * nr + ln) * MB + m;
+#pragma unroll
+                    for (int q = 0; q < PR; ++q) X[q] = q < nq ? xp[q * nr * MB] : 0.0;
+                    const double *uq = Uq + m;                 // U_QQ[a][q] at (q*nq + a)*MB
+#pragma unroll
+                    for (int a = 0; a < PR - 1; ++a)
+#pragma unroll
+                        for (int q = a + 1; q < PR; ++q)
+                            if (q < nq) X[q] -= X[a] * uq[(q * nq + a) * MB];
+#pragma unroll
+                    for (int q = 1; q < PR; ++q) if (q < nq) xp[q * nr * MB] = X[q];
+                }
+                __syncwarp();
+                stage_uqq(tk + 1);               // flies while this source's targets are updated
+                ls = Wp + (lpos - x0) * nr * MB + m;
+            } else {
+                const double *src = gP + (size_t)lpos * nr * MB;
+                for (int i = lane; i < nq * nr * MB; i += 32) Ls[i] = src[i];
+                __syncwarp();
+                ls = Ls + m;
+            }
+            for (int t = ln; t < ntg; t += NC * LN) {
+                double uu[NC][PR], w[NC][PR];
+                double *wp[NC];
+                bool ok[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    ok[c] = t + c * LN < ntg;
+                    const int e = pl.map[map0 + (ok[c] ? t + c * LN : t)];
+                    const double *up = gQ + (size_t)(e & 0xffff) * nq * MB + m;
+                    wp[c] = Wp + (e >> 16) * nr * MB + m;
+#pragma unroll
+                    for (int q = 0; q < PR; ++q) uu[c][q] = q < nq ? up[q * MB] : 0.0;
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int r = 0; r < PR; ++r) w[c][r] = r < nr ? wp[c][r * MB] : 0.0;
+#pragma unroll
+                for (int q = 0; q < PR; ++q) {
+                    if (q < nq) {
+                        double l[PR];
+#pragma unroll
+                        for (int r = 0; r < PR; ++r) l[r] = r < nr ? ls[(q * nr + r) * MB] : 0.0;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c)
+#pragma unroll
+                            for (int r = 0; r < PR; ++r) w[c][r] -= l[r] * uu[c][q];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (ok[c]) {
+#pragma unroll
+                        for (int r = 0; r < PR; ++r) if (r < nr) wp[c][r * MB] = w[c][r];
+                    }
+            }
+            __syncwarp();
+        }
+        cp_async_wait_all();
+        if (dmode) {
+            const int dpos = next - x0;      // position of the diagonal block relative to the chunk (negative for dmode 2)
+            if (dmode == 1) {
+                // Crout LU of the nr x nr diagonal block: lane ln owns row ln, pivot rows are
+                // broadcast with shuffles
+                double D[PR];
+                double *dp = Wp + (dpos * nr + ln) * MB + m;
+#pragma unroll
+                for (int j = 0; j < PR; ++j) D[j] = (ln < nr && j < nr) ? dp[j * nr * MB] : 0.0;
+#pragma unroll
+                for (int j = 0; j < PR; ++j) {
+                    if (j < nr) {
+                        const double piv = __shfl_sync(FULL, D[j], j * MB + m);
+                        const double inv = 1.0 / piv;
+                        if (ln == j) tl.invd[(p0 + j) * MB + m] = inv;
+#pragma unroll
+                        for (int i = j + 1; i < PR; ++i) {
+                            const double uji = __shfl_sync(FULL, D[i], j * MB + m) * inv;
+                            if (ln == j) D[i] = uji;
+                            else if (ln > j) D[i] -= D[j] * uji;
+                        }
+                    }
+                }
+                if (ln < nr) {
+#pragma unroll
+                    for (int j = 0; j < PR; ++j) if (j < nr) dp[j * nr * MB] = D[j];
+                }
+                __syncwarp();
+            }
+            // U part of the chunk:  U'_P[:, j] = inv(L'_PP) * w[:, j]  (forward substitution, thread local)
+            const int c0 = dmode == 1 ? dpos + nr : 0;
+            if (c0 < cw) {
+                double Lpp[PR][PR], inv[PR];
+                const double *lp = dmode == 1 ? (const double *)(Wp + dpos * nr * MB + m) : (gP + (size_t)next * nr * MB + m);
+#pragma unroll
+                for (int r = 0; r < PR; ++r) {
+                    inv[r] = r < nr ? tl.invd[(p0 + r) * MB + m] : 0.0;
+#pragma unroll
+                    for (int a = 0; a < PR; ++a) Lpp[r][a] = (a < r && r < nr) ? lp[(a * nr + r) * MB] : 0.0;
+                }
+                for (int t = c0 + ln; t < cw; t += LN) {
+                    double *wp = Wp + t * nr * MB + m;
+                    double w[PR];
+#pragma unroll
+                    for (int r = 0; r < PR; ++r) w[r] = r < nr ? wp[r * MB] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < PR; ++r) {
+#pragma unroll
+                        for (int a = 0; a < r; ++a) w[r] -= Lpp[r][a] * w[a];
+                        w[r] *= inv[r];
+                    }
+#pragma unroll
+                    for (int r = 0; r < PR; ++r) if (r < nr) wp[r * MB] = w[r];
+                }
+                __syncwarp();
+            }
+        }
+        {
+            double *dst = gP + (size_t)x0 * nr * MB;
+            const int n = cw * nr * MB;
+            if (MB == 1) {
+                for (int i = lane; i < n; i += 32) dst[i] = Wp[i];
+            } else {
+                double2 *d2 = reinterpret_cast<double2 *>(dst);
+                const double2 *s2 = reinterpret_cast<const double2 *>(Wp);
+                for (int i = lane; i < n / 2; i += 32) d2[i] = s2[i];
+            }
+        }
+        __syncwarp();
     }
-    __syncthreads();
+}
+
+// K5: W x = rhs over the block storage.  rhs, x in species order; y = permuted scratch.
+// Lane ln = cg*8 + r: row r of the panel, column group cg of LN/8; a warp-wide load of one
+// column position covers MB*8 consecutive doubles of the panel.  Eight column positions per lane
+// are in flight at a time and the panel two steps ahead is pulled towards L2 with one bulk
+// prefetch, so the sweep streams the factors instead of waiting on each panel.
+template <int MB>
+__device__ __forceinline__ double panel_dot(const double *gP, const double *y, const int *__restrict__ C,
+                                            int cbeg, int cend, int nr, int r, int cg, int m)
+{
+    constexpr int CG = 32 / MB / PR;
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    int c = cbeg + cg;
+    for (; c + 7 * CG < cend; c += 8 * CG) {
+        int ix[8];
+        double lv[8], yv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ix[j] = C[c + j * CG];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lv[j] = gP[((c + j * CG) * nr + r) * MB];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yv[j] = y[ix[j] * MB + m];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j & 3] += lv[j] * yv[j];
+    }
+    for (; c < cend; c += CG) a[0] += gP[(c * nr + r) * MB] * y[C[c] * MB + m];
+    return (a[0] + a[1]) + (a[2] + a[3]);
+}
+
+template <int MB>
+__device__ __forceinline__ void prefetch_panel_cols(const DevPlan &pl, const double *lu, int P, int c0, int c1)
+{
+    const int nr = pl.p_nrows[P];
+    const size_t a = (size_t)(lu + ((size_t)pl.p_base[P] + (size_t)c0 * nr) * MB);
+    const size_t nbytes = (size_t)(c1 - c0) * nr * MB * 8;
+    const size_t a16 = a & ~(size_t)15;
+    prefetch_l2_bulk((const void *)a16, (unsigned)((a + nbytes - a16) & ~(size_t)15));
+}
+
+template <int MB>
+__device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevPlan &pl, const double *rhs, double *x)
+{
+    constexpr int LN = 32 / MB, CG = LN / PR;
+    static_assert(CG >= 1, "at most 4 members per warp tile");
+    constexpr int AHEAD = 2;
+    const int m = tl.m, r = tl.ln % PR, cg = tl.ln / PR;
+    const double *lu = tl.lu;
+    double *y = tl.y;
+    // ---------------- forward:  L' y = P rhs ----------------
+    if (tl.lane < AHEAD && tl.lane < pl.npanels) prefetch_panel_cols<MB>(pl, lu, tl.lane, 0, pl.p_next[tl.lane] + pl.p_nrows[tl.lane]);
+    for (int P = 0; P < pl.npanels; ++P) {
+        const int nr = pl.p_nrows[P], next = pl.p_next[P], p0 = pl.p_row0[P];
+        const int *__restrict__ C = pl.cols + pl.p_cptr[P];
+        const double *gP = lu + (size_t)pl.p_base[P] * MB + m;
+        const bool rok = r < nr;
+        if (tl.lane == 0 && P + AHEAD < pl.npanels)
+            prefetch_panel_cols<MB>(pl, lu, P + AHEAD, 0, pl.p_next[P + AHEAD] + pl.p_nrows[P + AHEAD]);
+        double acc = rok ? panel_dot<MB>(gP, y, C, 0, next, nr, r, cg, m) : 0.0;
+#pragma unroll
+        for (int off = 16; off >= PR * MB; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+        double z = rok ? rhs[net.perm[p0 + r] * MB + m] - acc : 0.0;
+        const double dinv = rok ? tl.invd[(p0 + r) * MB + m] : 0.0;
+        double lint[PR - 1];
+#pragma unroll
+        for (int a = 0; a < PR - 1; ++a) lint[a] = (rok && a < r) ? gP[((next + a) * nr + r) * MB] : 0.0;
+#pragma unroll
+        for (int a = 0; a < PR - 1; ++a) {
+            const double yv = __shfl_sync(FULL, z * dinv, (cg * PR + a) * MB + m);   // y_a is final here
+            if (r > a) z -= lint[a] * yv;
+        }
+        if (cg == 0 && rok) y[(p0 + r) * MB + m] = z * dinv;
+        __syncwarp();
+    }
+    // ---------------- backward:  U' x = y ----------------
+    if (tl.lane < AHEAD && tl.lane < pl.npanels) {
+        const int P = pl.npanels - 1 - tl.lane;
+        prefetch_panel_cols<MB>(pl, lu, P, pl.p_next[P], pl.p_width[P]);
+    }
+    for (int P = pl.npanels - 1; P >= 0; --P) {
+        const int W = pl.p_width[P], nr = pl.p_nrows[P], next = pl.p_next[P], p0 = pl.p_row0[P];
+        const int *__restrict__ C = pl.cols + pl.p_cptr[P];
+        const double *gP = lu + (size_t)pl.p_base[P] * MB + m;
+        const bool rok = r < nr;
+        if (tl.lane == 0 && P - AHEAD >= 0) prefetch_panel_cols<MB>(pl, lu, P - AHEAD, pl.p_next[P - AHEAD], pl.p_width[P - AHEAD]);
+        double acc = rok ? panel_dot<MB>(gP, y, C, next + nr, W, nr, r, cg, m) : 0.0;
+#pragma unroll
+        for (int off = 16; off >= PR * MB; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+        double z = rok ? y[(p0 + r) * MB + m] - acc : 0.0;
+        double uint_[PR];
+#pragma unroll
+        for (int a = 1; a < PR; ++a) uint_[a] = (rok && a > r && a < nr) ? gP[((next + a) * nr + r) * MB] : 0.0;
+#pragma unroll
+        for (int a = PR - 1; a > 0; --a) {
+            const double xv = __shfl_sync(FULL, z, (cg * PR + a) * MB + m);        // U' has a unit diagonal
+            if (r < a) z -= uint_[a] * xv;
+        }
+        if (cg == 0 && rok) {
+            y[(p0 + r) * MB + m] = z;
+            x[net.perm[p0 + r] * MB + m] = z;
+        }
+        __syncwarp();
+    }
 }
 
 }  // namespace kb2

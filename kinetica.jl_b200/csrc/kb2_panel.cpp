@@ -1,11 +1,16 @@
-// Panel plan for the register-blocked sparse LU / panel triangular solves.
+// Block plan for the supernodal sparse LU / panel triangular solves.
 //
 // Rows of the (permuted) L\U pattern are grouped into panels of up to PR consecutive rows that
-// share one column pattern C_P (the union of their patterns; padding entries are explicit zeros
-// and stay exactly zero through the elimination).  The numeric factorisation walks the panels in
-// order; a panel is processed in column chunks of at most CW columns so that a thread holds its
-// PR x (CW/32) targets in registers while the pivots stream past.  Everything here is computed
-// once on the host and shared by all ensemble members.
+// share one column pattern C_P: the union of their exact patterns, closed so that whenever one
+// column of an earlier panel Q appears left of the diagonal, all of Q's columns do.  Padding
+// entries are explicit zeros and stay exactly zero through the elimination (every update that
+// reaches one has a structurally zero factor).  With complete source blocks the numeric
+// factorisation of a panel is a sequence of small dense products
+//     W_P[:, targets] -= L_PQ (nr x nq) * U_Q[:, targets]        for Q in the L part of P,
+// with L_PQ = W_P[:, Q] * inv(U_QQ) (block Crout: pivots on L, unit diagonal on U).
+// A panel wider than CW columns is processed in column chunks (units); chunk boundaries never
+// split a source block or the diagonal block.  Everything here is computed once on the host and
+// shared by all ensemble members.
 #include "kb2_internal.h"
 
 #include <algorithm>
@@ -17,8 +22,9 @@ std::string build_panels(Symbolic &sym, int64_t S)
     PanelPlan &pp = sym.panels;
     pp = PanelPlan();
     const int PR = PanelPlan::PR, CW = PanelPlan::CW;
-    // ---- panels: greedy runs of consecutive rows; a run stops when the union pattern would
-    // outgrow one chunk (unless the row alone is wider than a chunk) ----
+    if (S >= 65536) return "block plan packs column positions into 16 bits: S must be < 65536";
+    // ---- panels: greedy runs of consecutive rows.  A run stops when the padded block would hold
+    // much more than the exact entries of its rows. ----
     std::vector<int32_t> mark(S, -1), uni;
     pp.row_panel.assign(S, 0);
     pp.row_r.assign(S, 0);
@@ -28,19 +34,25 @@ std::string build_panels(Symbolic &sym, int64_t S)
         const int32_t P = (int32_t)pp.p_row0.size();
         uni.clear();
         int nr = 0;
+        int64_t exact = 0;
         while (nr < PR && p0 + nr < S) {
             const int64_t i = p0 + nr;
-            size_t before = uni.size();
+            const size_t before = uni.size();
+            auto add = [&](int32_t c) { if (mark[c] != P) { mark[c] = P; uni.push_back(c); } };
             for (int64_t q = sym.rowptr[i]; q < sym.rowptr[i + 1]; ++q) {
-                int32_t c = (int32_t)sym.colidx[q];
-                if (mark[c] != P) { mark[c] = P; uni.push_back(c); }
+                const int32_t c = (int32_t)sym.colidx[q];
+                if (c < p0) {       // close over the source panel of an external column
+                    const int32_t Q = pp.row_panel[c];
+                    for (int r = 0; r < pp.p_nrows[Q]; ++r) add(pp.p_row0[Q] + r);
+                } else add(c);
             }
-            // rows of the panel are pivots of each other: make sure every diagonal of the run is a column
-            if (nr > 0 && (int)uni.size() > CW && (int)before <= CW) {
+            const int64_t ex2 = exact + (sym.rowptr[i + 1] - sym.rowptr[i]);
+            if (nr > 0 && (int64_t)(nr + 1) * (int64_t)uni.size() > 2 * ex2 + 64) {
                 for (size_t z = before; z < uni.size(); ++z) mark[uni[z]] = -1;
                 uni.resize(before);
                 break;
             }
+            exact = ex2;
             ++nr;
         }
         std::sort(uni.begin(), uni.end());
@@ -64,190 +76,81 @@ std::string build_panels(Symbolic &sym, int64_t S)
     }
     pp.padded = base;
     const int32_t NP = (int32_t)pp.p_row0.size();
-    // ---- storage slot of every exact-pattern entry; assembly sources over the padded storage ----
+    // ---- storage slot of every exact-pattern entry (column-major inside a panel: c*nr + r), of
+    // every Jacobian entry and of every diagonal ----
     pp.slot_of.assign(sym.nnzLU, 0);
-    pp.slot_src.assign(pp.padded, 0);
+    pp.jslot.assign(sym.nnzJ, -1);
     pp.diag_slot.assign(S, 0);
     std::vector<int32_t> where(S, -1);
     for (int32_t P = 0; P < NP; ++P) {
         const int32_t *C = pp.cols.data() + pp.p_cptr[P];
-        const int W = pp.p_width[P];
+        const int W = pp.p_width[P], nr = pp.p_nrows[P];
         for (int c = 0; c < W; ++c) where[C[c]] = c;
-        for (int r = 0; r < pp.p_nrows[P]; ++r) {
+        for (int r = 0; r < nr; ++r) {
             const int64_t i = pp.p_row0[P] + r;
             for (int64_t q = sym.rowptr[i]; q < sym.rowptr[i + 1]; ++q) {
-                const int32_t slot = pp.p_base[P] + r * W + where[sym.colidx[q]];
+                const int32_t slot = pp.p_base[P] + where[sym.colidx[q]] * nr + r;
                 pp.slot_of[q] = slot;
-                pp.slot_src[slot] = sym.slot_src[q];
+                const int32_t src = sym.slot_src[q];
+                if ((src >> 1) > 0) pp.jslot[(src >> 1) - 1] = slot;
                 if (q == sym.diagpos[i]) pp.diag_slot[i] = slot;
             }
         }
     }
-    // ---- units (panel x column chunk), their pivot steps and column maps ----
-    // per-panel lookup of column -> position, rebuilt on demand for source panels
-    std::vector<int32_t> pos_in_Q(S, -1);
+    for (int64_t p = 0; p < sym.nnzJ; ++p) if (pp.jslot[p] < 0) return "internal error: Jacobian entry without a storage slot";
+    // ---- units, tasks and target maps ----
+    std::vector<int32_t> pos_in_P(S, -1);
     pp.n_fma_padded = 0;
     for (int32_t P = 0; P < NP; ++P) {
         const int32_t *C = pp.cols.data() + pp.p_cptr[P];
-        const int W = pp.p_width[P], next = pp.p_next[P], nr = pp.p_nrows[P], p0 = pp.p_row0[P];
-        // chunk boundaries: multiples of CW, never splitting the diagonal block [next, next+nr)
+        const int W = pp.p_width[P], next = pp.p_next[P], nr = pp.p_nrows[P];
+        for (int c = 0; c < W; ++c) pos_in_P[C[c]] = c;
+        // admissible cut positions: source-block starts in the L part, the diagonal block start,
+        // and every column position from the end of the diagonal block on
+        std::vector<char> cut_ok(W + 1, 0);
+        for (int c = 0; c < next; ++c) if (pp.row_r[C[c]] == 0) cut_ok[c] = 1;
+        cut_ok[next] = 1;
+        for (int c = next + nr; c <= W; ++c) cut_ok[c] = 1;
         std::vector<int> cuts{0};
         while (cuts.back() < W) {
-            int x0 = cuts.back(), x1 = std::min(W, x0 + CW);
-            if (x0 < next && x1 > next && x1 < next + nr) x1 = next;            // block would straddle: cut before it
-            if (x0 < next + nr && x0 >= next && x1 < next + nr) return "internal error: diagonal block wider than a chunk";
+            const int x0 = cuts.back();
+            int x1 = std::min(W, x0 + CW);
+            while (x1 > x0 && !cut_ok[x1]) --x1;
+            if (x1 == x0) return "internal error: no admissible chunk boundary";
             cuts.push_back(x1);
         }
         for (size_t ci = 0; ci + 1 < cuts.size(); ++ci) {
             const int x0 = cuts[ci], x1 = cuts[ci + 1];
-            PanelPlan::Unit u;
-            u.panel = P; u.x0 = x0; u.x1 = x1;
-            u.step0 = (int32_t)pp.s_e.size();
-            u.map0 = (int32_t)(pp.maps.size() / CW);
-            u.diag_here = (next >= x0 && next < x1) ? 1 : 0;
-            u.diag_before = (next + nr <= x0) ? 1 : 0;
-            // candidate pivots: external columns left of the chunk (PRE) and inside it (INCHUNK)
-            std::vector<int32_t> unit_maps;     // source panel ids, in first-use order
-            auto map_for = [&](int32_t Q) -> int32_t {
-                for (size_t z = 0; z < unit_maps.size(); ++z) if (unit_maps[z] == Q) return (int32_t)z;
-                // build the map: chunk column c -> position in C_Q (or -1)
+            const int32_t task0 = (int32_t)pp.n_tasks();
+            const int dmode = (next >= x0 && next < x1) ? 1 : (next + nr <= x0 ? 2 : 0);
+            const int lend = std::min(next, x1);
+            for (int e = 0; e < lend;) {
+                const int32_t Q = pp.row_panel[C[e]];
+                const int nq = pp.p_nrows[Q], WQ = pp.p_width[Q], nextQ = pp.p_next[Q];
+                if (pp.row_r[C[e]] != 0) return "internal error: source block is not complete";
                 const int32_t *CQ = pp.cols.data() + pp.p_cptr[Q];
-                for (int c = 0; c < pp.p_width[Q]; ++c) pos_in_Q[CQ[c]] = c;
-                for (int c = 0; c < CW; ++c) pp.maps.push_back(x0 + c < x1 ? pos_in_Q[C[x0 + c]] : -1);
-                for (int c = 0; c < pp.p_width[Q]; ++c) pos_in_Q[CQ[c]] = -1;
-                unit_maps.push_back(Q);
-                return (int32_t)unit_maps.size() - 1;
-            };
-            const int ext_end = std::min(next, x1);
-            u.n_pre = 0; u.n_ext = 0;
-            for (int e = 0; e < ext_end; ++e) {
-                const int32_t k = C[e];
-                const int32_t Q = pp.row_panel[k];
-                const int32_t *CQ = pp.cols.data() + pp.p_cptr[Q];
-                const int WQ = pp.p_width[Q];
-                // does row k (its panel pattern) reach into this chunk beyond column k?
-                int cnt = 0;
-                {
-                    const int lo = std::max(x0, e + 1);
-                    // two-pointer intersection of C[lo..x1) with CQ
-                    int a = lo, b2 = (int)(std::upper_bound(CQ, CQ + WQ, k) - CQ);
-                    while (a < x1 && b2 < WQ) {
-                        if (C[a] == CQ[b2]) { ++cnt; ++a; ++b2; }
-                        else if (C[a] < CQ[b2]) ++a; else ++b2;
-                    }
-                }
                 const bool inchunk = e >= x0;
-                if (cnt == 0 && !inchunk) continue;      // in-chunk pivots are always finalised (their L value must be stored)
-                pp.s_e.push_back(e);
-                pp.s_k.push_back(k);
-                pp.s_src.push_back(pp.p_base[Q] + pp.row_r[k] * WQ);
-                pp.s_map.push_back(cnt ? map_for(Q) : -1);
-                if (inchunk) ++u.n_ext; else ++u.n_pre;
-                pp.n_fma_padded += (int64_t)cnt * nr;
-            }
-            // PRE steps must precede in-chunk steps: they already do (e ascending, x0 splits them)
-            u.n_maps = (int32_t)unit_maps.size();
-            if (u.diag_here || u.diag_before) pp.n_fma_padded += (int64_t)nr * (nr - 1) / 2 * std::max(0, x1 - std::max(x0, next));
-            pp.units.push_back(u);
-        }
-    }
-    // ---- per-step staging tables.  The part of the pivot row that a unit needs is one contiguous
-    // slot range of the source panel's storage; the CTA copies that range into shared memory
-    // (SEG slots per stage) and every lane looks its targets up with a byte index relative to the
-    // range start.  A pivot whose targets span more than SEG source slots is split into several
-    // steps; the follow-up steps reuse the already published multipliers.
-    {
-        const int NQ = CW / 32, SEG = PanelPlan::SEG;
-        std::vector<int32_t> ne, nk, nsrc, nmap, nflag;
-        pp.s_meta.clear(); pp.s_idx.clear();
-        for (auto &u : pp.units) {
-            const int nsteps = u.n_pre + u.n_ext;
-            const int old0 = u.step0;
-            u.step0 = (int32_t)ne.size();
-            int n_pre_new = 0, n_in_new = 0;
-            for (int z = 0; z < nsteps; ++z) {
-                const size_t st = (size_t)old0 + z;
-                const bool pre = z < u.n_pre;
-                // absolute source slot per chunk column (or -1)
-                std::vector<int32_t> off(CW, -1);
-                if (pp.s_map[st] >= 0) {
-                    const int32_t *mp = pp.maps.data() + ((size_t)u.map0 + pp.s_map[st]) * CW;
-                    const int ce = pp.s_e[st] - u.x0;
-                    for (int cl = 0; cl < CW; ++cl)
-                        if (mp[cl] >= 0 && cl > ce) off[cl] = pp.s_src[st] + mp[cl];
+                const int32_t map0 = (int32_t)pp.map.size();
+                int ntg = 0;
+                for (int cq = nextQ + nq; cq < WQ; ++cq) {
+                    const int ppos = pos_in_P[CQ[cq]];
+                    if (ppos >= x0 && ppos < x1) { pp.map.push_back(cq | ((ppos - x0) << 16)); ++ntg; }
                 }
-                bool first = true;
-                for (;;) {
-                    int32_t lo = -1;
-                    for (int cl = 0; cl < CW; ++cl) if (off[cl] >= 0 && (lo < 0 || off[cl] < lo)) lo = off[cl];
-                    if (lo < 0 && !first) break;
-                    int32_t hi = lo;
-                    std::vector<int8_t> idx(CW, (int8_t)SEG);   // SEG = the stage's constant zero row
-                    if (lo >= 0)
-                        for (int cl = 0; cl < CW; ++cl)
-                            if (off[cl] >= 0 && off[cl] - lo < SEG) { idx[cl] = (int8_t)(off[cl] - lo); hi = std::max(hi, off[cl]); off[cl] = -1; }
-                    ne.push_back(pp.s_e[st]); nk.push_back(pp.s_k[st]);
-                    // meta: {first source slot, number of slots, pivot column, flags (1 = reuse multipliers)}
-                    pp.s_meta.push_back(lo < 0 ? 0 : lo);
-                    pp.s_meta.push_back(lo < 0 ? 0 : hi - lo + 1);
-                    pp.s_meta.push_back(pp.s_e[st]);
-                    pp.s_meta.push_back((first || pre) ? 0 : 1);   // in-chunk follow-ups reuse the published multipliers
-                    for (int cs = 0; cs < 32; ++cs) {
-                        uint32_t wd = 0;
-                        for (int q = 0; q < NQ; ++q) wd |= (uint32_t)(uint8_t)idx[cs * NQ + q] << (8 * q);
-                        pp.s_idx.push_back((int32_t)wd);
-                    }
-                    if (pre) ++n_pre_new; else ++n_in_new;
-                    first = false;
-                    if (lo < 0) break;
+                if (inchunk || ntg > 0) {
+                    pp.t_info.push_back(Q);
+                    pp.t_info.push_back(e | (inchunk ? (1 << 30) : 0));
+                    pp.t_info.push_back(ntg);
+                    pp.t_info.push_back(map0);
+                    pp.n_fma_padded += (int64_t)ntg * nr * nq + (inchunk ? (int64_t)nr * nq * (nq - 1) / 2 : 0);
                 }
+                e += nq;
             }
-            u.n_pre = n_pre_new; u.n_ext = n_in_new;
+            if (dmode) pp.n_fma_padded += (int64_t)nr * (nr - 1) / 2 * std::max(0, x1 - std::max(x0, next));
+            const int32_t ntask = (int32_t)pp.n_tasks() - task0;
+            const int32_t ui[8] = {P, x0, x1, task0, ntask, dmode, 0, 0};
+            pp.u_info.insert(pp.u_info.end(), ui, ui + 8);
         }
-        pp.s_e.swap(ne); pp.s_k.swap(nk);
-        pp.s_src.clear(); pp.s_map.clear(); pp.maps.clear();
-    }
-    // ---- blocks: up to NB consecutive steps share one barrier round.  In-chunk steps of one block
-    // all belong to the same owner lane (NQ consecutive pivot columns of one thread), which resolves
-    // the dependencies among its pivots before publishing their multipliers together.
-    {
-        const int NB = PanelPlan::NB, NQ = CW / 32;
-        pp.b_info.clear(); pp.b_idx.clear();
-        for (auto &u : pp.units) {
-            u.block0 = (int32_t)(pp.b_info.size() / 4);
-            const int n = u.n_pre + u.n_ext;
-            int z = 0;
-            while (z < n) {
-                const bool pre = z < u.n_pre;
-                const int lim = pre ? u.n_pre : n;
-                int cnt = 1;
-                const int owner = pre ? -1 : (pp.s_meta[4 * ((size_t)u.step0 + z) + 2] - u.x0) / NQ;
-                // multiplier buffer index of each step: new pivot -> next buffer, follow-up -> same buffer
-                int lj = 0;
-                std::vector<int> ljs{0};
-                while (z + cnt < lim && cnt < NB) {
-                    const size_t st = (size_t)u.step0 + z + cnt;
-                    const bool follow = (pp.s_meta[4 * st + 3] & 1) != 0;
-                    if (!pre && !follow && (pp.s_meta[4 * st + 2] - u.x0) / NQ != owner) break;
-                    if (!follow) ++lj;
-                    ljs.push_back(lj);
-                    ++cnt;
-                }
-                // a follow-up must stay in the block of its pivot
-                while (cnt > 1 && z + cnt < lim && (pp.s_meta[4 * ((size_t)u.step0 + z + cnt) + 3] & 1)) { --cnt; ljs.pop_back(); }
-                if (z + cnt < lim && (pp.s_meta[4 * ((size_t)u.step0 + z + cnt) + 3] & 1))
-                    return "a pivot row needs more staged segments than one block holds (unsupported pattern)";
-                for (int j = 0; j < cnt; ++j) pp.s_meta[4 * ((size_t)u.step0 + z + j) + 3] |= ljs[j] << 8;
-                int ljcode = 0;
-                for (int j = 0; j < cnt; ++j) ljcode |= ljs[j] << (8 + 2 * j);
-                pp.b_info.push_back(z); pp.b_info.push_back(cnt); pp.b_info.push_back((pre ? 0 : 1) | ljcode); pp.b_info.push_back(owner);
-                for (int cs = 0; cs < 32; ++cs)
-                    for (int j = 0; j < NB; ++j)
-                        pp.b_idx.push_back(j < cnt ? pp.s_idx[((size_t)u.step0 + z + j) * 32 + cs] : (int32_t)0x40404040);
-                z += cnt;
-            }
-            u.n_blocks = (int32_t)(pp.b_info.size() / 4) - u.block0;
-        }
+        for (int c = 0; c < W; ++c) pos_in_P[C[c]] = -1;
     }
     pp.ready = true;
     return "";

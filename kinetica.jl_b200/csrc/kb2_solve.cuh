@@ -1,61 +1,98 @@
-// Kernels that compose the tile primitives: stand-alone entry points and the fused solve.
+// Kernels that compose the warp-tile primitives: stand-alone entry points and the fused solve.
+// Every kernel runs one warp per CTA; a warp owns one tile of MB members at a time.
 #pragma once
 #include "kb2_kernels.cuh"
-#include "kb2_panel.cuh"
 
 namespace kb2 {
+
+__host__ __device__ constexpr size_t lu_smem_bytes(int mb) { return lu_smem_doubles(mb) * sizeof(double); }
+
+// ---------------------------------------------------------------------------------------------
+// Layout conversion between the caller's row-major [row][B] arrays and the tile-major device
+// layout [tile][row][MB]
+// ---------------------------------------------------------------------------------------------
+template <int MB>
+__global__ void k_rows_to_tiles(const double *rows, double *tiles, size_t nrows, int B, int Bt, size_t row_stride)
+{
+    const size_t n = nrows * (size_t)Bt;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = idx / Bt;
+        const int b = (int)(idx % Bt);
+        const double v = b < B ? rows[i * row_stride + (row_stride ? b : 0)] : 0.0;
+        tiles[((size_t)(b / MB) * nrows + i) * MB + b % MB] = v;
+    }
+}
+
+template <int MB>
+__global__ void k_tiles_to_rows(const double *tiles, double *rows, size_t nrows, int B)
+{
+    const size_t n = nrows * (size_t)B;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = idx / B;
+        const int b = (int)(idx % B);
+        rows[idx] = tiles[((size_t)(b / MB) * nrows + i) * MB + b % MB];
+    }
+}
+
+// tile-major [tile][S][MB] -> member-major [B][S] pack for the allgather
+template <int MB>
+__global__ void k_pack_bs(int S, int B, const double *tiles, double *dst)
+{
+    const size_t n = (size_t)S * B;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / S), i = (int)(idx % S);
+        dst[idx] = tiles[((size_t)(b / MB) * S + i) * MB + b % MB];
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Stand-alone kernels (kernel-level C-ABI entry points, per-kernel roofline timing)
 // ---------------------------------------------------------------------------------------------
 template <int MB>
-__global__ void k_rates(DevNet net, DevEns en, const double *T, int ntiles)
+__global__ void __launch_bounds__(32) k_rates(DevNet net, DevPlan pl, DevEns en, const double *T, int ntiles)
 {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        Tile<MB> tl(tile, en.Bp);
-        tile_rates(tl, net, en.k, T[tl.b], true, -1);
+        WTile<MB> tl(tile, net, pl, en);
+        tile_rates(tl, net, T[tl.b], true, -1);
     }
 }
 
 template <int MB>
-__global__ void k_rhs(DevNet net, DevEns en, int ntiles)
+__global__ void __launch_bounds__(32) k_rhs(DevNet net, DevPlan pl, DevEns en, int ntiles)
 {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        Tile<MB> tl(tile, en.Bp);
-        tile_rhs(tl, net, en.u, en.k, en.rv, 0, nullptr, nullptr);
+        WTile<MB> tl(tile, net, pl, en);
+        tile_rhs(tl, net, tl.u, tl.rv, 0, nullptr, nullptr);
+    }
+}
+
+// Jacobian values in CSC order, written tile-major into the (larger) LU storage of the tile
+template <int MB>
+__global__ void __launch_bounds__(32) k_jac(DevNet net, DevPlan pl, DevEns en, int ntiles)
+{
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        WTile<MB> tl(tile, net, pl, en);
+        tile_jac_csc(tl, net, tl.u, tl.lu);
     }
 }
 
 template <int MB>
-__global__ void k_jac(DevNet net, DevEns en, double *Jval, int ntiles)
-{
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        Tile<MB> tl(tile, en.Bp);
-        tile_jac_csc(tl, net, en.u, en.k, Jval);
-    }
-}
-
-template <int MB, int MINB>
-__global__ void __launch_bounds__(32 * MB, MINB) k_factor(DevNet net, DevPlan pl, DevEns en, const double *hg_inv, int ntiles, int mode)
+__global__ void __launch_bounds__(32) k_factor(DevNet net, DevPlan pl, DevEns en, const double *hg_inv, int ntiles, int mode)
 {
     extern __shared__ double smem[];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        Tile<MB> tl(tile, en.Bp);
-        if (mode & 1) tile_assemble_w(tl, net, en.u, en.k, hg_inv[tl.b], en.lu);
-        __syncthreads();
-        if (mode & 2) tile_lu_panels(tl, pl, en.lu, en.invd, smem);
-        __syncthreads();
+        WTile<MB> tl(tile, net, pl, en);
+        if (mode & 1) tile_assemble_w(tl, net, pl, tl.u, hg_inv[tl.b]);
+        if (mode & 2) tile_lu(tl, pl, smem);
     }
 }
 
-template <int MB, int MINB>
-__global__ void __launch_bounds__(32 * MB, MINB) k_trisolve(DevNet net, DevPlan pl, DevEns en, int ntiles)
+template <int MB>
+__global__ void __launch_bounds__(32) k_trisolve(DevNet net, DevPlan pl, DevEns en, int ntiles)
 {
-    extern __shared__ double smem[];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        Tile<MB> tl(tile, en.Bp);
-        tile_trisolve_panels(tl, net, pl, en.lu, en.invd, en.rv, en.y, en.ua, smem);
-        __syncthreads();
+        WTile<MB> tl(tile, net, pl, en);
+        tile_trisolve(tl, net, pl, tl.rv, tl.ua);
     }
 }
 
@@ -67,256 +104,231 @@ __global__ void k_profile(int B, int nt, const int *kind, const double *params, 
     X[idx] = profile_eval(kind[b], params + (size_t)b * 16, t[s]);
 }
 
-// [S][Bp] -> member-major [B][S] pack for the allgather (transpose fused into the pack)
-__global__ void k_pack_bs(int S, int B, int Bp, const double *src, double *dst)
-{
-    __shared__ double tile[32][33];
-    int b0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int i = i0 + r, b = b0 + threadIdx.x;
-        tile[r][threadIdx.x] = (i < S && b < Bp) ? src[(size_t)i * Bp + b] : 0.0;
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int b = b0 + r, i = i0 + threadIdx.x;
-        if (b < B && i < S) dst[(size_t)b * S + i] = tile[threadIdx.x][r];
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// The fused solve: one CTA integrates one tile of MB members from t0 to the last stop.
+// The fused solve: one warp integrates one tile of MB members from t0 to the last stop.
 // Rodas4 with per-member adaptive h; accept/reject and stop handling are masked per member while
-// the tile moves in lock-step.  Replaces init/solve!/reinit! of `pars.solver` and the
-// PresetTimeCallback rate update (reference src/solving/methods.jl:655-714,
+// the tile moves in lock-step.  The control state of a member is replicated in the registers of
+// its LN lanes (same inputs, same arithmetic, same decisions).  Replaces init/solve!/reinit! of
+// `pars.solver` and the PresetTimeCallback rate update (reference src/solving/methods.jl:655-714,
 // src/solving/solve_utils.jl:376-450).
 // ---------------------------------------------------------------------------------------------
-template <int MB>
 struct Ctl {
-    double t[MB], h[MB], hs[MB], hold[MB], errold[MB], T[MB];
-    long long iters[MB];
-    int ns[MB], si[MB], isave[MB], status[MB], hit[MB], active[MB], rejlast[MB], firstacc[MB], accept[MB], upd[MB], ridx[MB], sav[MB];
-    int nacc[MB], nrej[MB], nlu[MB], nrhs[MB];
+    double t, h, hs, hold, errold, T, hfirst;
+    long long iters;
+    int ns, si, isave, status, hit, active, rejlast, firstacc, accept, upd, ridx, sav, fresh;
+    int nacc, nrej, nlu, nrhs;
 };
 
 enum { ST_RUNNING = -1 };
 
 template <int MB>
-__device__ void tile_process_stop(const Tile<MB> &tl, const DevNet &net, const DevEns &en, Ctl<MB> &c, bool at_start)
+__device__ void tile_process_stop(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, bool at_start)
 {
-    // slot-0 thread of each member decides what its member does at this stop
-    if (tl.slot == 0) {
-        const int m = tl.m;
-        c.upd[m] = 0; c.sav[m] = -1;
-        const size_t sb = (size_t)tl.b * en.nstops;
-        const bool due = at_start ? (c.status[m] == ST_RUNNING && c.si[m] < c.ns[m] && en.stop_t[sb + c.si[m]] <= en.t0)
-                                  : (c.accept[m] && c.hit[m]);
-        if (due) {
-            const int s = c.si[m], fl = en.stop_flags[sb + s];
-            if (fl & 1) {
-                double T = en.Ttab ? en.Ttab[sb + s] : nan("");
-                if (isnan(T) && net.calc_mode == 0) T = profile_eval(en.pkind[tl.b], en.pparams + (size_t)tl.b * 16, en.stop_t[sb + s]);
-                c.T[m] = T; c.upd[m] = 1; c.ridx[m] = en.stop_ridx[sb + s];
-            }
-            if (fl & 2) c.sav[m] = c.isave[m]++;
-            c.si[m] = s + 1;
-            if (c.si[m] >= c.ns[m]) c.status[m] = 0;   // reached the end of tspan
+    constexpr int LN = 32 / MB;
+    c.upd = 0; c.sav = -1;
+    const size_t sb = (size_t)tl.b * en.nstops;
+    const bool due = at_start ? (c.status == ST_RUNNING && c.si < c.ns && en.stop_t[sb + c.si] <= en.t0)
+                              : (c.accept && c.hit);
+    if (due) {
+        const int s = c.si, fl = en.stop_flags[sb + s];
+        if (fl & 1) {
+            double T = en.Ttab ? en.Ttab[sb + s] : nan("");
+            if (isnan(T) && net.calc_mode == 0) T = profile_eval(en.pkind[tl.b], en.pparams + (size_t)tl.b * 16, en.stop_t[sb + s]);
+            c.T = T; c.upd = 1; c.ridx = en.stop_ridx[sb + s];
         }
+        if (fl & 2) c.sav = c.isave++;
+        c.si = s + 1;
+        if (c.si >= c.ns) c.status = 0;   // reached the end of tspan
     }
-    __syncthreads();
-    const int m = tl.m;
-    if (__syncthreads_or(c.upd[m])) tile_rates(tl, net, en.k, c.T[m], c.upd[m] != 0, c.ridx[m]);
-    const int sv = c.sav[m];
-    if (__syncthreads_or(sv >= 0)) {
+    if (__any_sync(FULL, c.upd)) tile_rates(tl, net, c.T, c.upd != 0, c.ridx);
+    const int sv = c.sav;
+    if (__any_sync(FULL, sv >= 0)) {
         if (sv >= 0)
-            for (int i = tl.slot; i < net.S; i += tl.nslot) {
-                const double v = en.u[(size_t)i * tl.Bp + tl.b];
-                en.out_u[((size_t)sv * net.S + i) * tl.Bp + tl.b] = v;
-                double *mx = en.out_umax + (size_t)i * tl.Bp + tl.b;
+            for (int i = tl.ln; i < net.S; i += LN) {
+                const double v = tl.u[i * MB + tl.m];
+                tl.out_u[((size_t)sv * net.S + i) * MB + tl.m] = v;
+                double *mx = tl.out_umax + i * MB + tl.m;
                 *mx = (sv == 0) ? v : fmax(*mx, v);
             }
+        __syncwarp();
     }
-    __syncthreads();
 }
 
 // Starting step size (Hairer-Nørsett-Wanner II.4, order 4).  Called once at t0 (`initial`) and
-// again after every discrete rate update, where the RHS jumps: members flagged in c.upd get
-// h = min(h, estimate).  Uses rv, ua, y as scratch.
+// again after a discrete rate update, where the RHS jumps, for members that have no step-size
+// memory yet: they get h = min(h, 0.1 * estimate).  Uses rv, ua, y as scratch.
 template <int MB>
-__device__ void tile_hinit(const Tile<MB> &tl, const DevNet &net, const DevEns &en, Ctl<MB> &c, double *red, bool initial)
+__device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, bool initial)
 {
-    const int m = tl.m, b = tl.b;
-    const size_t Bp = tl.Bp;
-    tile_rhs(tl, net, en.u, en.k, en.rv, 0, nullptr, nullptr);
-    __syncthreads();
+    constexpr int LN = 32 / MB;
+    const int m = tl.m;
+    tile_rhs(tl, net, tl.u, tl.rv, 0, nullptr, nullptr);
     double d0 = 0, d1 = 0;
-    for (int i = tl.slot; i < net.S; i += tl.nslot) {
-        const double ui = en.u[(size_t)i * Bp + b], fi = en.rv[(size_t)i * Bp + b];
+    for (int i = tl.ln; i < net.S; i += LN) {
+        const double ui = tl.u[i * MB + m], fi = tl.rv[i * MB + m];
         const double sc = en.abstol + en.reltol * fabs(ui);
         d0 += (ui / sc) * (ui / sc); d1 += (fi / sc) * (fi / sc);
     }
-    d0 = sqrt(tile_sum(tl, d0, red) / net.S);
-    d1 = sqrt(tile_sum(tl, d1, red) / net.S);
+    d0 = sqrt(member_sum<MB>(d0) / net.S);
+    d1 = sqrt(member_sum<MB>(d1) / net.S);
     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-    for (int i = tl.slot; i < net.S; i += tl.nslot)
-        en.ua[(size_t)i * Bp + b] = en.u[(size_t)i * Bp + b] + h0 * en.rv[(size_t)i * Bp + b];
-    __syncthreads();
-    tile_rhs(tl, net, en.ua, en.k, en.y, 0, nullptr, nullptr);
-    __syncthreads();
+    for (int i = tl.ln; i < net.S; i += LN) tl.ua[i * MB + m] = tl.u[i * MB + m] + h0 * tl.rv[i * MB + m];
+    __syncwarp();
+    tile_rhs(tl, net, tl.ua, tl.y, 0, nullptr, nullptr);
     double d2 = 0;
-    for (int i = tl.slot; i < net.S; i += tl.nslot) {
-        const double sc = en.abstol + en.reltol * fabs(en.u[(size_t)i * Bp + b]);
-        const double q = (en.y[(size_t)i * Bp + b] - en.rv[(size_t)i * Bp + b]) / sc;
+    for (int i = tl.ln; i < net.S; i += LN) {
+        const double sc = en.abstol + en.reltol * fabs(tl.u[i * MB + m]);
+        const double q = (tl.y[i * MB + m] - tl.rv[i * MB + m]) / sc;
         d2 += q * q;
     }
-    d2 = sqrt(tile_sum(tl, d2, red) / net.S) / h0;
+    d2 = sqrt(member_sum<MB>(d2) / net.S) / h0;
     const double dm = fmax(d1, d2);
     const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
     const double hn = fmin(100.0 * h0, h1);
-    if (tl.slot == 0) {
-        if (initial) { c.h[m] = hn; c.hold[m] = hn; c.nrhs[m] += 2; }
-        else if (c.upd[m] && c.status[m] == ST_RUNNING) { c.h[m] = fmin(c.h[m], 0.1 * hn); c.nrhs[m] += 2; }   // 0.1: see DESIGN.md §3
-    }
-    __syncthreads();
+    if (initial) { c.h = hn; c.hold = hn; c.nrhs += 2; }
+    else if (c.upd && c.status == ST_RUNNING && !(c.hfirst > 0.0)) { c.h = fmin(c.h, 0.1 * hn); c.nrhs += 2; }
+    __syncwarp();
+}
+
+// Step size after a discrete rate update.  The jump in k throws the fast species off their
+// quasi-steady state, so the step must drop to the fast time scale again; consecutive updates of
+// a profile are alike, so the step size that the controller found optimal right after the
+// previous update (c.hfirst) is the prediction for this one.  Members without that memory fall
+// back to the starting-step estimate.
+template <int MB>
+__device__ void tile_restart_h(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c)
+{
+    const bool upd = c.upd && c.status == ST_RUNNING;
+    if (upd) { c.fresh = 1; c.firstacc = 1; }
+    if (__any_sync(FULL, upd && !(c.hfirst > 0.0))) tile_hinit(tl, net, en, c, false);
+    if (upd && c.hfirst > 0.0) c.h = fmin(c.h, c.hfirst);
 }
 
 template <int MB>
-__device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en, Ctl<MB> &c, double *lbuf, double *red)
+__device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en, double *Wp)
 {
-    Tile<MB> tl(tile, en.Bp);
-    const int m = tl.m;
-    const size_t Bp = tl.Bp;
-    const int b = tl.b;
-    if (tl.slot == 0) {
-        c.t[m] = en.t0; c.si[m] = 0; c.isave[m] = 0; c.iters[m] = 0;
-        c.ns[m] = en.stop_cnt[b];
-        c.status[m] = (b < en.B && c.ns[m] > 0) ? ST_RUNNING : 0;
-        c.nacc[m] = c.nrej[m] = c.nlu[m] = c.nrhs[m] = 0;
-        c.rejlast[m] = 0; c.firstacc[m] = 1; c.accept[m] = 0; c.hit[m] = 0;
-        c.errold[m] = 1.0;
-        // initial conditions: static -> value, variable -> X_start (condition_set.jl:111-121);
-        // both sit in the profile's X(0) for every supported kind
-        c.T[m] = (net.calc_mode == 0) ? profile_eval(en.pkind[b], en.pparams + (size_t)b * 16, -1.0) : 0.0;
-    }
-    __syncthreads();
-    tile_rates(tl, net, en.k, c.T[m], true, -1);     // k(initial conditions), methods.jl:668
-    __syncthreads();
+    constexpr int LN = 32 / MB;
+    WTile<MB> tl(tile, net, pl, en);
+    const int m = tl.m, b = tl.b, ln = tl.ln;
+    Ctl c;
+    c.t = en.t0; c.si = 0; c.isave = 0; c.iters = 0;
+    c.ns = en.stop_cnt[b];
+    c.status = (b < en.B && c.ns > 0) ? ST_RUNNING : 0;
+    c.nacc = c.nrej = c.nlu = c.nrhs = 0;
+    c.rejlast = 0; c.firstacc = 1; c.accept = 0; c.hit = 0; c.active = 0; c.upd = 0; c.ridx = -1; c.sav = -1;
+    c.errold = 1.0; c.h = 0.0; c.hs = 1.0; c.hold = 0.0; c.hfirst = 0.0; c.fresh = 0;
+    // initial conditions: static -> value, variable -> X_start (condition_set.jl:111-121); both sit
+    // in the profile's X(0) for every supported kind
+    c.T = (net.calc_mode == 0) ? profile_eval(en.pkind[b], en.pparams + (size_t)b * 16, -1.0) : 0.0;
+    tile_rates(tl, net, c.T, true, -1);     // k(initial conditions), methods.jl:668
     tile_process_stop(tl, net, en, c, true);
-    tile_hinit(tl, net, en, c, red, true);
+    tile_hinit(tl, net, en, c, true);
+    const size_t sb = (size_t)b * en.nstops;
     // ---- main loop ----
     for (;;) {
-        if (tl.slot == 0) {
-            int act = (c.status[m] == ST_RUNNING);
+        {
+            int act = (c.status == ST_RUNNING);
             double hs = 1.0;
             int hit = 0;
             if (act) {
-                if (++c.iters[m] > en.maxiters) { c.status[m] = 1; act = 0; }
+                if (++c.iters > en.maxiters) { c.status = 1; act = 0; }
                 else {
-                    const double tstop = en.stop_t[(size_t)b * en.nstops + c.si[m]];
-                    hs = c.h[m];
-                    if (c.t[m] + 1.01 * hs >= tstop) { hs = tstop - c.t[m]; hit = 1; }
-                    if (hs < en.dtmin && !hit) { c.status[m] = 2; act = 0; hs = 1.0; }
+                    const double tstop = en.stop_t[sb + c.si];
+                    hs = c.h;
+                    if (c.t + 1.01 * hs >= tstop) { hs = tstop - c.t; hit = 1; }
+                    if (hs < en.dtmin && !hit) { c.status = 2; act = 0; hs = 1.0; }
                 }
             }
-            c.active[m] = act; c.hs[m] = hs; c.hit[m] = hit; c.accept[m] = 0;
+            c.active = act; c.hs = hs; c.hit = hit; c.accept = 0;
         }
-        __syncthreads();
-        if (!__syncthreads_or(c.active[m])) break;
-        const double hs = c.hs[m];
-        tile_assemble_w(tl, net, en.u, en.k, 1.0 / (hs * kGamma), en.lu);
-        __syncthreads();
-        tile_lu_panels(tl, pl, en.lu, en.invd, lbuf);
-        __syncthreads();
+        if (!__any_sync(FULL, c.active)) break;
+        const double hs = c.hs;
+        tile_assemble_w(tl, net, pl, tl.u, 1.0 / (hs * kGamma));
+        tile_lu(tl, pl, Wp);
         for (int s = 0; s < 6; ++s) {
-            const double *Us = en.u;
+            const double *Us = tl.u;
             if (s > 0) {
-                for (int i = tl.slot; i < net.S; i += tl.nslot) {
-                    const size_t o = (size_t)i * Bp + b;
-                    double a = en.u[o];
-                    for (int q = 0; q < s; ++q) a += cA[s][q] * en.K[q][o];
-                    en.ua[o] = a;
+                for (int i = ln; i < net.S; i += LN) {
+                    const int o = i * MB + m;
+                    double a = tl.u[o];
+                    for (int q = 0; q < s; ++q) a += cA[s][q] * tl.K[q][o];
+                    tl.ua[o] = a;
                 }
-                __syncthreads();
-                Us = en.ua;
+                __syncwarp();
+                Us = tl.ua;
             }
             double cs[5];
             for (int q = 0; q < s; ++q) cs[q] = cC[s][q] / hs;
-            tile_rhs(tl, net, Us, en.k, en.rv, s, en.K, cs);
-            __syncthreads();
-            tile_trisolve_panels(tl, net, pl, en.lu, en.invd, en.rv, en.y, en.K[s], red);
-            __syncthreads();
+            tile_rhs(tl, net, Us, tl.rv, s, tl.K, cs);
+            tile_trisolve(tl, net, pl, tl.rv, tl.K[s]);
         }
         // error estimate = K6; new solution = ua + K6
         double e2 = 0.0;
         int neg = 0;
-        for (int i = tl.slot; i < net.S; i += tl.nslot) {
-            const size_t o = (size_t)i * Bp + b;
-            const double k6 = en.K[5][o], un = en.ua[o] + k6;
-            const double sc = en.abstol + en.reltol * fmax(fabs(en.u[o]), fabs(un));
+        for (int i = ln; i < net.S; i += LN) {
+            const int o = i * MB + m;
+            const double k6 = tl.K[5][o], un = tl.ua[o] + k6;
+            const double sc = en.abstol + en.reltol * fmax(fabs(tl.u[o]), fabs(un));
             e2 += (k6 / sc) * (k6 / sc);
             neg |= (un < 0.0);
         }
-        double err = sqrt(tile_sum(tl, e2, red) / net.S);
-        const double nneg = en.ban_neg ? tile_sum(tl, (double)neg, red) : 0.0;
+        double err = sqrt(member_sum<MB>(e2) / net.S);
+        const double nneg = en.ban_neg ? member_sum<MB>((double)neg) : 0.0;
         if (!(err < INFINITY)) err = INFINITY;          // NaN/Inf (singular pivot, overflow) -> reject
         if (nneg > 0.0) err = fmax(err, 1e4);            // isoutofdomain, methods.jl:169-171
-        if (tl.slot == 0 && c.active[m]) {
+        if (c.active) {
             double fac = (err < INFINITY) ? fmax(1.0 / 6.0, fmin(5.0, pow(err, 0.25) / 0.9)) : 5.0;
             double hnew = hs / fac;
-            c.nlu[m]++; c.nrhs[m] += 6;
+            c.nlu++; c.nrhs += 6;
             if (err <= 1.0) {
-                c.nacc[m]++;
-                if (!c.firstacc[m]) {
-                    double facgus = (c.hold[m] / hs) * pow(err * err / c.errold[m], 0.25) / 0.9;
+                c.nacc++;
+                if (!c.firstacc) {
+                    double facgus = (c.hold / hs) * pow(err * err / c.errold, 0.25) / 0.9;
                     facgus = fmax(1.0 / 6.0, fmin(5.0, facgus));
                     fac = fmax(fac, facgus);
                     hnew = hs / fac;
                 }
-                c.firstacc[m] = 0;
-                c.hold[m] = hs; c.errold[m] = fmax(1e-2, err);
-                if (c.rejlast[m]) hnew = fmin(hnew, hs);
-                c.rejlast[m] = 0;
-                c.accept[m] = 1;
-                if (c.hit[m]) { c.t[m] = en.stop_t[(size_t)b * en.nstops + c.si[m]]; c.h[m] = fmax(hnew, c.h[m]); }
-                else { c.t[m] += hs; c.h[m] = hnew; }
+                if (c.fresh) { c.hfirst = hs / fmax(1.0 / 6.0, fmin(5.0, pow(err, 0.25) / 0.9)); c.fresh = 0; }
+                c.firstacc = 0;
+                c.hold = hs; c.errold = fmax(1e-2, err);
+                if (c.rejlast) hnew = fmin(hnew, hs);
+                c.rejlast = 0;
+                c.accept = 1;
+                if (c.hit) { c.t = en.stop_t[sb + c.si]; c.h = fmax(hnew, c.h); }
+                else { c.t += hs; c.h = hnew; }
             } else {
-                c.nrej[m]++; c.rejlast[m] = 1; c.h[m] = hnew;
-                if (hnew < en.dtmin) c.status[m] = 2;
+                c.nrej++; c.rejlast = 1; c.h = hnew;
+                if (hnew < en.dtmin) c.status = 2;
             }
         }
-        __syncthreads();
-        if (c.accept[m])
-            for (int i = tl.slot; i < net.S; i += tl.nslot) {
-                const size_t o = (size_t)i * Bp + b;
-                en.u[o] = en.ua[o] + en.K[5][o];
+        if (c.accept)
+            for (int i = ln; i < net.S; i += LN) {
+                const int o = i * MB + m;
+                tl.u[o] = tl.ua[o] + tl.K[5][o];
             }
-        __syncthreads();
+        __syncwarp();
         tile_process_stop(tl, net, en, c, false);
-        if (__syncthreads_or(c.upd[m])) tile_hinit(tl, net, en, c, red, false);
+        if (__any_sync(FULL, c.upd)) tile_restart_h(tl, net, en, c);
     }
-    if (tl.slot == 0 && b < en.B) {
-        en.status[b] = c.status[m] == ST_RUNNING ? 5 : c.status[m];
+    if (ln == 0 && b < en.B) {
+        en.status[b] = c.status == ST_RUNNING ? 5 : c.status;
         long long *st = en.stats + (size_t)b * 8;
-        st[0] = c.nacc[m]; st[1] = c.nrej[m]; st[2] = c.nlu[m]; st[3] = c.nrhs[m];
-        st[4] = c.isave[m]; st[5] = c.si[m]; st[6] = 0; st[7] = 0;
+        st[0] = c.nacc; st[1] = c.nrej; st[2] = c.nlu; st[3] = c.nrhs;
+        st[4] = c.isave; st[5] = c.si; st[6] = 0; st[7] = 0;
     }
-    __syncthreads();
+    __syncwarp();
 }
 
-template <int MB, int MINB>
-__global__ void __launch_bounds__(32 * MB, MINB) k_solve(DevNet net, DevPlan pl, DevEns en, int ntiles, int *tile_counter)
+template <int MB>
+__global__ void __launch_bounds__(32) k_solve(DevNet net, DevPlan pl, DevEns en, int ntiles, int *tile_counter)
 {
     extern __shared__ double smem[];
-    __shared__ Ctl<MB> c;
-    __shared__ int s_tile;
-    double *lbuf = smem;
-    double *red = smem + lu_smem_doubles(32 * MB, MB);
     for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1);
-        __syncthreads();
-        const int tile = s_tile;
-        __syncthreads();
+        int tile = 0;
+        if ((threadIdx.x & 31) == 0) tile = atomicAdd(tile_counter, 1);
+        tile = __shfl_sync(FULL, tile, 0);
         if (tile >= ntiles) break;
-        solve_tile<MB>(tile, net, pl, en, c, lbuf, red);
+        solve_tile<MB>(tile, net, pl, en, smem);
     }
 }
 

@@ -258,21 +258,18 @@ std::string build_symbolic(const Network &net, int ordering, Symbolic &sym)
             sym.slot_src[q] = (p1 << 1) | (sym.colidx[q] == a ? 1 : 0);
         }
     }
-    // ---- elimination schedule ----
+    // ---- work orders of the gather loops (load balance: hub species have rows of hundreds of
+    // terms, which one lane must not walk alone) ----
     {
-        sym.tgt_off.assign(sym.nnzLU, 0);
-        sym.tgt.clear();
-        sym.tgt.reserve((size_t)sym.n_fma);
-        std::vector<int32_t> where(S, -1);
-        for (int64_t i = 0; i < S; ++i) {
-            for (int64_t q = sym.rowptr[i]; q < sym.rowptr[i + 1]; ++q) where[sym.colidx[q]] = (int32_t)(q - sym.rowptr[i]);
-            for (int64_t p = sym.rowptr[i]; p < sym.diagpos[i]; ++p) {
-                int64_t k = sym.colidx[p];
-                sym.tgt_off[p] = (uint32_t)sym.tgt.size();
-                for (int64_t q = sym.diagpos[k] + 1; q < sym.rowptr[k + 1]; ++q) sym.tgt.push_back(where[sym.colidx[q]]);
-            }
-        }
-        if ((int64_t)sym.tgt.size() != sym.n_fma) return "internal error: schedule size mismatch";
+        auto order_by_len = [](const std::vector<int32_t> &ptr, int64_t n, int thr, std::vector<int32_t> &ord, int32_t &nlong) {
+            ord.resize(n);
+            for (int64_t i = 0; i < n; ++i) ord[i] = (int32_t)i;
+            std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b]; });
+            nlong = 0;
+            while (nlong < n && ptr[ord[nlong] + 1] - ptr[ord[nlong]] > thr) ++nlong;
+        };
+        order_by_len(sym.rhs_ptr, S, Symbolic::RHS_LONG, sym.rhs_order, sym.rhs_nlong);
+        order_by_len(sym.jt_ptr, sym.nnzJ, Symbolic::JAC_LONG, sym.j_order, sym.j_nlong);
     }
     sym.ready = true;
     return "";

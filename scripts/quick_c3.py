@@ -23,8 +23,8 @@ for cs in conds:
 t = time.time()
 es = kb.EnsembleSolver(sd, rd, calc)
 print("symbolic+upload s", time.time() - t, "nnzJ nnzLU nfma", es.nnzJ, es.nnzLU, es.n_fma, flush=True)
-es.h.set_tiling(mb, nt)
-for rep in range(2):
+es.h.set_tiling(mb, 0)
+for rep in range(int(os.environ.get("KB2_REPS", "2"))):
     t = time.time()
     es.prepare(conds, pars, synthetic_u0(S))
     t1 = time.time()
@@ -33,6 +33,7 @@ for rep in range(2):
     out_u, umax, status, stats = es.fetch()
     t3 = time.time()
     print(f"rep{rep}: prepare {t1-t:.3f}s run {ms:.1f} ms (wall {t2-t1:.3f}) fetch {t3-t2:.3f}s  solves/s(device) {B/ms*1e3:.1f}")
+print("launch", es.h.get_launch_info())
 print("status counts", np.bincount(status), "steps acc mean/min/max", stats[:, 0].mean(), stats[:, 0].min(), stats[:, 0].max(),
       "rej mean", stats[:, 1].mean())
 for w, name in enumerate(["arrhenius", "rhs", "jac", "factor", "trisolve"]):

@@ -21,15 +21,15 @@ peak = 6546.2
 bytes_ = {"arrhenius": 8 * (R + 1), "rhs": 8 * (R + 2 * S), "jac": 8 * (R + S + h.nnzJ),
           "factor": 8 * (R + S + h.nnzJ + 2 * h.nnzLU), "trisolve": 8 * (h.nnzLU + 2 * S)}
 only = os.environ.get("KB2_ONLY")
-combos = [(8, 0), (8, 1), (4, 0), (4, 1), (16, 0), (2, 1)]
-if only:
-    combos = [(int(os.environ.get("KB2_MB", "8")), int(os.environ.get("KB2_VAR", "0")))]
-for mb, var in combos:
-    h.set_tiling(mb, var)
+combos = [int(x) for x in os.environ.get("KB2_MB", "4,2,1").split(",")]
+for mb in combos:
+    var = 0
+    h.set_tiling(mb, 0)
     h.eval_rhs(u, k)
     h.factor(u, k, np.full(B, 1e6), want_lu=False)
     out = []
     bytes_["assemble"] = 8 * (R + S + h.nnzJ + h.nnzLU); bytes_["lu_only"] = 8 * 2 * h.nnzLU
+    t0 = time.time()
     for w, nm in enumerate(["arrhenius", "rhs", "jac", "factor", "trisolve", "assemble", "lu_only"]):
         if only and nm not in only.split(","):
             continue
@@ -37,4 +37,4 @@ for mb, var in combos:
         gb = bytes_[nm] * B / ms / 1e6
         extra = f" {2 * h.n_fma * B / ms / 1e9:.2f}TF(exact) {2 * st['fma_padded'] * B / ms / 1e9:.2f}TF(padded)" if nm == "factor" else ""
         out.append(f"{nm} {ms:.3f}ms {gb:.0f}GB/s({gb / peak * 100:.1f}%)" + extra)
-    print(f"mb={mb} var={var}: " + " | ".join(out), flush=True)
+    print(f"mb={mb}: " + " | ".join(out), flush=True)
