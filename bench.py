@@ -140,7 +140,7 @@ def cpu_reference(name, n_members, steps, warmup, nthreads, tol="default"):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))

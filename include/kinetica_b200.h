@@ -77,7 +77,7 @@ int32_t kb2_get_lu_pattern(kb2_handle h, int64_t *rowptr, int64_t *colidx, int64
  * FMAs incl. padding, widest panel, target-map entries, block barriers per LU (always 0)} */
 int32_t kb2_get_plan_stats(kb2_handle h, int64_t *out);
 /* raw plan tables for host-side verification; which: 0 p_row0, 1 p_nrows, 2 p_width, 3 p_next,
- * 4 p_base, 5 p_cptr, 6 cols, 7 u_info (8 per unit), 8 t_info (4 per task), 9 map, 10 slot_of,
+ * 4 p_base, 5 p_cptr, 6 cols, 7 u_info (12 per unit), 8 t_info (12 per task), 9 map, 10 slot_of,
  * 11 jslot, 12 diag_slot.  Returns the length (copies when cap is large enough), -1 on error. */
 int64_t kb2_get_plan_array(kb2_handle h, int32_t which, int32_t *out, int64_t cap);
 

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkinetica_b200.so")
+LIB_PATH = os.environ.get("KB2_LIB") or os.path.join(_HERE, "libkinetica_b200.so")   # KB2_LIB: experimental builds only
 
 _i32, _i64, _f64 = C.c_int32, C.c_int64, C.c_double
 _pi32, _pi64, _pf64 = C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_f64)
@@ -168,8 +168,8 @@ class Handle:
             a = np.zeros(max(n, 1), dtype=np.int32)
             self._lib.kb2_get_plan_array(self._h, which, a.ctypes.data_as(_pi32), n)
             out[name] = a[:n]
-        out["u_info"] = out["u_info"].reshape(-1, 8)
-        out["t_info"] = out["t_info"].reshape(-1, 4)
+        out["u_info"] = out["u_info"].reshape(-1, 12)
+        out["t_info"] = out["t_info"].reshape(-1, 12)
         return out
 
     def get_launch_info(self):

@@ -451,6 +451,11 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
     rc |= dev_alloc(h, P, Bp, &h->scal);
     if (rc) { free_pool(h->ens_allocs); return rc; }
     e.Ns = (int)Ns;
+    {
+        bool fits = false;
+        warp_smem_bytes(e.MB, h->net.S, &fits);
+        e.u_smem = fits ? 1 : 0;
+    }
     h->ens_B = B; h->ens_Ns = Ns; h->ens_mb = e.MB;
     h->ens_fixed = P.size();
     return 0;
@@ -569,6 +574,21 @@ static int upload_uk(kb2_ctx *h, int64_t B, const double *u, const double *k)
     return rc;
 }
 
+static int launch_rhs(kb2_ctx *h)
+{
+    DevEns &e = h->de;
+    const int ntiles = n_tiles(e);
+    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr);
+    DISPATCH_MB(e.MB, {
+        int r = set_smem(h, k_rhs<MB>, smem);
+        if (r) return r;
+        k_rhs<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles);
+    });
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return 0;
+}
+
 extern "C" int32_t kb2_eval_rhs(kb2_handle h, int64_t B, const double *u, const double *k, double *du)
 {
     if (!h) return 1;
@@ -577,9 +597,7 @@ extern "C" int32_t kb2_eval_rhs(kb2_handle h, int64_t B, const double *u, const 
     if ((rc = upload_uk(h, B, u, k))) return rc;
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
-    DISPATCH_MB(e.MB, (k_rhs<MB><<<std::min(ntiles, 32 * h->sm_count), 32, 0, h->stream>>>(h->dn, h->dp, e, ntiles)));
-    h->launches++;
-    CU(h, cudaGetLastError());
+    if ((rc = launch_rhs(h))) return rc;
     if ((rc = down_tiles(h, du, e.rv, h->net.S, B))) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -609,7 +627,7 @@ static int launch_factor(kb2_ctx *h, const double *d_hg, int mode = 3)
 {
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
-    const size_t smem = lu_smem_bytes(e.MB);
+    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr);
     DISPATCH_MB(e.MB, {
         int r = set_smem(h, k_factor<MB>, smem);
         if (r) return r;
@@ -624,7 +642,12 @@ static int launch_trisolve(kb2_ctx *h)
 {
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
-    DISPATCH_MB(e.MB, (k_trisolve<MB><<<std::min(ntiles, 32 * h->sm_count), 32, 0, h->stream>>>(h->dn, h->dp, e, ntiles)));
+    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr);
+    DISPATCH_MB(e.MB, {
+        int r = set_smem(h, k_trisolve<MB>, smem);
+        if (r) return r;
+        k_trisolve<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles);
+    });
     h->launches++;
     CU(h, cudaGetLastError());
     return 0;
@@ -683,7 +706,7 @@ extern "C" int32_t kb2_time_kernel(kb2_handle h, int32_t which, int64_t B, int32
         int rc = 0;
         switch (which) {
         case 0: DISPATCH_MB(e.MB, (k_rates<MB><<<grid, 32, 0, h->stream>>>(h->dn, h->dp, e, h->scal, ntiles))); h->launches++; break;
-        case 1: DISPATCH_MB(e.MB, (k_rhs<MB><<<grid, 32, 0, h->stream>>>(h->dn, h->dp, e, ntiles))); h->launches++; break;
+        case 1: rc = launch_rhs(h); break;
         case 2: DISPATCH_MB(e.MB, (k_jac<MB><<<grid, 32, 0, h->stream>>>(h->dn, h->dp, e, ntiles))); h->launches++; break;
         case 3: rc = launch_factor(h, h->scal); break;
         case 4: rc = launch_trisolve(h); break;
@@ -800,7 +823,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     CU(h, cudaSetDevice(h->device));
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
-    const size_t smem = lu_smem_bytes(e.MB);
+    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr);
     CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
     CU(h, cudaEventRecord(h->ev0, h->stream));
     DISPATCH_MB(e.MB, {

@@ -34,15 +34,19 @@ struct PanelPlan {
     std::vector<int32_t> slot_of;     // exact-pattern slot -> storage slot  p_base + c*nr + r
     std::vector<int32_t> jslot;       // Jacobian entry (CSC order) -> storage slot
     std::vector<int32_t> diag_slot;   // per pivot row
-    // units = (panel, column chunk [x0,x1)); 8 ints each:
-    // {panel, x0, x1, first task, tasks, diagonal mode (0 later chunk, 1 in this chunk, 2 earlier chunk), 0, 0}
+    // units = (panel, column chunk [x0,x1)); UREC ints each:
+    // {panel, x0, x1, first task, tasks, diagonal mode (0 later chunk, 1 in this chunk, 2 earlier chunk),
+    //  slot of U'_QQ of the first in-chunk source (-1 none), its nq, nr, next, first row, base slot}
+    static constexpr int UREC = 12, TREC = 12;
     std::vector<int32_t> u_info;
-    // tasks = source blocks applied to a unit; 4 ints each:
-    // {source panel Q, position of Q's first column in the target pattern | in-chunk << 30, targets, first map entry}
+    // tasks = source blocks applied to a unit; TREC ints each:
+    // {source panel Q, position of Q's first column in the target pattern | in-chunk << 30, targets, first map entry,
+    //  nq, base slot of Q, slot of U'_QQ, slot of U'_QQ of the next in-chunk source (-1 none), its nq,
+    //  first slot and number of slots of the span of U' columns the targets touch, 0}
     std::vector<int32_t> t_info;
     std::vector<int32_t> map;         // per target: (column position in Q's pattern) | (column position in the chunk << 16)
-    int64_t n_units() const { return (int64_t)u_info.size() / 8; }
-    int64_t n_tasks() const { return (int64_t)t_info.size() / 4; }
+    int64_t n_units() const { return (int64_t)u_info.size() / UREC; }
+    int64_t n_tasks() const { return (int64_t)t_info.size() / TREC; }
 };
 
 // Everything the kernels need that depends only on the network (shared by all members).

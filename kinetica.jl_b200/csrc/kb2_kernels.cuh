@@ -58,8 +58,9 @@ struct DevNet {
 struct DevPlan {
     int npanels, nunits, padded;
     const int *p_row0, *p_nrows, *p_width, *p_next, *p_base, *p_cptr, *cols;
-    const int4 *u_info;       // 2 per unit: {panel, x0, x1, task0}, {ntask, dmode, 0, 0}
-    const int4 *t_info;       // {Q, lpos | inchunk << 30, ntargets, map0}
+    const int4 *u_info;       // 3 per unit: {panel, x0, x1, task0}, {ntask, dmode, first U'_QQ slot, its nq}, {nr, next, row0, base}
+    const int4 *t_info;       // 3 per task: {Q, lpos | inchunk << 30, ntargets, map0}, {nq, base of Q, U'_QQ slot, next U'_QQ slot},
+                              //             {next nq, first slot of the target span, slots of the span, 0}
     const int *map;           // (column position in Q) | (column position in the chunk << 16)
 };
 
@@ -68,6 +69,7 @@ struct DevPlan {
 // contiguous block per array and every access of the warp covers whole MB*8-byte segments.
 struct DevEns {
     int B, Bp, MB;
+    int u_smem;               // 1: a tile's state vector (S*MB doubles) fits the warp's shared memory and is staged there for the gathers
     double *u, *ua, *rv, *y, *K[6], *k, *rate, *lu, *invd;
     // conditions
     int nstops;               // row length of the per-member stop tables
@@ -174,6 +176,12 @@ __device__ inline double profile_eval(int kind, const double *p, double t)
 // ---------------------------------------------------------------------------------------------
 // Warp-tile primitives.
 // ---------------------------------------------------------------------------------------------
+#ifndef KB2_NC
+#define KB2_NC 3               // target columns per lane and pass in the LU update
+#endif
+#ifndef KB2_RHS_U
+#define KB2_RHS_U 4            // rows per lane in flight in the gather loops
+#endif
 constexpr int PR = 8;          // rows per panel (PanelPlan::PR)
 constexpr int CWMAX = 96;      // columns per chunk (PanelPlan::CW)
 constexpr unsigned FULL = 0xffffffffu;
@@ -217,6 +225,50 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
     if (bytes >= 16) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// L2 residency control.  The factors stream through L2 once per triangular sweep (evict_first),
+// while the finished U' blocks of the last few panels are re-read by the panels that follow
+// (evict_last): with the hints the 126 MB L2 keeps that window instead of the stream.
+__device__ __forceinline__ unsigned long long l2_policy_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_hint(double *a, double v, unsigned long long p)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(p) : "memory");
+}
+__device__ __forceinline__ void st2_hint(double2 *a, double2 v, unsigned long long p)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(a), "d"(v.x), "d"(v.y), "l"(p) : "memory");
+}
+__device__ __forceinline__ double ld_hint(const double *a, unsigned long long p)
+{
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 ld2_hint(const double2 *a, unsigned long long p)
+{
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cp_async16_hint(void *smem_dst, const void *gsrc, unsigned long long p)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "l"(p) : "memory");
+}
+__device__ __forceinline__ void cp_async8_hint(void *smem_dst, const void *gsrc, unsigned long long p)
+{
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "l"(p) : "memory");
+}
+
 // K1: k[r][m] for the member's current condition value T (masked by `upd`)
 template <int MB>
 __device__ void tile_rates(const WTile<MB> &tl, const DevNet &net, double T, bool upd, int ridx)
@@ -236,13 +288,18 @@ __device__ void tile_rates(const WTile<MB> &tl, const DevNet &net, double T, boo
 // K2: mass-action right-hand side in two gather passes (no atomics, fixed summation order):
 //   rate_j = k_j * prod u^nu                      (lanes over reactions, coalesced k / rate)
 //   du_i   = sum_e coef_e * rate_{j(e)}           (gather CSR of species i, ascending reactions)
-// out_i = du_i + sum_q cs[q]*Kq_i  (stage right-hand side fusion)
+// out_i = du_i + sum_{q<nk} cs_q*K_q,i  (stage right-hand side fusion)
 template <int MB>
 __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u, double *out, int nk,
-                         double *const *Kq, const double *cs)
+                         double cs0, double cs1, double cs2, double cs3, double cs4, double *su)
 {
     constexpr int LN = 32 / MB;
     const int m = tl.m;
+    if (su) {       // stage the state vector in shared memory: the reactant gathers never leave the SM
+        for (int i = tl.lane; i < net.S * MB; i += 32) su[i] = u[i];
+        __syncwarp();
+        u = su;
+    }
     {
         constexpr int UR = 4;
         for (int j0 = tl.ln; j0 < net.R; j0 += UR * LN) {
@@ -279,13 +336,17 @@ __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u
         double a = member_sum<MB>((a0 + a1) + (a2 + a3));
         if (tl.ln == 0) {
             const int o = i * MB + m;
-            for (int q = 0; q < nk; ++q) a += cs[q] * Kq[q][o];
+            if (nk > 0) a += cs0 * tl.K[0][o];
+            if (nk > 1) a += cs1 * tl.K[1][o];
+            if (nk > 2) a += cs2 * tl.K[2][o];
+            if (nk > 3) a += cs3 * tl.K[3][o];
+            if (nk > 4) a += cs4 * tl.K[4][o];
             out[o] = a;
         }
     }
     // the other rows one per lane, eight at a time (independent gather chains), in order of
     // decreasing length so that rows walked together are about equally long
-    constexpr int U = 8;
+    constexpr int U = KB2_RHS_U;
     for (int z0 = net.rhs_nlong + tl.ln; z0 < net.S; z0 += U * LN) {
         int e[U], n[U], sp[U];
         double acc[U];
@@ -320,7 +381,11 @@ __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u
             if (sp[v] >= 0) {
                 const int o = sp[v] * MB + m;
                 double a = acc[v];
-                for (int q = 0; q < nk; ++q) a += cs[q] * Kq[q][o];
+                if (nk > 0) a += cs0 * tl.K[0][o];
+                if (nk > 1) a += cs1 * tl.K[1][o];
+                if (nk > 2) a += cs2 * tl.K[2][o];
+                if (nk > 3) a += cs3 * tl.K[3][o];
+                if (nk > 4) a += cs4 * tl.K[4][o];
                 out[o] = a;
             }
         }
@@ -353,16 +418,22 @@ __device__ void tile_jac_csc(const WTile<MB> &tl, const DevNet &net, const doubl
 // 16-byte stores), -J entries scattered to their slots (four entries per lane in flight), then
 // the diagonal shift.
 template <int MB>
-__device__ void tile_assemble_w(const WTile<MB> &tl, const DevNet &net, const DevPlan &pl, const double *u, double hg_inv)
+__device__ void tile_assemble_w(const WTile<MB> &tl, const DevNet &net, const DevPlan &pl, const double *u, double hg_inv, double *su)
 {
     constexpr int LN = 32 / MB;
     const int m = tl.m;
+    if (su) {
+        for (int i = tl.lane; i < net.S * MB; i += 32) su[i] = u[i];
+        __syncwarp();
+        u = su;
+    }
     if (MB == 1) {
         for (int i = tl.lane; i < pl.padded; i += 32) tl.lu[i] = 0.0;
     } else {
         double2 *z = reinterpret_cast<double2 *>(tl.lu);       // padded*MB is even: every tile is 16-byte aligned
         const int n2 = pl.padded * MB / 2;
-        for (int i = tl.lane; i < n2; i += 32) z[i] = make_double2(0.0, 0.0);
+        const unsigned long long pol = l2_policy_first();
+        for (int i = tl.lane; i < n2; i += 32) st2_hint(z + i, make_double2(0.0, 0.0), pol);
     }
     __syncwarp();
     // entries with many terms (hub columns): the lanes of the member stride over the terms
@@ -384,7 +455,7 @@ __device__ void tile_assemble_w(const WTile<MB> &tl, const DevNet &net, const De
         if (tl.ln == 0) tl.lu[(size_t)net.jslot[p] * MB + m] = -a;
     }
     // the other entries one per lane, eight in flight, longest first
-    constexpr int U = 8;
+    constexpr int U = KB2_RHS_U;
     for (int z0 = net.j_nlong + tl.ln; z0 < net.nnzJ; z0 += U * LN) {
         int t[U], n[U], pe[U];
         double v[U];
@@ -428,13 +499,22 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 // shared memory of a factorising warp, in doubles: one staged chunk of a panel, the unit upper
 // diagonal block U'_QQ of the next in-chunk source (prefetched with cp.async) and the finished
 // L'_PQ block of a source that lies in an earlier chunk
-__host__ __device__ constexpr size_t lu_smem_doubles(int mb) { return (size_t)(CWMAX * PR + 2 * PR * PR) * mb; }
+__host__ __device__ constexpr size_t lu_smem_doubles(int mb) { return (size_t)(CWMAX * PR + 3 * PR * PR) * mb; }
 
 // K4: block Crout LU of the padded panel storage, in place:  W = L' U'  with the pivots on L'
 // and a unit diagonal on U'; invd[i] = 1/L'_ii is kept for the substitutions.
@@ -442,95 +522,109 @@ __host__ __device__ constexpr size_t lu_smem_doubles(int mb) { return (size_t)(C
 // Q in the L part:   L_PQ = X * inv(U_QQ)  (lane ln owns row ln),  then every lane updates its
 // share of the target columns, three columns per pass,
 //     w[:, j] -= L_PQ * U_Q[:, j]
-// with the 24 U' values of the pass in flight together and L_PQ broadcast from shared memory
-// (8 loads feed 24 FMAs).
+// with L_PQ broadcast from shared memory (8 loads feed 24 FMAs).
+// The source blocks of a unit form a software pipeline, because one warp has nobody else to hide
+// its latencies behind: while source k is applied, the task record and target map of source k+1
+// are already in registers, its U' values (first pass) are in flight into registers, and its
+// U'_QQ or L'_PQ block is in flight into shared memory with cp.async; the next unit's chunk and
+// target spans are pulled towards L2 with bulk prefetches.
 template <int MB>
 __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
 {
-    constexpr int LN = 32 / MB, NC = 3;
+    constexpr int LN = 32 / MB, NC = KB2_NC;
     const int m = tl.m, ln = tl.ln, lane = tl.lane;
     double *lu = tl.lu;
     double *Uq = Wp + CWMAX * PR * MB;       // [q][a][m]: U'_QQ of the next in-chunk source
-    double *Ls = Uq + PR * PR * MB;          // [q][r][m]: L'_PQ of a source from an earlier chunk
+    double *Ls = Uq + PR * PR * MB;          // [2][q][r][m]: L'_PQ of sources from an earlier chunk (double buffered)
+    const unsigned long long pol_first = l2_policy_first(), pol_last = l2_policy_last();
+    int4 na = pl.u_info[0], nb = pl.u_info[1], nc = pl.u_info[2];
     for (int un = 0; un < pl.nunits; ++un) {
-        const int4 ua = pl.u_info[2 * un], ub = pl.u_info[2 * un + 1];
-        const int P = ua.x, x0 = ua.y, x1 = ua.z, task0 = ua.w, ntask = ub.x, dmode = ub.y;
-        const int nr = pl.p_nrows[P], next = pl.p_next[P], p0 = pl.p_row0[P];
+        const int4 ua = na, ub = nb, uc = nc;
+        const int x0 = ua.y, x1 = ua.z, task0 = ua.w, ntask = ub.x, dmode = ub.y;
+        const int nr = uc.x, next = uc.y, p0 = uc.z;
         const int cw = x1 - x0;
-        double *gP = lu + (size_t)pl.p_base[P] * MB;
-        // pull what the NEXT unit will read towards L2 while this one is being eliminated: its
-        // own chunk and, per source block, the span of U' columns its targets touch
+        double *gP = lu + (size_t)uc.w * MB;
+        const int4 *trec = pl.t_info + (size_t)3 * task0;
+        // ---- the chunk goes to shared memory with one burst of cp.async (group C): every byte of
+        // it is in flight at once while the prologue below runs ----
+        {
+            const double *src = gP + (size_t)x0 * nr * MB;
+            const int n = cw * nr * MB;
+            if (MB == 1) {
+                for (int i = lane; i < n; i += 32) cp_async8(Wp + i, src + i);
+            } else {
+                for (int i = lane; i < n / 2; i += 32) cp_async16_hint(Wp + 2 * i, src + 2 * i, pol_first);
+            }
+            cp_async_commit();
+        }
+        // ---- prologue of the task pipeline: records of the first two sources, the first one's
+        // staged block and target map ----
+        int4 ca = make_int4(0, 0, 0, 0), cb = ca, cc = ca, xa = ca, xb = ca, xc = ca;
+        if (ntask > 0) { ca = trec[0]; cb = trec[1]; cc = trec[2]; }
+        if (ntask > 1) { xa = trec[3]; xb = trec[4]; xc = trec[5]; }
+        if (ntask > 0 && !(ca.y >> 30)) {        // group A(-1): L' block of a first source that lies in an earlier chunk
+            const double *src = gP + (size_t)(ca.y & 0x3fffffff) * nr * MB;
+            for (int i = lane; i < cb.x * nr * MB; i += 32) cp_async8(Ls + i, src + i);
+        }
+        cp_async_commit();
+        if (ub.z >= 0) {                         // group B(-1): U'_QQ of the first in-chunk source
+            const double *src = lu + (size_t)ub.z * MB;
+            for (int i = lane; i < ub.w * ub.w * MB; i += 32) cp_async8(Uq + i, src + i);
+        }
+        cp_async_commit();
+        // next unit: its record, and L2 prefetch of its chunk and of its sources' target spans
         if (un + 1 < pl.nunits) {
-            const int4 na = pl.u_info[2 * un + 2], nb = pl.u_info[2 * un + 3];
+            na = pl.u_info[3 * un + 3]; nb = pl.u_info[3 * un + 4]; nc = pl.u_info[3 * un + 5];
             if (lane == 31) {
-                const int nrn = pl.p_nrows[na.x];
-                const char *a = (const char *)(lu + ((size_t)pl.p_base[na.x] + (size_t)na.y * nrn) * MB);
-                const size_t nbytes = (size_t)(na.z - na.y) * nrn * MB * 8;
+                const char *a = (const char *)(lu + ((size_t)nc.w + (size_t)na.y * nc.x) * MB);
+                const size_t nbytes = (size_t)(na.z - na.y) * nc.x * MB * 8;
                 const size_t a16 = (size_t)a & ~(size_t)15;
                 prefetch_l2_bulk((const void *)a16, (unsigned)(((size_t)a + nbytes - a16) & ~(size_t)15));
             } else {
                 for (int tk = lane; tk < nb.x; tk += 31) {
-                    const int4 ti = pl.t_info[na.w + tk];
-                    if (ti.z > 0) {
-                        const int nq = pl.p_nrows[ti.x];
-                        const int c0 = pl.map[ti.w] & 0xffff, c1 = (pl.map[ti.w + ti.z - 1] & 0xffff) + 1;
-                        const char *a = (const char *)(lu + ((size_t)pl.p_base[ti.x] + (size_t)c0 * nq) * MB);
-                        const size_t nbytes = (size_t)(c1 - c0) * nq * MB * 8;
+                    const int4 t2 = pl.t_info[(size_t)3 * (na.w + tk) + 2];
+                    if (t2.z > 0) {
+                        const char *a = (const char *)(lu + (size_t)t2.y * MB);
+                        const size_t nbytes = (size_t)t2.z * MB * 8;
                         const size_t a16 = (size_t)a & ~(size_t)15;
                         prefetch_l2_bulk((const void *)a16, (unsigned)(((size_t)a + nbytes - a16) & ~(size_t)15));
                     }
                 }
             }
         }
-        // stage the first in-chunk source's U'_QQ while the chunk itself is being loaded
-        auto stage_uqq = [&](int tk) {
-            for (; tk < ntask; ++tk) {
-                const int4 ti = pl.t_info[task0 + tk];
-                if (ti.y >> 30) {
-                    const int Q = ti.x, nq = pl.p_nrows[Q];
-                    const double *src = lu + ((size_t)pl.p_base[Q] + (size_t)pl.p_next[Q] * nq) * MB;
-                    for (int i = lane; i < nq * nq * MB; i += 32) cp_async8(Uq + i, src + i);
-                    break;
-                }
-            }
-            cp_async_commit();
-        };
-        stage_uqq(0);
-        {
-            // chunk -> shared memory, eight 16-byte loads per lane in flight
-            const double *src = gP + (size_t)x0 * nr * MB;
-            const int n = cw * nr * MB;
-            if (MB == 1) {
-                for (int i0 = lane; i0 < n; i0 += 32 * 8) {
-                    double v[8];
+        int cmap[NC];
+        double cu[NC][PR];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = i0 + 32 * j < n ? src[i0 + 32 * j] : 0.0;
+        for (int c = 0; c < NC; ++c) cmap[c] = (ntask > 0 && ca.z > 0) ? pl.map[ca.w + min(ln + c * LN, ca.z - 1)] : 0;
+        // U' values of the first source's first pass
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) if (i0 + 32 * j < n) Wp[i0 + 32 * j] = v[j];
-                }
-            } else {
-                const double2 *s2 = reinterpret_cast<const double2 *>(src);
-                double2 *d2 = reinterpret_cast<double2 *>(Wp);
-                const int n2 = n / 2;
-                for (int i0 = lane; i0 < n2; i0 += 32 * 8) {
-                    double2 v[8];
+        for (int c = 0; c < NC; ++c) {
+            const double *up = lu + ((size_t)cb.y + (size_t)(cmap[c] & 0xffff) * cb.x) * MB + m;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = i0 + 32 * j < n2 ? s2[i0 + 32 * j] : make_double2(0.0, 0.0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) if (i0 + 32 * j < n2) d2[i0 + 32 * j] = v[j];
-                }
-            }
+            for (int q = 0; q < PR; ++q) cu[c][q] = (ntask > 0 && ca.z > 0 && q < cb.x) ? ld_hint(up + q * MB, pol_last) : 0.0;
         }
         __syncwarp();
         for (int tk = 0; tk < ntask; ++tk) {
-            const int4 ti = pl.t_info[task0 + tk];
-            const int Q = ti.x, lpos = ti.y & 0x3fffffff, inch = ti.y >> 30, ntg = ti.z, map0 = ti.w;
-            const int nq = pl.p_nrows[Q];
-            const double *gQ = lu + (size_t)pl.p_base[Q] * MB;
+            const int lpos = ca.y & 0x3fffffff, inch = ca.y >> 30, ntg = ca.z, map0 = ca.w;
+            const int nq = cb.x;
+            const double *gQ = lu + (size_t)cb.y * MB;
+            const bool has_next = tk + 1 < ntask;
+            // ---- look ahead: record of source k+2, target map of source k+1, staged L' of k+1 ----
+            int4 ya = make_int4(0, 0, 0, 0), yb = ya, yc = ya;
+            if (tk + 2 < ntask) { ya = trec[3 * (tk + 2)]; yb = trec[3 * (tk + 2) + 1]; yc = trec[3 * (tk + 2) + 2]; }
+            int xmap[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) xmap[c] = (has_next && xa.z > 0) ? pl.map[xa.w + min(ln + c * LN, xa.z - 1)] : 0;
+            if (has_next && !(xa.y >> 30)) {     // group A(k): L' block of source k+1
+                const double *src = gP + (size_t)(xa.y & 0x3fffffff) * nr * MB;
+                double *dst = Ls + ((tk + 1) & 1) * PR * PR * MB;
+                for (int i = lane; i < xb.x * nr * MB; i += 32) cp_async8(dst + i, src + i);
+            }
+            cp_async_commit();
+            cp_async_wait_but1();                // everything but A(k) has landed: L' or U'_QQ of source k
+            __syncwarp();
             const double *ls;                    // L'_PQ as [q][r][m] in shared memory
             if (inch) {
-                cp_async_wait_all();
-                __syncwarp();
                 if (ln < nr) {
                     double X[PR];
                     double *xp = Wp + ((lpos - x0) * nr + ln) * MB + m;
@@ -546,53 +640,81 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
                     for (int q = 1; q < PR; ++q) if (q < nq) xp[q * nr * MB] = X[q];
                 }
                 __syncwarp();
-                stage_uqq(tk + 1);               // flies while this source's targets are updated
+                if (cb.w >= 0) {                 // group B(k): U'_QQ of the next in-chunk source
+                    const double *src = lu + (size_t)cb.w * MB;
+                    for (int i = lane; i < cc.x * cc.x * MB; i += 32) cp_async8(Uq + i, src + i);
+                }
                 ls = Wp + (lpos - x0) * nr * MB + m;
             } else {
-                const double *src = gP + (size_t)lpos * nr * MB;
-                for (int i = lane; i < nq * nr * MB; i += 32) Ls[i] = src[i];
-                __syncwarp();
-                ls = Ls + m;
+                ls = Ls + (tk & 1) * PR * PR * MB + m;
             }
-            for (int t = ln; t < ntg; t += NC * LN) {
-                double uu[NC][PR], w[NC][PR];
+            cp_async_commit();
+            // ---- passes over the target columns.  The U' values of the first pass were loaded
+            // during the previous source; during the first pass those of the next source are put in
+            // flight.  Further passes of a wide source load on demand. ----
+            double xu[NC][PR];
+            bool first = true;
+            for (int t = ln; first || t < ntg; t += NC * LN) {
+                double w[NC][PR];
                 double *wp[NC];
                 bool ok[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     ok[c] = t + c * LN < ntg;
-                    const int e = pl.map[map0 + (ok[c] ? t + c * LN : t)];
-                    const double *up = gQ + (size_t)(e & 0xffff) * nq * MB + m;
+                    int e = cmap[c];
+                    if (!first) {
+                        e = pl.map[map0 + (ok[c] ? t + c * LN : t)];
+                        const double *up = gQ + (size_t)(e & 0xffff) * nq * MB + m;
+#pragma unroll
+                        for (int q = 0; q < PR; ++q) cu[c][q] = q < nq ? ld_hint(up + q * MB, pol_last) : 0.0;
+                    }
                     wp[c] = Wp + (e >> 16) * nr * MB + m;
 #pragma unroll
-                    for (int q = 0; q < PR; ++q) uu[c][q] = q < nq ? up[q * MB] : 0.0;
+                    for (int r = 0; r < PR; ++r) w[c][r] = (r < nr && ntg > 0) ? wp[c][r * MB] : 0.0;
                 }
+                if (first) {
+                    // U' values of source k+1 fly while source k is applied
 #pragma unroll
-                for (int c = 0; c < NC; ++c)
+                    for (int c = 0; c < NC; ++c) {
+                        const double *up = lu + ((size_t)xb.y + (size_t)(xmap[c] & 0xffff) * xb.x) * MB + m;
 #pragma unroll
-                    for (int r = 0; r < PR; ++r) w[c][r] = r < nr ? wp[c][r * MB] : 0.0;
-#pragma unroll
-                for (int q = 0; q < PR; ++q) {
-                    if (q < nq) {
-                        double l[PR];
-#pragma unroll
-                        for (int r = 0; r < PR; ++r) l[r] = r < nr ? ls[(q * nr + r) * MB] : 0.0;
-#pragma unroll
-                        for (int c = 0; c < NC; ++c)
-#pragma unroll
-                            for (int r = 0; r < PR; ++r) w[c][r] -= l[r] * uu[c][q];
+                        for (int q = 0; q < PR; ++q) xu[c][q] = (has_next && xa.z > 0 && q < xb.x) ? ld_hint(up + q * MB, pol_last) : 0.0;
                     }
                 }
+                if (ntg > 0) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c)
-                    if (ok[c]) {
+                    for (int q = 0; q < PR; ++q) {
+                        if (q < nq) {
+                            double l[PR];
 #pragma unroll
-                        for (int r = 0; r < PR; ++r) if (r < nr) wp[c][r * MB] = w[c][r];
+                            for (int r = 0; r < PR; ++r) l[r] = r < nr ? ls[(q * nr + r) * MB] : 0.0;
+#pragma unroll
+                            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                                for (int r = 0; r < PR; ++r) w[c][r] -= l[r] * cu[c][q];
+                        }
                     }
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+                        if (ok[c]) {
+#pragma unroll
+                            for (int r = 0; r < PR; ++r) if (r < nr) wp[c][r * MB] = w[c][r];
+                        }
+                }
+                first = false;
             }
             __syncwarp();
+            // rotate the pipeline
+            ca = xa; cb = xb; cc = xc; xa = ya; xb = yb; xc = yc;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                cmap[c] = xmap[c];
+#pragma unroll
+                for (int q = 0; q < PR; ++q) cu[c][q] = xu[c][q];
+            }
         }
         cp_async_wait_all();
+        __syncwarp();
         if (dmode) {
             const int dpos = next - x0;      // position of the diagonal block relative to the chunk (negative for dmode 2)
             if (dmode == 1) {
@@ -656,9 +778,13 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
             if (MB == 1) {
                 for (int i = lane; i < n; i += 32) dst[i] = Wp[i];
             } else {
+                // L' columns are only read again by the forward sweeps (stream them through L2);
+                // the diagonal block and U' columns are re-read by the next panels (keep them)
                 double2 *d2 = reinterpret_cast<double2 *>(dst);
                 const double2 *s2 = reinterpret_cast<const double2 *>(Wp);
-                for (int i = lane; i < n / 2; i += 32) d2[i] = s2[i];
+                const int nl = min(max(next - x0, 0), cw) * nr * MB / 2;
+                for (int i = lane; i < nl; i += 32) st2_hint(d2 + i, s2[i], pol_first);
+                for (int i = nl + lane; i < n / 2; i += 32) st2_hint(d2 + i, s2[i], pol_last);
             }
         }
         __syncwarp();
@@ -666,14 +792,17 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
 }
 
 // K5: W x = rhs over the block storage.  rhs, x in species order; y = permuted scratch.
-// Lane ln = cg*8 + r: row r of the panel, column group cg of LN/8; a warp-wide load of one
-// column position covers MB*8 consecutive doubles of the panel.  Eight column positions per lane
-// are in flight at a time and the panel two steps ahead is pulled towards L2 with one bulk
-// prefetch, so the sweep streams the factors instead of waiting on each panel.
-template <int MB>
-__device__ __forceinline__ double panel_dot(const double *gP, const double *y, const int *__restrict__ C,
+// Lane ln = cg*8 + r: row r of the panel, column group cg of LN/8; one column position of a
+// panel is MB*8 consecutive doubles.  A sweep is a chain over the panels, so what counts is the
+// latency of one link: the columns a panel needs (values and column indices) are copied into
+// shared memory with one burst of cp.async — every byte of the panel in flight at once — after
+// the panel two links ahead has been pulled into L2 with a bulk prefetch; a panel too wide for
+// the buffer (hub rows) is read straight from global memory, eight positions per lane in flight.
+template <int MB, bool SMEM>
+__device__ __forceinline__ double panel_dot(const double *vals, const int *idx, const double *y,
                                             int cbeg, int cend, int nr, int r, int cg, int m)
 {
+    // vals[(c*nr + r)*MB], idx[c]: shared-memory copies (SMEM) or the global arrays
     constexpr int CG = 32 / MB / PR;
     double a[4] = {0.0, 0.0, 0.0, 0.0};
     int c = cbeg + cg;
@@ -681,15 +810,15 @@ __device__ __forceinline__ double panel_dot(const double *gP, const double *y, c
         int ix[8];
         double lv[8], yv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ix[j] = C[c + j * CG];
+        for (int j = 0; j < 8; ++j) ix[j] = idx[c + j * CG];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) lv[j] = gP[((c + j * CG) * nr + r) * MB];
+        for (int j = 0; j < 8; ++j) lv[j] = vals[((c + j * CG) * nr + r) * MB];
 #pragma unroll
         for (int j = 0; j < 8; ++j) yv[j] = y[ix[j] * MB + m];
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j & 3] += lv[j] * yv[j];
     }
-    for (; c < cend; c += CG) a[0] += gP[(c * nr + r) * MB] * y[C[c] * MB + m];
+    for (; c < cend; c += CG) a[0] += vals[(c * nr + r) * MB] * y[idx[c] * MB + m];
     return (a[0] + a[1]) + (a[2] + a[3]);
 }
 
@@ -703,12 +832,30 @@ __device__ __forceinline__ void prefetch_panel_cols(const DevPlan &pl, const dou
     prefetch_l2_bulk((const void *)a16, (unsigned)((a + nbytes - a16) & ~(size_t)15));
 }
 
+// columns [c0, c1) of panel P -> shared memory (values as in global memory, then the column indices)
 template <int MB>
-__device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevPlan &pl, const double *rhs, double *x)
+__device__ __forceinline__ void stage_panel_cols(double *buf, int *cbuf, const double *gsrc, const int *csrc, int ncol, int nr, int lane)
+{
+    const int n = ncol * nr * MB;
+    if (MB == 1) {
+        for (int i = lane; i < n; i += 32) cp_async8(buf + i, gsrc + i);
+    } else {
+        const unsigned long long pol = l2_policy_first();
+        for (int i = lane; i < n / 2; i += 32) cp_async16_hint(buf + 2 * i, gsrc + 2 * i, pol);
+    }
+    for (int i = lane; i < ncol; i += 32) cp_async4(cbuf + i, csrc + i);
+    cp_async_commit();
+}
+
+template <int MB>
+__device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevPlan &pl, const double *rhs, double *x, double *sm)
 {
     constexpr int LN = 32 / MB, CG = LN / PR;
     static_assert(CG >= 1, "at most 4 members per warp tile");
     constexpr int AHEAD = 2;
+    constexpr int CAPC = 2 * PR * PR * MB;                          // column indices (ints) at the tail of the buffer
+    constexpr int CAPD = (CWMAX * PR + 2 * PR * PR) * MB;            // values (doubles)
+    int *cbuf = reinterpret_cast<int *>(sm + CAPD);
     const int m = tl.m, r = tl.ln % PR, cg = tl.ln / PR;
     const double *lu = tl.lu;
     double *y = tl.y;
@@ -716,19 +863,31 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
     if (tl.lane < AHEAD && tl.lane < pl.npanels) prefetch_panel_cols<MB>(pl, lu, tl.lane, 0, pl.p_next[tl.lane] + pl.p_nrows[tl.lane]);
     for (int P = 0; P < pl.npanels; ++P) {
         const int nr = pl.p_nrows[P], next = pl.p_next[P], p0 = pl.p_row0[P];
-        const int *__restrict__ C = pl.cols + pl.p_cptr[P];
-        const double *gP = lu + (size_t)pl.p_base[P] * MB + m;
+        const int *C = pl.cols + pl.p_cptr[P];
+        const double *gP = lu + (size_t)pl.p_base[P] * MB;
         const bool rok = r < nr;
+        const int ncol = next + nr;                                  // L part and diagonal block
+        const bool staged = ncol * nr * MB <= CAPD && ncol <= CAPC;
+        if (staged) stage_panel_cols<MB>(sm, cbuf, gP, C, ncol, nr, tl.lane);
         if (tl.lane == 0 && P + AHEAD < pl.npanels)
             prefetch_panel_cols<MB>(pl, lu, P + AHEAD, 0, pl.p_next[P + AHEAD] + pl.p_nrows[P + AHEAD]);
-        double acc = rok ? panel_dot<MB>(gP, y, C, 0, next, nr, r, cg, m) : 0.0;
+        const double bz = rok ? rhs[net.perm[p0 + r] * MB + m] : 0.0;
+        const double dinv = rok ? tl.invd[(p0 + r) * MB + m] : 0.0;
+        const double *vals = staged ? (const double *)sm + m : gP + m;
+        double acc;
+        if (staged) {
+            cp_async_wait_all();
+            __syncwarp();
+            acc = rok ? panel_dot<MB, true>(vals, cbuf, y, 0, next, nr, r, cg, m) : 0.0;
+        } else {
+            acc = rok ? panel_dot<MB, false>(vals, C, y, 0, next, nr, r, cg, m) : 0.0;
+        }
 #pragma unroll
         for (int off = 16; off >= PR * MB; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
-        double z = rok ? rhs[net.perm[p0 + r] * MB + m] - acc : 0.0;
-        const double dinv = rok ? tl.invd[(p0 + r) * MB + m] : 0.0;
+        double z = bz - acc;
         double lint[PR - 1];
 #pragma unroll
-        for (int a = 0; a < PR - 1; ++a) lint[a] = (rok && a < r) ? gP[((next + a) * nr + r) * MB] : 0.0;
+        for (int a = 0; a < PR - 1; ++a) lint[a] = (rok && a < r) ? vals[((next + a) * nr + r) * MB] : 0.0;
 #pragma unroll
         for (int a = 0; a < PR - 1; ++a) {
             const double yv = __shfl_sync(FULL, z * dinv, (cg * PR + a) * MB + m);   // y_a is final here
@@ -744,17 +903,29 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
     }
     for (int P = pl.npanels - 1; P >= 0; --P) {
         const int W = pl.p_width[P], nr = pl.p_nrows[P], next = pl.p_next[P], p0 = pl.p_row0[P];
-        const int *__restrict__ C = pl.cols + pl.p_cptr[P];
-        const double *gP = lu + (size_t)pl.p_base[P] * MB + m;
+        const int *C = pl.cols + pl.p_cptr[P] + next;                // from the diagonal block on
+        const double *gP = lu + ((size_t)pl.p_base[P] + (size_t)next * nr) * MB;
         const bool rok = r < nr;
+        const int ncol = W - next;                                   // diagonal block and U part
+        const bool staged = ncol * nr * MB <= CAPD && ncol <= CAPC;
+        if (staged) stage_panel_cols<MB>(sm, cbuf, gP, C, ncol, nr, tl.lane);
         if (tl.lane == 0 && P - AHEAD >= 0) prefetch_panel_cols<MB>(pl, lu, P - AHEAD, pl.p_next[P - AHEAD], pl.p_width[P - AHEAD]);
-        double acc = rok ? panel_dot<MB>(gP, y, C, next + nr, W, nr, r, cg, m) : 0.0;
+        const double yz = rok ? y[(p0 + r) * MB + m] : 0.0;
+        const double *vals = staged ? (const double *)sm + m : gP + m;
+        double acc;
+        if (staged) {
+            cp_async_wait_all();
+            __syncwarp();
+            acc = rok ? panel_dot<MB, true>(vals, cbuf, y, nr, ncol, nr, r, cg, m) : 0.0;
+        } else {
+            acc = rok ? panel_dot<MB, false>(vals, C, y, nr, ncol, nr, r, cg, m) : 0.0;
+        }
 #pragma unroll
         for (int off = 16; off >= PR * MB; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
-        double z = rok ? y[(p0 + r) * MB + m] - acc : 0.0;
+        double z = yz - acc;
         double uint_[PR];
 #pragma unroll
-        for (int a = 1; a < PR; ++a) uint_[a] = (rok && a > r && a < nr) ? gP[((next + a) * nr + r) * MB] : 0.0;
+        for (int a = 1; a < PR; ++a) uint_[a] = (rok && a > r && a < nr) ? vals[(a * nr + r) * MB] : 0.0;
 #pragma unroll
         for (int a = PR - 1; a > 0; --a) {
             const double xv = __shfl_sync(FULL, z, (cg * PR + a) * MB + m);        // U' has a unit diagonal

@@ -131,24 +131,38 @@ std::string build_panels(Symbolic &sym, int64_t S)
                 const int32_t *CQ = pp.cols.data() + pp.p_cptr[Q];
                 const bool inchunk = e >= x0;
                 const int32_t map0 = (int32_t)pp.map.size();
-                int ntg = 0;
+                int ntg = 0, cq_min = 0, cq_max = 0;
                 for (int cq = nextQ + nq; cq < WQ; ++cq) {
                     const int ppos = pos_in_P[CQ[cq]];
-                    if (ppos >= x0 && ppos < x1) { pp.map.push_back(cq | ((ppos - x0) << 16)); ++ntg; }
+                    if (ppos >= x0 && ppos < x1) {
+                        pp.map.push_back(cq | ((ppos - x0) << 16));
+                        if (ntg == 0) cq_min = cq;
+                        cq_max = cq;
+                        ++ntg;
+                    }
                 }
                 if (inchunk || ntg > 0) {
-                    pp.t_info.push_back(Q);
-                    pp.t_info.push_back(e | (inchunk ? (1 << 30) : 0));
-                    pp.t_info.push_back(ntg);
-                    pp.t_info.push_back(map0);
+                    // {Q, lpos | inchunk << 30, targets, first map entry, nq, base of Q, slot of U'_QQ,
+                    //  [next in-chunk source: slot of its U'_QQ, its nq], [span of U' columns the targets touch: first slot, slots], 0}
+                    const int32_t rec[PanelPlan::TREC] = {Q, e | (inchunk ? (1 << 30) : 0), ntg, map0, nq, pp.p_base[Q],
+                                                          pp.p_base[Q] + nextQ * nq, -1, 0,
+                                                          pp.p_base[Q] + cq_min * nq, ntg ? (cq_max + 1 - cq_min) * nq : 0, 0};
+                    pp.t_info.insert(pp.t_info.end(), rec, rec + PanelPlan::TREC);
                     pp.n_fma_padded += (int64_t)ntg * nr * nq + (inchunk ? (int64_t)nr * nq * (nq - 1) / 2 : 0);
                 }
                 e += nq;
             }
             if (dmode) pp.n_fma_padded += (int64_t)nr * (nr - 1) / 2 * std::max(0, x1 - std::max(x0, next));
             const int32_t ntask = (int32_t)pp.n_tasks() - task0;
-            const int32_t ui[8] = {P, x0, x1, task0, ntask, dmode, 0, 0};
-            pp.u_info.insert(pp.u_info.end(), ui, ui + 8);
+            // link every task (and the unit) to the next in-chunk source, whose U'_QQ is staged ahead
+            int32_t nx_off = -1, nx_nq = 0;
+            for (int32_t tk = ntask - 1; tk >= 0; --tk) {
+                int32_t *rec = pp.t_info.data() + (size_t)(task0 + tk) * PanelPlan::TREC;
+                rec[7] = nx_off; rec[8] = nx_nq;
+                if (rec[1] >> 30) { nx_off = rec[6]; nx_nq = rec[4]; }
+            }
+            const int32_t ui[PanelPlan::UREC] = {P, x0, x1, task0, ntask, dmode, nx_off, nx_nq, nr, next, pp.p_row0[P], pp.p_base[P]};
+            pp.u_info.insert(pp.u_info.end(), ui, ui + PanelPlan::UREC);
         }
         for (int c = 0; c < W; ++c) pos_in_P[C[c]] = -1;
     }

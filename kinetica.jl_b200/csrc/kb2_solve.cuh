@@ -6,6 +6,15 @@
 namespace kb2 {
 
 __host__ __device__ constexpr size_t lu_smem_bytes(int mb) { return lu_smem_doubles(mb) * sizeof(double); }
+// Shared memory of a warp: what the factorisation needs, or the tile's state vector if that is
+// larger and still leaves seven warps per SM (232448 bytes / 7, minus 1 KB the system reserves)
+inline size_t warp_smem_bytes(int mb, int64_t S, bool *u_fits)
+{
+    const size_t base = lu_smem_bytes(mb), ub = (size_t)S * mb * sizeof(double), cap = 232448 / 7 - 1024;
+    const size_t smem = (ub > base && ub <= cap) ? ub : base;
+    if (u_fits) *u_fits = ub <= smem;
+    return smem;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Layout conversion between the caller's row-major [row][B] arrays and the tile-major device
@@ -60,9 +69,10 @@ __global__ void __launch_bounds__(32) k_rates(DevNet net, DevPlan pl, DevEns en,
 template <int MB>
 __global__ void __launch_bounds__(32) k_rhs(DevNet net, DevPlan pl, DevEns en, int ntiles)
 {
+    extern __shared__ double smem[];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en);
-        tile_rhs(tl, net, tl.u, tl.rv, 0, nullptr, nullptr);
+        tile_rhs(tl, net, tl.u, tl.rv, 0, 0.0, 0.0, 0.0, 0.0, 0.0, en.u_smem ? smem : nullptr);
     }
 }
 
@@ -82,7 +92,7 @@ __global__ void __launch_bounds__(32) k_factor(DevNet net, DevPlan pl, DevEns en
     extern __shared__ double smem[];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en);
-        if (mode & 1) tile_assemble_w(tl, net, pl, tl.u, hg_inv[tl.b]);
+        if (mode & 1) tile_assemble_w(tl, net, pl, tl.u, hg_inv[tl.b], en.u_smem ? smem : nullptr);
         if (mode & 2) tile_lu(tl, pl, smem);
     }
 }
@@ -90,9 +100,10 @@ __global__ void __launch_bounds__(32) k_factor(DevNet net, DevPlan pl, DevEns en
 template <int MB>
 __global__ void __launch_bounds__(32) k_trisolve(DevNet net, DevPlan pl, DevEns en, int ntiles)
 {
+    extern __shared__ double smem[];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en);
-        tile_trisolve(tl, net, pl, tl.rv, tl.ua);
+        tile_trisolve(tl, net, pl, tl.rv, tl.ua, smem);
     }
 }
 
@@ -158,11 +169,11 @@ __device__ void tile_process_stop(const WTile<MB> &tl, const DevNet &net, const 
 // again after a discrete rate update, where the RHS jumps, for members that have no step-size
 // memory yet: they get h = min(h, 0.1 * estimate).  Uses rv, ua, y as scratch.
 template <int MB>
-__device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, bool initial)
+__device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, bool initial, double *su)
 {
     constexpr int LN = 32 / MB;
     const int m = tl.m;
-    tile_rhs(tl, net, tl.u, tl.rv, 0, nullptr, nullptr);
+    tile_rhs(tl, net, tl.u, tl.rv, 0, 0.0, 0.0, 0.0, 0.0, 0.0, su);
     double d0 = 0, d1 = 0;
     for (int i = tl.ln; i < net.S; i += LN) {
         const double ui = tl.u[i * MB + m], fi = tl.rv[i * MB + m];
@@ -174,7 +185,7 @@ __device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns 
     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
     for (int i = tl.ln; i < net.S; i += LN) tl.ua[i * MB + m] = tl.u[i * MB + m] + h0 * tl.rv[i * MB + m];
     __syncwarp();
-    tile_rhs(tl, net, tl.ua, tl.y, 0, nullptr, nullptr);
+    tile_rhs(tl, net, tl.ua, tl.y, 0, 0.0, 0.0, 0.0, 0.0, 0.0, su);
     double d2 = 0;
     for (int i = tl.ln; i < net.S; i += LN) {
         const double sc = en.abstol + en.reltol * fabs(tl.u[i * MB + m]);
@@ -196,11 +207,11 @@ __device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns 
 // previous update (c.hfirst) is the prediction for this one.  Members without that memory fall
 // back to the starting-step estimate.
 template <int MB>
-__device__ void tile_restart_h(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c)
+__device__ void tile_restart_h(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, double *su)
 {
     const bool upd = c.upd && c.status == ST_RUNNING;
     if (upd) { c.fresh = 1; c.firstacc = 1; }
-    if (__any_sync(FULL, upd && !(c.hfirst > 0.0))) tile_hinit(tl, net, en, c, false);
+    if (__any_sync(FULL, upd && !(c.hfirst > 0.0))) tile_hinit(tl, net, en, c, false, su);
     if (upd && c.hfirst > 0.0) c.h = fmin(c.h, c.hfirst);
 }
 
@@ -210,6 +221,7 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
     constexpr int LN = 32 / MB;
     WTile<MB> tl(tile, net, pl, en);
     const int m = tl.m, b = tl.b, ln = tl.ln;
+    double *su = en.u_smem ? Wp : nullptr;      // the gathers of RHS / Jacobian read the state from shared memory
     Ctl c;
     c.t = en.t0; c.si = 0; c.isave = 0; c.iters = 0;
     c.ns = en.stop_cnt[b];
@@ -222,7 +234,7 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
     c.T = (net.calc_mode == 0) ? profile_eval(en.pkind[b], en.pparams + (size_t)b * 16, -1.0) : 0.0;
     tile_rates(tl, net, c.T, true, -1);     // k(initial conditions), methods.jl:668
     tile_process_stop(tl, net, en, c, true);
-    tile_hinit(tl, net, en, c, true);
+    tile_hinit(tl, net, en, c, true, su);
     const size_t sb = (size_t)b * en.nstops;
     // ---- main loop ----
     for (;;) {
@@ -243,24 +255,37 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
         }
         if (!__any_sync(FULL, c.active)) break;
         const double hs = c.hs;
-        tile_assemble_w(tl, net, pl, tl.u, 1.0 / (hs * kGamma));
-        tile_lu(tl, pl, Wp);
+        tile_assemble_w(tl, net, pl, tl.u, 1.0 / (hs * kGamma), su);
+        {
+            // the factorisation needs every register it can get: give it a tile view of its own,
+            // recomputed behind an optimisation barrier, so that the pointers of the other phases
+            // are not kept alive across it
+            int tile_lu_ = tile;
+            asm volatile("" : "+r"(tile_lu_));
+            const WTile<MB> tlu(tile_lu_, net, pl, en);
+            tile_lu(tlu, pl, Wp);
+        }
         for (int s = 0; s < 6; ++s) {
             const double *Us = tl.u;
             if (s > 0) {
+                // ua = u + sum_{q<s} a_sq K_q  (stage 6 shares stage 5's coefficients plus K5)
+                const double a0 = cA[s][0], a1 = cA[s][1], a2 = cA[s][2], a3 = cA[s][3], a4 = cA[s][4];
                 for (int i = ln; i < net.S; i += LN) {
                     const int o = i * MB + m;
-                    double a = tl.u[o];
-                    for (int q = 0; q < s; ++q) a += cA[s][q] * tl.K[q][o];
+                    double a = tl.u[o] + a0 * tl.K[0][o];
+                    if (s > 1) a += a1 * tl.K[1][o];
+                    if (s > 2) a += a2 * tl.K[2][o];
+                    if (s > 3) a += a3 * tl.K[3][o];
+                    if (s > 4) a += a4 * tl.K[4][o];
                     tl.ua[o] = a;
                 }
                 __syncwarp();
                 Us = tl.ua;
             }
-            double cs[5];
-            for (int q = 0; q < s; ++q) cs[q] = cC[s][q] / hs;
-            tile_rhs(tl, net, Us, tl.rv, s, tl.K, cs);
-            tile_trisolve(tl, net, pl, tl.rv, tl.K[s]);
+            const double ih = 1.0 / hs;
+            tile_rhs(tl, net, Us, tl.rv, s, cC[s][0] * ih, cC[s][1] * ih, cC[s][2] * ih, cC[s][3] * ih, cC[s][4] * ih, su);
+            double *Ks = s == 0 ? tl.K[0] : s == 1 ? tl.K[1] : s == 2 ? tl.K[2] : s == 3 ? tl.K[3] : s == 4 ? tl.K[4] : tl.K[5];
+            tile_trisolve(tl, net, pl, tl.rv, Ks, Wp);
         }
         // error estimate = K6; new solution = ua + K6
         double e2 = 0.0;
@@ -308,7 +333,7 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
             }
         __syncwarp();
         tile_process_stop(tl, net, en, c, false);
-        if (__any_sync(FULL, c.upd)) tile_restart_h(tl, net, en, c);
+        if (__any_sync(FULL, c.upd)) tile_restart_h(tl, net, en, c, su);
     }
     if (ln == 0 && b < en.B) {
         en.status[b] = c.status == ST_RUNNING ? 5 : c.status;

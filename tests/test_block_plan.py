@@ -15,14 +15,25 @@ def run_plan(plan, lu):
     tile_lu in kinetica.jl_b200/csrc/kb2_kernels.cuh step for step."""
     P_ = plan
     invd = {}
-    for (P, x0, x1, task0, ntask, dmode, _, _) in P_["u_info"]:
+    for (P, x0, x1, task0, ntask, dmode, fi_off, fi_nq, nr_, nxt_, p0_, base_) in P_["u_info"]:
         nr, nxt, base, p0 = P_["p_nrows"][P], P_["p_next"][P], P_["p_base"][P], P_["p_row0"][P]
+        assert (nr_, nxt_, p0_, base_) == (nr, nxt, p0, base)
         cw = x1 - x0
+        inch_seen = []
         Wp = lu[base + x0 * nr: base + x1 * nr].reshape(cw, nr).copy()          # [c][r]
         for tk in range(task0, task0 + ntask):
-            Q, lp, ntg, map0 = P_["t_info"][tk]
+            Q, lp, ntg, map0, nq_, bq_, uqq_, nx_off, nx_nq, pf_off, pf_len, _ = P_["t_info"][tk]
             lpos, inch = lp & 0x3fffffff, lp >> 30
             nq, nxq, bq = P_["p_nrows"][Q], P_["p_next"][Q], P_["p_base"][Q]
+            assert (nq_, bq_, uqq_) == (nq, bq, bq + nxq * nq)
+            # staging links: the next in-chunk source after this task
+            later = [P_["t_info"][z] for z in range(tk + 1, task0 + ntask) if P_["t_info"][z][1] >> 30]
+            assert (nx_off, nx_nq) == ((later[0][6], later[0][4]) if later else (-1, 0))
+            if inch:
+                inch_seen.append((uqq_, nq))
+            if ntg:
+                pqs = [P_["map"][map0 + t] & 0xffff for t in range(ntg)]
+                assert pf_off == bq + min(pqs) * nq and pf_len == (max(pqs) + 1 - min(pqs)) * nq
             if inch:
                 X = Wp[lpos - x0: lpos - x0 + nq].T.copy()                        # [r][q]
                 Uqq = lu[bq + nxq * nq: bq + (nxq + nq) * nq].reshape(nq, nq).T     # [a][q]
@@ -39,6 +50,7 @@ def run_plan(plan, lu):
                 assert 0 <= pp < cw
                 u = lu[bq + pq * nq: bq + (pq + 1) * nq]
                 Wp[pp] -= L @ u
+        assert (fi_off, fi_nq) == (inch_seen[0] if inch_seen else (-1, 0))
         if dmode:
             dpos = nxt - x0
             if dmode == 1:
