@@ -411,6 +411,10 @@ extern "C" int32_t kb2_set_member_stops(kb2_handle h, int64_t B, int64_t nstops_
 static int pick_mb(kb2_ctx *h, int64_t B)
 {
     if (h->mb_user) return h->mb_user;
+    if (const char *ev = getenv("KB2_MB")) {       // testing / tuning knob, same meaning as kb2_set_tiling
+        const int v = atoi(ev);
+        if (v == 1 || v == 2 || v == 4) return v;
+    }
     // four members per warp tile (32-byte sectors fully used) unless the ensemble is too small to
     // give every SM a few warps
     int mb = 4;
@@ -455,6 +459,9 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
         bool fits = false;
         warp_smem_bytes(e.MB, h->net.S, &fits);
         e.u_smem = fits ? 1 : 0;
+#ifdef KB2_NO_USMEM
+        e.u_smem = 0;
+#endif
     }
     h->ens_B = B; h->ens_Ns = Ns; h->ens_mb = e.MB;
     h->ens_fixed = P.size();
@@ -578,11 +585,11 @@ static int launch_rhs(kb2_ctx *h)
 {
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
-    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr);
+    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr) + 16;
     DISPATCH_MB(e.MB, {
         int r = set_smem(h, k_rhs<MB>, smem);
         if (r) return r;
-        k_rhs<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles);
+        k_rhs<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles, (int)smem - 16);
     });
     h->launches++;
     CU(h, cudaGetLastError());
@@ -627,11 +634,11 @@ static int launch_factor(kb2_ctx *h, const double *d_hg, int mode = 3)
 {
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
-    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr);
+    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr) + 16;
     DISPATCH_MB(e.MB, {
         int r = set_smem(h, k_factor<MB>, smem);
         if (r) return r;
-        k_factor<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, d_hg, ntiles, mode);
+        k_factor<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, d_hg, ntiles, mode, (int)smem - 16);
     });
     h->launches++;
     CU(h, cudaGetLastError());
@@ -642,11 +649,11 @@ static int launch_trisolve(kb2_ctx *h)
 {
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
-    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr);
+    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr) + 16;
     DISPATCH_MB(e.MB, {
         int r = set_smem(h, k_trisolve<MB>, smem);
         if (r) return r;
-        k_trisolve<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles);
+        k_trisolve<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles, (int)smem - 16);
     });
     h->launches++;
     CU(h, cudaGetLastError());
@@ -823,7 +830,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     CU(h, cudaSetDevice(h->device));
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
-    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr);
+    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr) + 16;
     CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
     CU(h, cudaEventRecord(h->ev0, h->stream));
     DISPATCH_MB(e.MB, {
@@ -835,7 +842,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
         h->last_ctas_per_sm = per_sm;
         // persistent warps: every resident slot pulls tiles from an atomic counter
         const int grid = std::min(ntiles, per_sm * h->sm_count);
-        k_solve<MB><<<grid, 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles, h->d_counter);
+        k_solve<MB><<<grid, 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles, h->d_counter, (int)smem - 16);
     });
     h->launches++;
     CU(h, cudaEventRecord(h->ev1, h->stream));

@@ -176,23 +176,96 @@ __device__ inline double profile_eval(int kind, const double *p, double t)
 // ---------------------------------------------------------------------------------------------
 // Warp-tile primitives.
 // ---------------------------------------------------------------------------------------------
+#ifndef KB2_TRISTAGE
+#define KB2_TRISTAGE 0        // 1: stage the panels of the sweeps in shared memory (faster stand-alone, slower inside the fused solve)
+#endif
+#ifndef KB2_LU_PREFETCH
+#define KB2_LU_PREFETCH 1     // U' values of the next source block are loaded while the current one is applied
+#endif
+#ifndef KB2_CHUNK_BULK
+#define KB2_CHUNK_BULK 1      // panel chunks go to shared memory with one bulk copy
+#endif
 #ifndef KB2_NC
 #define KB2_NC 3               // target columns per lane and pass in the LU update
 #endif
 #ifndef KB2_RHS_U
-#define KB2_RHS_U 4            // rows per lane in flight in the gather loops
+#define KB2_RHS_U 8            // rows per lane in flight in the gather loops
 #endif
 constexpr int PR = 8;          // rows per panel (PanelPlan::PR)
 constexpr int CWMAX = 96;      // columns per chunk (PanelPlan::CW)
 constexpr unsigned FULL = 0xffffffffu;
+
+// ---- bulk asynchronous copies (TMA, 1-D): the large contiguous transfers of a warp — a panel
+// chunk, the columns of a panel for a sweep, the state vector — are handed to the copy engine
+// with ONE instruction and complete on a shared-memory mbarrier.  They never sit in the
+// load/store unit, so the short latency-critical loads of the other warps on the SM (which are
+// in other phases of their own solves) do not queue behind them.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+// Per-warp copy channel: one mbarrier and its phase parity, both in the warp's shared memory.
+struct BulkChan {
+    unsigned bar;      // shared-memory address of the mbarrier (0: bulk copies disabled, e.g. MB = 1 alignment)
+    int *par;          // phase parity of the next completion
+};
+// all lanes call; the copy is issued by lane 0 after the warp has finished with the destination.
+// `fence`: the source was written with ordinary stores by this warp since the last fence.
+__device__ __forceinline__ void bulk_issue(const BulkChan &ch, void *dst, const void *src, unsigned bytes, int lane, bool fence)
+{
+    if (fence) fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) bulk_g2s(smem_u32(dst), src, bytes, ch.bar);
+}
+__device__ __forceinline__ void bulk_wait(const BulkChan &ch, int lane)
+{
+    const int p = *ch.par;
+    mbar_wait(ch.bar, (unsigned)p);
+    __syncwarp();
+    if (lane == 0) *ch.par = p ^ 1;
+    __syncwarp();
+}
+
+// one channel per warp (= per CTA), set up once at kernel start; the mbarrier lives behind the
+// data_bytes of dynamic shared memory the kernel was launched with
+template <int MB>
+__device__ __forceinline__ BulkChan chan_setup(double *smem, int data_bytes)
+{
+    BulkChan ch;
+    char *tail = reinterpret_cast<char *>(smem) + data_bytes;
+    ch.bar = MB >= 2 ? smem_u32(tail) : 0u;        // MB = 1: tiles are only 8-byte aligned, bulk copies need 16
+    ch.par = reinterpret_cast<int *>(tail + 8);
+    if ((threadIdx.x & 31) == 0) {
+        if (ch.bar) mbar_init(ch.bar);
+        *ch.par = 0;
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncwarp();
+    return ch;
+}
 
 template <int MB>
 struct WTile {
     static constexpr int LN = 32 / MB;
     int lane, m, ln, b;
     double *u, *ua, *rv, *y, *K[6], *k, *rate, *lu, *invd, *out_u, *out_umax;
-    __device__ WTile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en)
+    BulkChan ch;
+    __device__ WTile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en, const BulkChan &chan)
     {
+        ch = chan;
         lane = threadIdx.x & 31;
         m = lane % MB;
         ln = lane / MB;
@@ -242,21 +315,33 @@ __device__ __forceinline__ unsigned long long l2_policy_first()
 }
 __device__ __forceinline__ void st_hint(double *a, double v, unsigned long long p)
 {
+#ifndef KB2_L2_HINTS
+    (void)p; *a = v; return;
+#endif
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(p) : "memory");
 }
 __device__ __forceinline__ void st2_hint(double2 *a, double2 v, unsigned long long p)
 {
+#ifndef KB2_L2_HINTS
+    (void)p; *a = v; return;
+#endif
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(a), "d"(v.x), "d"(v.y), "l"(p) : "memory");
 }
 __device__ __forceinline__ double ld_hint(const double *a, unsigned long long p)
 {
     double v;
+#ifndef KB2_L2_HINTS
+    (void)p; return *a;
+#endif
     asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ double2 ld2_hint(const double2 *a, unsigned long long p)
 {
     double2 v;
+#ifndef KB2_L2_HINTS
+    (void)p; return *a;
+#endif
     asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(p) : "memory");
     return v;
 }
@@ -296,8 +381,13 @@ __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u
     constexpr int LN = 32 / MB;
     const int m = tl.m;
     if (su) {       // stage the state vector in shared memory: the reactant gathers never leave the SM
-        for (int i = tl.lane; i < net.S * MB; i += 32) su[i] = u[i];
-        __syncwarp();
+        if (tl.ch.bar) {
+            bulk_issue(tl.ch, su, u, (unsigned)(net.S * MB * 8), tl.lane, true);
+            bulk_wait(tl.ch, tl.lane);
+        } else {
+            for (int i = tl.lane; i < net.S * MB; i += 32) su[i] = u[i];
+            __syncwarp();
+        }
         u = su;
     }
     {
@@ -423,8 +513,13 @@ __device__ void tile_assemble_w(const WTile<MB> &tl, const DevNet &net, const De
     constexpr int LN = 32 / MB;
     const int m = tl.m;
     if (su) {
-        for (int i = tl.lane; i < net.S * MB; i += 32) su[i] = u[i];
-        __syncwarp();
+        if (tl.ch.bar) {
+            bulk_issue(tl.ch, su, u, (unsigned)(net.S * MB * 8), tl.lane, true);
+            bulk_wait(tl.ch, tl.lane);
+        } else {
+            for (int i = tl.lane; i < net.S * MB; i += 32) su[i] = u[i];
+            __syncwarp();
+        }
         u = su;
     }
     if (MB == 1) {
@@ -492,6 +587,7 @@ __device__ void tile_assemble_w(const WTile<MB> &tl, const DevNet &net, const De
     }
     __syncwarp();
     for (int i = tl.ln; i < net.S; i += LN) tl.lu[(size_t)net.diag_slot[i] * MB + m] += hg_inv;
+    fence_proxy_async();        // the factorisation reads these values with bulk copies
     __syncwarp();
 }
 
@@ -545,15 +641,27 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
         const int cw = x1 - x0;
         double *gP = lu + (size_t)uc.w * MB;
         const int4 *trec = pl.t_info + (size_t)3 * task0;
-        // ---- the chunk goes to shared memory with one burst of cp.async (group C): every byte of
-        // it is in flight at once while the prologue below runs ----
+        // ---- the chunk goes to shared memory with one bulk copy (cp.async group C without a copy
+        // engine channel): it is in flight while the prologue below runs ----
         {
             const double *src = gP + (size_t)x0 * nr * MB;
             const int n = cw * nr * MB;
-            if (MB == 1) {
+            if (KB2_CHUNK_BULK && tl.ch.bar) {
+                bulk_issue(tl.ch, Wp, src, (unsigned)(n * 8), lane, false);
+            } else if (MB == 1) {
                 for (int i = lane; i < n; i += 32) cp_async8(Wp + i, src + i);
             } else {
-                for (int i = lane; i < n / 2; i += 32) cp_async16_hint(Wp + 2 * i, src + 2 * i, pol_first);
+                // eight 16-byte loads per lane in flight
+                const double2 *s2 = reinterpret_cast<const double2 *>(src);
+                double2 *d2 = reinterpret_cast<double2 *>(Wp);
+                const int n2 = n / 2;
+                for (int i0 = lane; i0 < n2; i0 += 32 * 8) {
+                    double2 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = i0 + 32 * j < n2 ? s2[i0 + 32 * j] : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (i0 + 32 * j < n2) d2[i0 + 32 * j] = v[j];
+                }
             }
             cp_async_commit();
         }
@@ -601,8 +709,9 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
         for (int c = 0; c < NC; ++c) {
             const double *up = lu + ((size_t)cb.y + (size_t)(cmap[c] & 0xffff) * cb.x) * MB + m;
 #pragma unroll
-            for (int q = 0; q < PR; ++q) cu[c][q] = (ntask > 0 && ca.z > 0 && q < cb.x) ? ld_hint(up + q * MB, pol_last) : 0.0;
+            for (int q = 0; q < PR; ++q) cu[c][q] = (KB2_LU_PREFETCH && ntask > 0 && ca.z > 0 && q < cb.x) ? ld_hint(up + q * MB, pol_last) : 0.0;
         }
+        if (KB2_CHUNK_BULK && tl.ch.bar) bulk_wait(tl.ch, lane);      // the chunk has landed
         __syncwarp();
         for (int tk = 0; tk < ntask; ++tk) {
             const int lpos = ca.y & 0x3fffffff, inch = ca.y >> 30, ntg = ca.z, map0 = ca.w;
@@ -649,59 +758,91 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
                 ls = Ls + (tk & 1) * PR * PR * MB + m;
             }
             cp_async_commit();
-            // ---- passes over the target columns.  The U' values of the first pass were loaded
-            // during the previous source; during the first pass those of the next source are put in
-            // flight.  Further passes of a wide source load on demand. ----
+            // ---- first pass: U' values were loaded during the previous source ----
             double xu[NC][PR];
-            bool first = true;
-            for (int t = ln; first || t < ntg; t += NC * LN) {
+            if (ntg > 0) {
                 double w[NC][PR];
+                double *wp[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    wp[c] = Wp + (cmap[c] >> 16) * nr * MB + m;
+                    if (!KB2_LU_PREFETCH) {
+                        const double *up = gQ + (size_t)(cmap[c] & 0xffff) * nq * MB + m;
+#pragma unroll
+                        for (int q = 0; q < PR; ++q) cu[c][q] = q < nq ? ld_hint(up + q * MB, pol_last) : 0.0;
+                    }
+#pragma unroll
+                    for (int r = 0; r < PR; ++r) w[c][r] = r < nr ? wp[c][r * MB] : 0.0;
+                }
+                // U' values of source k+1 fly while source k is applied
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const double *up = lu + ((size_t)xb.y + (size_t)(xmap[c] & 0xffff) * xb.x) * MB + m;
+#pragma unroll
+                    for (int q = 0; q < PR; ++q) xu[c][q] = (KB2_LU_PREFETCH && has_next && xa.z > 0 && q < xb.x) ? ld_hint(up + q * MB, pol_last) : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < PR; ++q) {
+                    if (q < nq) {
+                        double l[PR];
+#pragma unroll
+                        for (int r = 0; r < PR; ++r) l[r] = r < nr ? ls[(q * nr + r) * MB] : 0.0;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c)
+#pragma unroll
+                            for (int r = 0; r < PR; ++r) w[c][r] -= l[r] * cu[c][q];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (ln + c * LN < ntg) {
+#pragma unroll
+                        for (int r = 0; r < PR; ++r) if (r < nr) wp[c][r * MB] = w[c][r];
+                    }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const double *up = lu + ((size_t)xb.y + (size_t)(xmap[c] & 0xffff) * xb.x) * MB + m;
+#pragma unroll
+                    for (int q = 0; q < PR; ++q) xu[c][q] = (KB2_LU_PREFETCH && has_next && xa.z > 0 && q < xb.x) ? ld_hint(up + q * MB, pol_last) : 0.0;
+                }
+            }
+            // ---- further passes of a wide source: loaded on demand ----
+            for (int t = ln + NC * LN; t < ntg; t += NC * LN) {
+                double uu[NC][PR], w[NC][PR];
                 double *wp[NC];
                 bool ok[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     ok[c] = t + c * LN < ntg;
-                    int e = cmap[c];
-                    if (!first) {
-                        e = pl.map[map0 + (ok[c] ? t + c * LN : t)];
-                        const double *up = gQ + (size_t)(e & 0xffff) * nq * MB + m;
-#pragma unroll
-                        for (int q = 0; q < PR; ++q) cu[c][q] = q < nq ? ld_hint(up + q * MB, pol_last) : 0.0;
-                    }
+                    const int e = pl.map[map0 + (ok[c] ? t + c * LN : t)];
+                    const double *up = gQ + (size_t)(e & 0xffff) * nq * MB + m;
                     wp[c] = Wp + (e >> 16) * nr * MB + m;
 #pragma unroll
-                    for (int r = 0; r < PR; ++r) w[c][r] = (r < nr && ntg > 0) ? wp[c][r * MB] : 0.0;
+                    for (int q = 0; q < PR; ++q) uu[c][q] = q < nq ? ld_hint(up + q * MB, pol_last) : 0.0;
                 }
-                if (first) {
-                    // U' values of source k+1 fly while source k is applied
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        const double *up = lu + ((size_t)xb.y + (size_t)(xmap[c] & 0xffff) * xb.x) * MB + m;
+                for (int c = 0; c < NC; ++c)
 #pragma unroll
-                        for (int q = 0; q < PR; ++q) xu[c][q] = (has_next && xa.z > 0 && q < xb.x) ? ld_hint(up + q * MB, pol_last) : 0.0;
+                    for (int r = 0; r < PR; ++r) w[c][r] = r < nr ? wp[c][r * MB] : 0.0;
+#pragma unroll
+                for (int q = 0; q < PR; ++q) {
+                    if (q < nq) {
+                        double l[PR];
+#pragma unroll
+                        for (int r = 0; r < PR; ++r) l[r] = r < nr ? ls[(q * nr + r) * MB] : 0.0;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c)
+#pragma unroll
+                            for (int r = 0; r < PR; ++r) w[c][r] -= l[r] * uu[c][q];
                     }
                 }
-                if (ntg > 0) {
 #pragma unroll
-                    for (int q = 0; q < PR; ++q) {
-                        if (q < nq) {
-                            double l[PR];
+                for (int c = 0; c < NC; ++c)
+                    if (ok[c]) {
 #pragma unroll
-                            for (int r = 0; r < PR; ++r) l[r] = r < nr ? ls[(q * nr + r) * MB] : 0.0;
-#pragma unroll
-                            for (int c = 0; c < NC; ++c)
-#pragma unroll
-                                for (int r = 0; r < PR; ++r) w[c][r] -= l[r] * cu[c][q];
-                        }
+                        for (int r = 0; r < PR; ++r) if (r < nr) wp[c][r * MB] = w[c][r];
                     }
-#pragma unroll
-                    for (int c = 0; c < NC; ++c)
-                        if (ok[c]) {
-#pragma unroll
-                            for (int r = 0; r < PR; ++r) if (r < nr) wp[c][r * MB] = w[c][r];
-                        }
-                }
-                first = false;
             }
             __syncwarp();
             // rotate the pipeline
@@ -832,19 +973,28 @@ __device__ __forceinline__ void prefetch_panel_cols(const DevPlan &pl, const dou
     prefetch_l2_bulk((const void *)a16, (unsigned)((a + nbytes - a16) & ~(size_t)15));
 }
 
-// columns [c0, c1) of panel P -> shared memory (values as in global memory, then the column indices)
+// columns [c0, c1) of panel P -> shared memory: the values with one bulk copy (or cp.async when
+// the warp has no copy-engine channel), the column indices with cp.async
 template <int MB>
-__device__ __forceinline__ void stage_panel_cols(double *buf, int *cbuf, const double *gsrc, const int *csrc, int ncol, int nr, int lane)
+__device__ __forceinline__ void stage_panel_cols(const BulkChan &ch, double *buf, int *cbuf, const double *gsrc, const int *csrc,
+                                                 int ncol, int nr, int lane)
 {
     const int n = ncol * nr * MB;
-    if (MB == 1) {
-        for (int i = lane; i < n; i += 32) cp_async8(buf + i, gsrc + i);
+    if (ch.bar) {
+        bulk_issue(ch, buf, gsrc, (unsigned)(n * 8), lane, false);
     } else {
-        const unsigned long long pol = l2_policy_first();
-        for (int i = lane; i < n / 2; i += 32) cp_async16_hint(buf + 2 * i, gsrc + 2 * i, pol);
+        for (int i = lane; i < n; i += 32) cp_async8(buf + i, gsrc + i);
     }
     for (int i = lane; i < ncol; i += 32) cp_async4(cbuf + i, csrc + i);
     cp_async_commit();
+}
+
+template <int MB>
+__device__ __forceinline__ void stage_panel_wait(const BulkChan &ch, int lane)
+{
+    cp_async_wait_all();
+    if (ch.bar) bulk_wait(ch, lane);
+    else __syncwarp();
 }
 
 template <int MB>
@@ -859,6 +1009,8 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
     const int m = tl.m, r = tl.ln % PR, cg = tl.ln / PR;
     const double *lu = tl.lu;
     double *y = tl.y;
+    fence_proxy_async();        // the factors were written with ordinary stores and are read with bulk copies
+    __syncwarp();
     // ---------------- forward:  L' y = P rhs ----------------
     if (tl.lane < AHEAD && tl.lane < pl.npanels) prefetch_panel_cols<MB>(pl, lu, tl.lane, 0, pl.p_next[tl.lane] + pl.p_nrows[tl.lane]);
     for (int P = 0; P < pl.npanels; ++P) {
@@ -867,8 +1019,8 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
         const double *gP = lu + (size_t)pl.p_base[P] * MB;
         const bool rok = r < nr;
         const int ncol = next + nr;                                  // L part and diagonal block
-        const bool staged = ncol * nr * MB <= CAPD && ncol <= CAPC;
-        if (staged) stage_panel_cols<MB>(sm, cbuf, gP, C, ncol, nr, tl.lane);
+        const bool staged = KB2_TRISTAGE && ncol * nr * MB <= CAPD && ncol <= CAPC;
+        if (staged) stage_panel_cols<MB>(tl.ch, sm, cbuf, gP, C, ncol, nr, tl.lane);
         if (tl.lane == 0 && P + AHEAD < pl.npanels)
             prefetch_panel_cols<MB>(pl, lu, P + AHEAD, 0, pl.p_next[P + AHEAD] + pl.p_nrows[P + AHEAD]);
         const double bz = rok ? rhs[net.perm[p0 + r] * MB + m] : 0.0;
@@ -876,8 +1028,7 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
         const double *vals = staged ? (const double *)sm + m : gP + m;
         double acc;
         if (staged) {
-            cp_async_wait_all();
-            __syncwarp();
+            stage_panel_wait<MB>(tl.ch, tl.lane);
             acc = rok ? panel_dot<MB, true>(vals, cbuf, y, 0, next, nr, r, cg, m) : 0.0;
         } else {
             acc = rok ? panel_dot<MB, false>(vals, C, y, 0, next, nr, r, cg, m) : 0.0;
@@ -907,15 +1058,14 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
         const double *gP = lu + ((size_t)pl.p_base[P] + (size_t)next * nr) * MB;
         const bool rok = r < nr;
         const int ncol = W - next;                                   // diagonal block and U part
-        const bool staged = ncol * nr * MB <= CAPD && ncol <= CAPC;
-        if (staged) stage_panel_cols<MB>(sm, cbuf, gP, C, ncol, nr, tl.lane);
+        const bool staged = KB2_TRISTAGE && ncol * nr * MB <= CAPD && ncol <= CAPC;
+        if (staged) stage_panel_cols<MB>(tl.ch, sm, cbuf, gP, C, ncol, nr, tl.lane);
         if (tl.lane == 0 && P - AHEAD >= 0) prefetch_panel_cols<MB>(pl, lu, P - AHEAD, pl.p_next[P - AHEAD], pl.p_width[P - AHEAD]);
         const double yz = rok ? y[(p0 + r) * MB + m] : 0.0;
         const double *vals = staged ? (const double *)sm + m : gP + m;
         double acc;
         if (staged) {
-            cp_async_wait_all();
-            __syncwarp();
+            stage_panel_wait<MB>(tl.ch, tl.lane);
             acc = rok ? panel_dot<MB, true>(vals, cbuf, y, nr, ncol, nr, r, cg, m) : 0.0;
         } else {
             acc = rok ? panel_dot<MB, false>(vals, C, y, nr, ncol, nr, r, cg, m) : 0.0;

@@ -11,9 +11,9 @@ __host__ __device__ constexpr size_t lu_smem_bytes(int mb) { return lu_smem_doub
 inline size_t warp_smem_bytes(int mb, int64_t S, bool *u_fits)
 {
     const size_t base = lu_smem_bytes(mb), ub = (size_t)S * mb * sizeof(double), cap = 232448 / 7 - 1024;
-    const size_t smem = (ub > base && ub <= cap) ? ub : base;
+    const size_t smem = (ub > base && ub + 16 <= cap) ? ub : base;
     if (u_fits) *u_fits = ub <= smem;
-    return smem;
+    return smem;            // data bytes; kernels are launched with 16 more for the copy channel's mbarrier
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -60,18 +60,20 @@ __global__ void k_pack_bs(int S, int B, const double *tiles, double *dst)
 template <int MB>
 __global__ void __launch_bounds__(32) k_rates(DevNet net, DevPlan pl, DevEns en, const double *T, int ntiles)
 {
+    BulkChan ch; ch.bar = 0; ch.par = nullptr;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        WTile<MB> tl(tile, net, pl, en);
+        WTile<MB> tl(tile, net, pl, en, ch);
         tile_rates(tl, net, T[tl.b], true, -1);
     }
 }
 
 template <int MB>
-__global__ void __launch_bounds__(32) k_rhs(DevNet net, DevPlan pl, DevEns en, int ntiles)
+__global__ void __launch_bounds__(32) k_rhs(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes)
 {
     extern __shared__ double smem[];
+    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        WTile<MB> tl(tile, net, pl, en);
+        WTile<MB> tl(tile, net, pl, en, ch);
         tile_rhs(tl, net, tl.u, tl.rv, 0, 0.0, 0.0, 0.0, 0.0, 0.0, en.u_smem ? smem : nullptr);
     }
 }
@@ -80,29 +82,32 @@ __global__ void __launch_bounds__(32) k_rhs(DevNet net, DevPlan pl, DevEns en, i
 template <int MB>
 __global__ void __launch_bounds__(32) k_jac(DevNet net, DevPlan pl, DevEns en, int ntiles)
 {
+    BulkChan ch; ch.bar = 0; ch.par = nullptr;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        WTile<MB> tl(tile, net, pl, en);
+        WTile<MB> tl(tile, net, pl, en, ch);
         tile_jac_csc(tl, net, tl.u, tl.lu);
     }
 }
 
 template <int MB>
-__global__ void __launch_bounds__(32) k_factor(DevNet net, DevPlan pl, DevEns en, const double *hg_inv, int ntiles, int mode)
+__global__ void __launch_bounds__(32) k_factor(DevNet net, DevPlan pl, DevEns en, const double *hg_inv, int ntiles, int mode, int data_bytes)
 {
     extern __shared__ double smem[];
+    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        WTile<MB> tl(tile, net, pl, en);
+        WTile<MB> tl(tile, net, pl, en, ch);
         if (mode & 1) tile_assemble_w(tl, net, pl, tl.u, hg_inv[tl.b], en.u_smem ? smem : nullptr);
         if (mode & 2) tile_lu(tl, pl, smem);
     }
 }
 
 template <int MB>
-__global__ void __launch_bounds__(32) k_trisolve(DevNet net, DevPlan pl, DevEns en, int ntiles)
+__global__ void __launch_bounds__(32) k_trisolve(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes)
 {
     extern __shared__ double smem[];
+    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        WTile<MB> tl(tile, net, pl, en);
+        WTile<MB> tl(tile, net, pl, en, ch);
         tile_trisolve(tl, net, pl, tl.rv, tl.ua, smem);
     }
 }
@@ -216,10 +221,10 @@ __device__ void tile_restart_h(const WTile<MB> &tl, const DevNet &net, const Dev
 }
 
 template <int MB>
-__device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en, double *Wp)
+__device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en, double *Wp, const BulkChan &ch)
 {
     constexpr int LN = 32 / MB;
-    WTile<MB> tl(tile, net, pl, en);
+    WTile<MB> tl(tile, net, pl, en, ch);
     const int m = tl.m, b = tl.b, ln = tl.ln;
     double *su = en.u_smem ? Wp : nullptr;      // the gathers of RHS / Jacobian read the state from shared memory
     Ctl c;
@@ -262,7 +267,7 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
             // are not kept alive across it
             int tile_lu_ = tile;
             asm volatile("" : "+r"(tile_lu_));
-            const WTile<MB> tlu(tile_lu_, net, pl, en);
+            const WTile<MB> tlu(tile_lu_, net, pl, en, ch);
             tile_lu(tlu, pl, Wp);
         }
         for (int s = 0; s < 6; ++s) {
@@ -345,15 +350,16 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
 }
 
 template <int MB>
-__global__ void __launch_bounds__(32) k_solve(DevNet net, DevPlan pl, DevEns en, int ntiles, int *tile_counter)
+__global__ void __launch_bounds__(32) k_solve(DevNet net, DevPlan pl, DevEns en, int ntiles, int *tile_counter, int data_bytes)
 {
     extern __shared__ double smem[];
+    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
     for (;;) {
         int tile = 0;
         if ((threadIdx.x & 31) == 0) tile = atomicAdd(tile_counter, 1);
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= ntiles) break;
-        solve_tile<MB>(tile, net, pl, en, smem);
+        solve_tile<MB>(tile, net, pl, en, smem, ch);
     }
 }
 

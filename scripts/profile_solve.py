@@ -17,6 +17,7 @@ conds = [kb.ConditionSet({"T": kb.LinearDirectProfile(rate=100.0, X_start=600.0 
 for cs in conds:
     cs.solve_variable_conditions(pars)
 es = kb.EnsembleSolver(sd, rd, calc)
+es.h.set_tiling(int(os.environ.get('KB2_MBSET', '0')), 0)
 for rep in range(2):
     es.prepare(conds, pars, synthetic_u0(S))
     ms = es.run()

@@ -116,8 +116,9 @@ def test_rhs_deterministic(small):
     assert np.array_equal(a, b)            # gather CSR, no atomics: bit-identical run to run
 
 
-@pytest.mark.parametrize("S,R,ordering,B", [(96, 400, 0, 19), (420, 2100, 3, 9), (420, 2100, 0, 16), (30, 60, 1, 3)])
-def test_factor_and_trisolve_panels(built, S, R, ordering, B):
+@pytest.mark.parametrize("S,R,ordering,B,mb", [(96, 400, 0, 19, 0), (420, 2100, 3, 9, 1), (420, 2100, 0, 16, 4), (30, 60, 1, 3, 0),
+                                               (420, 2100, 3, 10, 2), (200, 1000, 3, 37, 4), (96, 400, 4, 8, 2)])
+def test_factor_and_trisolve_panels(built, S, R, ordering, B, mb):
     """Panel LU + panel triangular solves on networks whose hub rows span several column chunks
     (S = 420: widest panel > 3 chunks), for every ordering mode and ragged member counts."""
     from kinetica_b200 import _lib
@@ -127,9 +128,10 @@ def test_factor_and_trisolve_panels(built, S, R, ordering, B):
     h = _lib.Handle(0)
     h.set_network(S, *rd.flatten())
     h.symbolic(ordering)
+    h.set_tiling(mb)        # members per warp tile: 0 auto (1 for these small ensembles), 1, 2, 4
     st = h.get_plan_stats()
     if S == 420:
-        assert st["max_width"] > 256 and st["units"] > st["panels"]
+        assert st["max_width"] > 96 and st["units"] > st["panels"]
     net = ko.Network(S, rd.id_reacs, rd.id_prods, rd.stoic_reacs, rd.stoic_prods)
     _factor_trisolve_check(h, net, B, seed=S)
     h.close()

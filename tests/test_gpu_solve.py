@@ -113,6 +113,24 @@ def test_ensemble_vs_c_oracle(ensemble_case):
         assert np.array_equal(o.umax, np.max(np.array(o.sol.u), axis=0))
 
 
+@pytest.mark.parametrize("mb", [2, 4])
+def test_tile_sizes_agree(ensemble_case, monkeypatch, mb):
+    """The ensemble solved with 2 and 4 members per warp tile (the sizes large ensembles run at;
+    this small one defaults to 1) against the 1-member-per-tile solution, ragged last tile included."""
+    import kinetica_b200 as kb
+    from kinetica_b200.synthetic import synthetic_u0
+    sd, rd, Ea, A, Ts, conds, outs = ensemble_case
+    monkeypatch.setenv("KB2_MB", str(mb))
+    calc = kb.PrecalculatedArrheniusCalculator(Ea, A, k_max=1e12)
+    pars = kb.ODESimulationParams(tspan=(0.0, 1.0), u0=synthetic_u0(sd.n), save_interval=0.1,
+                                  low_k_cutoff="none", solve_chunks=False, abstol=1e-12, reltol=1e-10)
+    got = kb.solve_network(kb.B200EnsembleODESolve(pars, conds, calc), sd, rd)
+    for a, b in zip(got, outs):
+        assert a.sol.retcode == "Success"
+        _check(np.array(a.sol.u), np.array(b.sol.u))
+        assert np.array_equal(a.umax, np.max(np.array(a.sol.u), axis=0))
+
+
 def test_default_tolerances_vs_tight(ensemble_case):
     """Reference-default tolerances (abstol 1e-10, reltol 1e-8) against the tight solution: the
     solver's own global error, bounded at 1e-4 relative."""
