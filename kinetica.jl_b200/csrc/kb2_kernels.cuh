@@ -483,24 +483,74 @@ __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u
     __syncwarp();
 }
 
-// K3: analytic Jacobian entry p = (i,l):  J_p = sum_t coef_t * k_j * d(prod)/du_l
-template <int MB>
-__device__ __forceinline__ double jac_entry(const WTile<MB> &tl, const DevNet &net, int p, const double *u)
+// K3: analytic Jacobian entries  J_p = sum_t coef_t * k_j * d(prod)/du_l  for every entry p of
+// the fixed CSC pattern, handed to `put(p, J_p)`.  Entries with many terms (hub columns) are
+// split across the lanes of the member; the others go one per lane, KB2_RHS_U in flight, longest
+// first, branch-free (an exhausted entry re-reads its last term with coefficient 0).
+template <int MB, class Put>
+__device__ __forceinline__ void tile_jac_entries(const WTile<MB> &tl, const DevNet &net, const double *u, Put put)
 {
-    double acc = 0.0;
-    const int t1 = net.jt_ptr[p + 1];
-    for (int t = net.jt_ptr[p]; t < t1; ++t) {
-        const int j = net.jt_rxn[t], pk = net.jt_pack[t];
-        acc += (double)(pk >> 2) * drate_of(net.rdesc[j], pk & 3, u, MB, tl.m, tl.k[j * MB + tl.m]);
+    constexpr int LN = 32 / MB;
+    const int m = tl.m;
+    for (int z = 0; z < net.j_nlong; ++z) {
+        const int p = net.j_order[z];
+        const int t1 = net.jt_ptr[p + 1];
+        double a0 = 0.0, a1 = 0.0;
+        int t = net.jt_ptr[p] + tl.ln;
+        for (; t + LN < t1; t += 2 * LN) {
+            const int j0 = net.jt_rxn[t], pk0 = net.jt_pack[t], j1 = net.jt_rxn[t + LN], pk1 = net.jt_pack[t + LN];
+            a0 += (double)(pk0 >> 2) * drate_of(net.rdesc[j0], pk0 & 3, u, MB, m, tl.k[j0 * MB + m]);
+            a1 += (double)(pk1 >> 2) * drate_of(net.rdesc[j1], pk1 & 3, u, MB, m, tl.k[j1 * MB + m]);
+        }
+        for (; t < t1; t += LN) {
+            const int j0 = net.jt_rxn[t], pk0 = net.jt_pack[t];
+            a0 += (double)(pk0 >> 2) * drate_of(net.rdesc[j0], pk0 & 3, u, MB, m, tl.k[j0 * MB + m]);
+        }
+        const double a = member_sum<MB>(a0 + a1);
+        if (tl.ln == 0) put(p, a);
     }
-    return acc;
+    constexpr int U = KB2_RHS_U;
+    for (int z0 = net.j_nlong + tl.ln; z0 < net.nnzJ; z0 += U * LN) {
+        int t[U], n[U], pe[U];
+        double v[U];
+        int len = 0;
+#pragma unroll
+        for (int x = 0; x < U; ++x) {
+            const int z = z0 + x * LN;
+            pe[x] = z < net.nnzJ ? net.j_order[z] : -1;
+            t[x] = pe[x] >= 0 ? net.jt_ptr[pe[x]] : 0;
+            n[x] = pe[x] >= 0 ? net.jt_ptr[pe[x] + 1] - t[x] : 0;
+            v[x] = 0.0;
+            len = max(len, n[x]);
+        }
+        for (int z = 0; z < len; ++z) {
+            int jj[U], pk[U];
+            int4 d[U];
+            double kj[U], dr[U];
+#pragma unroll
+            for (int x = 0; x < U; ++x) {
+                const int tt = t[x] + min(z, max(n[x] - 1, 0));
+                jj[x] = net.jt_rxn[tt];
+                pk[x] = z < n[x] ? net.jt_pack[tt] : (net.jt_pack[tt] & 3);     // exhausted entry: coefficient 0
+            }
+#pragma unroll
+            for (int x = 0; x < U; ++x) { d[x] = net.rdesc[jj[x]]; kj[x] = tl.k[jj[x] * MB + m]; }
+#pragma unroll
+            for (int x = 0; x < U; ++x) dr[x] = drate_of(d[x], pk[x] & 3, u, MB, m, kj[x]);
+#pragma unroll
+            for (int x = 0; x < U; ++x) v[x] += (double)(pk[x] >> 2) * dr[x];
+        }
+#pragma unroll
+        for (int x = 0; x < U; ++x)
+            if (pe[x] >= 0) put(pe[x], v[x]);
+    }
 }
 
 template <int MB>
 __device__ void tile_jac_csc(const WTile<MB> &tl, const DevNet &net, const double *u, double *Jval)
 {
-    constexpr int LN = 32 / MB;
-    for (int p = tl.ln; p < net.nnzJ; p += LN) Jval[p * MB + tl.m] = jac_entry(tl, net, p, u);
+    const int m = tl.m;
+    tile_jac_entries<MB>(tl, net, u, [&](int p, double v) { Jval[p * MB + m] = v; });
     __syncwarp();
 }
 
@@ -531,60 +581,7 @@ __device__ void tile_assemble_w(const WTile<MB> &tl, const DevNet &net, const De
         for (int i = tl.lane; i < n2; i += 32) st2_hint(z + i, make_double2(0.0, 0.0), pol);
     }
     __syncwarp();
-    // entries with many terms (hub columns): the lanes of the member stride over the terms
-    for (int z = 0; z < net.j_nlong; ++z) {
-        const int p = net.j_order[z];
-        const int t1 = net.jt_ptr[p + 1];
-        double a0 = 0.0, a1 = 0.0;
-        int t = net.jt_ptr[p] + tl.ln;
-        for (; t + LN < t1; t += 2 * LN) {
-            const int j0 = net.jt_rxn[t], pk0 = net.jt_pack[t], j1 = net.jt_rxn[t + LN], pk1 = net.jt_pack[t + LN];
-            a0 += (double)(pk0 >> 2) * drate_of(net.rdesc[j0], pk0 & 3, u, MB, m, tl.k[j0 * MB + m]);
-            a1 += (double)(pk1 >> 2) * drate_of(net.rdesc[j1], pk1 & 3, u, MB, m, tl.k[j1 * MB + m]);
-        }
-        for (; t < t1; t += LN) {
-            const int j0 = net.jt_rxn[t], pk0 = net.jt_pack[t];
-            a0 += (double)(pk0 >> 2) * drate_of(net.rdesc[j0], pk0 & 3, u, MB, m, tl.k[j0 * MB + m]);
-        }
-        const double a = member_sum<MB>(a0 + a1);
-        if (tl.ln == 0) tl.lu[(size_t)net.jslot[p] * MB + m] = -a;
-    }
-    // the other entries one per lane, eight in flight, longest first
-    constexpr int U = KB2_RHS_U;
-    for (int z0 = net.j_nlong + tl.ln; z0 < net.nnzJ; z0 += U * LN) {
-        int t[U], n[U], pe[U];
-        double v[U];
-        int len = 0;
-#pragma unroll
-        for (int x = 0; x < U; ++x) {
-            const int z = z0 + x * LN;
-            pe[x] = z < net.nnzJ ? net.j_order[z] : -1;
-            t[x] = pe[x] >= 0 ? net.jt_ptr[pe[x]] : 0;
-            n[x] = pe[x] >= 0 ? net.jt_ptr[pe[x] + 1] - t[x] : 0;
-            v[x] = 0.0;
-            len = max(len, n[x]);
-        }
-        for (int z = 0; z < len; ++z) {
-            int jj[U], pk[U];
-            int4 d[U];
-            double kj[U], dr[U];
-#pragma unroll
-            for (int x = 0; x < U; ++x) {
-                const int tt = t[x] + min(z, max(n[x] - 1, 0));
-                jj[x] = net.jt_rxn[tt];
-                pk[x] = z < n[x] ? net.jt_pack[tt] : (net.jt_pack[tt] & 3);     // exhausted entry: coefficient 0
-            }
-#pragma unroll
-            for (int x = 0; x < U; ++x) { d[x] = net.rdesc[jj[x]]; kj[x] = tl.k[jj[x] * MB + m]; }
-#pragma unroll
-            for (int x = 0; x < U; ++x) dr[x] = drate_of(d[x], pk[x] & 3, u, MB, m, kj[x]);
-#pragma unroll
-            for (int x = 0; x < U; ++x) v[x] -= (double)(pk[x] >> 2) * dr[x];
-        }
-#pragma unroll
-        for (int x = 0; x < U; ++x)
-            if (pe[x] >= 0) tl.lu[(size_t)net.jslot[pe[x]] * MB + m] = v[x];
-    }
+    tile_jac_entries<MB>(tl, net, u, [&](int p, double v) { tl.lu[(size_t)net.jslot[p] * MB + m] = -v; });
     __syncwarp();
     for (int i = tl.ln; i < net.S; i += LN) tl.lu[(size_t)net.diag_slot[i] * MB + m] += hg_inv;
     fence_proxy_async();        // the factorisation reads these values with bulk copies
