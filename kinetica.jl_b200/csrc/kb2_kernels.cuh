@@ -185,6 +185,15 @@ __device__ inline double profile_eval(int kind, const double *p, double t)
 #ifndef KB2_CHUNK_BULK
 #define KB2_CHUNK_BULK 1      // panel chunks go to shared memory with one bulk copy
 #endif
+#ifndef KB2_TRI_U
+#define KB2_TRI_U 8            // column positions per lane in flight in the triangular sweeps
+#endif
+#ifndef KB2_TRI_AHEAD
+#define KB2_TRI_AHEAD 0        // panels pulled towards L2 ahead of the sweep (0: the panel about to be read; -1: none)
+#endif
+#ifndef KB2_LU_L2PF
+#define KB2_LU_L2PF 1         // bulk L2 prefetch of the next unit's chunk and target spans
+#endif
 #ifndef KB2_NC
 #define KB2_NC 3               // target columns per lane and pass in the LU update
 #endif
@@ -680,6 +689,8 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
         // next unit: its record, and L2 prefetch of its chunk and of its sources' target spans
         if (un + 1 < pl.nunits) {
             na = pl.u_info[3 * un + 3]; nb = pl.u_info[3 * un + 4]; nc = pl.u_info[3 * un + 5];
+        }
+        if (KB2_LU_L2PF && un + 1 < pl.nunits) {
             if (lane == 31) {
                 const char *a = (const char *)(lu + ((size_t)nc.w + (size_t)na.y * nc.x) * MB);
                 const size_t nbytes = (size_t)(na.z - na.y) * nc.x * MB * 8;
@@ -941,20 +952,20 @@ __device__ __forceinline__ double panel_dot(const double *vals, const int *idx, 
                                             int cbeg, int cend, int nr, int r, int cg, int m)
 {
     // vals[(c*nr + r)*MB], idx[c]: shared-memory copies (SMEM) or the global arrays
-    constexpr int CG = 32 / MB / PR;
+    constexpr int CG = 32 / MB / PR, TU = KB2_TRI_U;
     double a[4] = {0.0, 0.0, 0.0, 0.0};
     int c = cbeg + cg;
-    for (; c + 7 * CG < cend; c += 8 * CG) {
-        int ix[8];
-        double lv[8], yv[8];
+    for (; c + (TU - 1) * CG < cend; c += TU * CG) {
+        int ix[TU];
+        double lv[TU], yv[TU];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ix[j] = idx[c + j * CG];
+        for (int j = 0; j < TU; ++j) ix[j] = idx[c + j * CG];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) lv[j] = vals[((c + j * CG) * nr + r) * MB];
+        for (int j = 0; j < TU; ++j) lv[j] = vals[((c + j * CG) * nr + r) * MB];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) yv[j] = y[ix[j] * MB + m];
+        for (int j = 0; j < TU; ++j) yv[j] = y[ix[j] * MB + m];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j & 3] += lv[j] * yv[j];
+        for (int j = 0; j < TU; ++j) a[j & 3] += lv[j] * yv[j];
     }
     for (; c < cend; c += CG) a[0] += vals[(c * nr + r) * MB] * y[idx[c] * MB + m];
     return (a[0] + a[1]) + (a[2] + a[3]);
@@ -999,7 +1010,7 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
 {
     constexpr int LN = 32 / MB, CG = LN / PR;
     static_assert(CG >= 1, "at most 4 members per warp tile");
-    constexpr int AHEAD = 2;
+    constexpr int AHEAD = KB2_TRI_AHEAD;
     constexpr int CAPC = 2 * PR * PR * MB;                          // column indices (ints) at the tail of the buffer
     constexpr int CAPD = (CWMAX * PR + 2 * PR * PR) * MB;            // values (doubles)
     int *cbuf = reinterpret_cast<int *>(sm + CAPD);
@@ -1009,7 +1020,7 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
     fence_proxy_async();        // the factors were written with ordinary stores and are read with bulk copies
     __syncwarp();
     // ---------------- forward:  L' y = P rhs ----------------
-    if (tl.lane < AHEAD && tl.lane < pl.npanels) prefetch_panel_cols<MB>(pl, lu, tl.lane, 0, pl.p_next[tl.lane] + pl.p_nrows[tl.lane]);
+    if (AHEAD > 0 && tl.lane < AHEAD && tl.lane < pl.npanels) prefetch_panel_cols<MB>(pl, lu, tl.lane, 0, pl.p_next[tl.lane] + pl.p_nrows[tl.lane]);
     for (int P = 0; P < pl.npanels; ++P) {
         const int nr = pl.p_nrows[P], next = pl.p_next[P], p0 = pl.p_row0[P];
         const int *C = pl.cols + pl.p_cptr[P];
@@ -1018,7 +1029,7 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
         const int ncol = next + nr;                                  // L part and diagonal block
         const bool staged = KB2_TRISTAGE && ncol * nr * MB <= CAPD && ncol <= CAPC;
         if (staged) stage_panel_cols<MB>(tl.ch, sm, cbuf, gP, C, ncol, nr, tl.lane);
-        if (tl.lane == 0 && P + AHEAD < pl.npanels)
+        if (AHEAD >= 0 && tl.lane == 0 && P + AHEAD < pl.npanels)
             prefetch_panel_cols<MB>(pl, lu, P + AHEAD, 0, pl.p_next[P + AHEAD] + pl.p_nrows[P + AHEAD]);
         const double bz = rok ? rhs[net.perm[p0 + r] * MB + m] : 0.0;
         const double dinv = rok ? tl.invd[(p0 + r) * MB + m] : 0.0;
@@ -1045,7 +1056,7 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
         __syncwarp();
     }
     // ---------------- backward:  U' x = y ----------------
-    if (tl.lane < AHEAD && tl.lane < pl.npanels) {
+    if (AHEAD > 0 && tl.lane < AHEAD && tl.lane < pl.npanels) {
         const int P = pl.npanels - 1 - tl.lane;
         prefetch_panel_cols<MB>(pl, lu, P, pl.p_next[P], pl.p_width[P]);
     }
@@ -1057,7 +1068,7 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
         const int ncol = W - next;                                   // diagonal block and U part
         const bool staged = KB2_TRISTAGE && ncol * nr * MB <= CAPD && ncol <= CAPC;
         if (staged) stage_panel_cols<MB>(tl.ch, sm, cbuf, gP, C, ncol, nr, tl.lane);
-        if (tl.lane == 0 && P - AHEAD >= 0) prefetch_panel_cols<MB>(pl, lu, P - AHEAD, pl.p_next[P - AHEAD], pl.p_width[P - AHEAD]);
+        if (AHEAD >= 0 && tl.lane == 0 && P - AHEAD >= 0) prefetch_panel_cols<MB>(pl, lu, P - AHEAD, pl.p_next[P - AHEAD], pl.p_width[P - AHEAD]);
         const double yz = rok ? y[(p0 + r) * MB + m] : 0.0;
         const double *vals = staged ? (const double *)sm + m : gP + m;
         double acc;

@@ -349,8 +349,11 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
     __syncwarp();
 }
 
+#ifndef KB2_MINB2
+#define KB2_MINB2 1           // minimum resident warps per SM requested for the MB = 2 instantiation of k_solve
+#endif
 template <int MB>
-__global__ void __launch_bounds__(32) k_solve(DevNet net, DevPlan pl, DevEns en, int ntiles, int *tile_counter, int data_bytes)
+__global__ void __launch_bounds__(32, MB == 2 ? KB2_MINB2 : 1) k_solve(DevNet net, DevPlan pl, DevEns en, int ntiles, int *tile_counter, int data_bytes)
 {
     extern __shared__ double smem[];
     const BulkChan ch = chan_setup<MB>(smem, data_bytes);
