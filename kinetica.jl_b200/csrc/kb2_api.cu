@@ -137,7 +137,7 @@ extern "C" int32_t kb2_set_tiling(kb2_handle h, int32_t mb, int32_t reserved)
 {
     if (!h) return 1;
     (void)reserved;
-    if (mb != 0 && mb != 1 && mb != 2 && mb != 4) FAIL(h, "members_per_tile must be 0 (auto), 1, 2 or 4");
+    if (mb != 0 && mb != 1 && mb != 2 && mb != 4 && mb != 8) FAIL(h, "members_per_tile must be 0 (auto), 1, 2, 4 or 8");
     h->mb_user = mb;
     h->ens_B = -1;            // the tile size is baked into the device layout
     h->prepared = false;
@@ -413,7 +413,7 @@ static int pick_mb(kb2_ctx *h, int64_t B)
     if (h->mb_user) return h->mb_user;
     if (const char *ev = getenv("KB2_MB")) {       // testing / tuning knob, same meaning as kb2_set_tiling
         const int v = atoi(ev);
-        if (v == 1 || v == 2 || v == 4) return v;
+        if (v == 1 || v == 2 || v == 4 || v == 8) return v;
     }
     // four members per warp tile (32-byte sectors fully used) unless the ensemble is too small to
     // give every SM a few warps
@@ -472,6 +472,7 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
     switch (mb) {                                                     \
     case 1: { constexpr int MB = 1; __VA_ARGS__; } break;             \
     case 2: { constexpr int MB = 2; __VA_ARGS__; } break;             \
+    case 8: { constexpr int MB = 8; __VA_ARGS__; } break;             \
     default: { constexpr int MB = 4; __VA_ARGS__; } break;            \
     }
 

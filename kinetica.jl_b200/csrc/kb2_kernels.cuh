@@ -634,6 +634,7 @@ template <int MB>
 __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
 {
     constexpr int LN = 32 / MB, NC = KB2_NC;
+    constexpr int RL = LN < PR ? LN : PR, RPL = PR / RL;      // lanes that own rows, rows per such lane (row = ln + rr*RL)
     const int m = tl.m, ln = tl.ln, lane = tl.lane;
     double *lu = tl.lu;
     double *Uq = Wp + CWMAX * PR * MB;       // [q][a][m]: U'_QQ of the next in-chunk source
@@ -742,19 +743,23 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
             __syncwarp();
             const double *ls;                    // L'_PQ as [q][r][m] in shared memory
             if (inch) {
-                if (ln < nr) {
-                    double X[PR];
-                    double *xp = Wp + ((lpos - x0) * nr + ln) * MB + m;
 #pragma unroll
-                    for (int q = 0; q < PR; ++q) X[q] = q < nq ? xp[q * nr * MB] : 0.0;
-                    const double *uq = Uq + m;                 // U_QQ[a][q] at (q*nq + a)*MB
+                for (int rr = 0; rr < RPL; ++rr) {
+                    const int row = ln + rr * RL;
+                    if (ln < RL && row < nr) {
+                        double X[PR];
+                        double *xp = Wp + ((lpos - x0) * nr + row) * MB + m;
 #pragma unroll
-                    for (int a = 0; a < PR - 1; ++a)
+                        for (int q = 0; q < PR; ++q) X[q] = q < nq ? xp[q * nr * MB] : 0.0;
+                        const double *uq = Uq + m;                 // U_QQ[a][q] at (q*nq + a)*MB
 #pragma unroll
-                        for (int q = a + 1; q < PR; ++q)
-                            if (q < nq) X[q] -= X[a] * uq[(q * nq + a) * MB];
+                        for (int a = 0; a < PR - 1; ++a)
 #pragma unroll
-                    for (int q = 1; q < PR; ++q) if (q < nq) xp[q * nr * MB] = X[q];
+                            for (int q = a + 1; q < PR; ++q)
+                                if (q < nq) X[q] -= X[a] * uq[(q * nq + a) * MB];
+#pragma unroll
+                        for (int q = 1; q < PR; ++q) if (q < nq) xp[q * nr * MB] = X[q];
+                    }
                 }
                 __syncwarp();
                 if (cb.w >= 0) {                 // group B(k): U'_QQ of the next in-chunk source
@@ -867,29 +872,43 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
         if (dmode) {
             const int dpos = next - x0;      // position of the diagonal block relative to the chunk (negative for dmode 2)
             if (dmode == 1) {
-                // Crout LU of the nr x nr diagonal block: lane ln owns row ln, pivot rows are
-                // broadcast with shuffles
-                double D[PR];
-                double *dp = Wp + (dpos * nr + ln) * MB + m;
+                // Crout LU of the nr x nr diagonal block: lane ln (< RL) owns rows ln + rr*RL, pivot
+                // rows are broadcast with shuffles
+                double D[RPL][PR];
 #pragma unroll
-                for (int j = 0; j < PR; ++j) D[j] = (ln < nr && j < nr) ? dp[j * nr * MB] : 0.0;
+                for (int rr = 0; rr < RPL; ++rr) {
+                    const int row = ln + rr * RL;
+                    const double *dp = Wp + (dpos * nr + row) * MB + m;
+#pragma unroll
+                    for (int j = 0; j < PR; ++j) D[rr][j] = (ln < RL && row < nr && j < nr) ? dp[j * nr * MB] : 0.0;
+                }
 #pragma unroll
                 for (int j = 0; j < PR; ++j) {
                     if (j < nr) {
-                        const double piv = __shfl_sync(FULL, D[j], j * MB + m);
+                        const int oj = j % RL, sj = j / RL;          // owner lane and register slot of pivot row j
+                        const double piv = __shfl_sync(FULL, D[sj][j], oj * MB + m);
                         const double inv = 1.0 / piv;
-                        if (ln == j) tl.invd[(p0 + j) * MB + m] = inv;
+                        if (ln == oj) tl.invd[(p0 + j) * MB + m] = inv;
 #pragma unroll
                         for (int i = j + 1; i < PR; ++i) {
-                            const double uji = __shfl_sync(FULL, D[i], j * MB + m) * inv;
-                            if (ln == j) D[i] = uji;
-                            else if (ln > j) D[i] -= D[j] * uji;
+                            const double uji = __shfl_sync(FULL, D[sj][i], oj * MB + m) * inv;
+#pragma unroll
+                            for (int rr = 0; rr < RPL; ++rr) {
+                                const int row = ln + rr * RL;
+                                if (ln == oj && rr == sj) D[rr][i] = uji;
+                                else if (row > j && ln < RL) D[rr][i] -= D[rr][j] * uji;
+                            }
                         }
                     }
                 }
-                if (ln < nr) {
 #pragma unroll
-                    for (int j = 0; j < PR; ++j) if (j < nr) dp[j * nr * MB] = D[j];
+                for (int rr = 0; rr < RPL; ++rr) {
+                    const int row = ln + rr * RL;
+                    if (ln < RL && row < nr) {
+                        double *dp = Wp + (dpos * nr + row) * MB + m;
+#pragma unroll
+                        for (int j = 0; j < PR; ++j) if (j < nr) dp[j * nr * MB] = D[rr][j];
+                    }
                 }
                 __syncwarp();
             }
@@ -948,27 +967,40 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
 // the panel two links ahead has been pulled into L2 with a bulk prefetch; a panel too wide for
 // the buffer (hub rows) is read straight from global memory, eight positions per lane in flight.
 template <int MB, bool SMEM>
-__device__ __forceinline__ double panel_dot(const double *vals, const int *idx, const double *y,
-                                            int cbeg, int cend, int nr, int r, int cg, int m)
+__device__ __forceinline__ void panel_dot(const double *vals, const int *idx, const double *y,
+                                          int cbeg, int cend, int nr, int r0, int cg, int m, double *out)
 {
-    // vals[(c*nr + r)*MB], idx[c]: shared-memory copies (SMEM) or the global arrays
-    constexpr int CG = 32 / MB / PR, TU = KB2_TRI_U;
-    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    // vals[(c*nr + r)*MB], idx[c]: shared-memory copies (SMEM) or the global arrays.
+    // A lane accumulates its RPL rows r0 + rr*RL over the column positions of its group.
+    constexpr int LN = 32 / MB, RL = LN < PR ? LN : PR, RPL = PR / RL, CG = LN / RL, TU = KB2_TRI_U / RPL;
+    double a[RPL][2];
+#pragma unroll
+    for (int rr = 0; rr < RPL; ++rr) a[rr][0] = a[rr][1] = 0.0;
     int c = cbeg + cg;
     for (; c + (TU - 1) * CG < cend; c += TU * CG) {
         int ix[TU];
-        double lv[TU], yv[TU];
+        double lv[RPL][TU], yv[TU];
 #pragma unroll
         for (int j = 0; j < TU; ++j) ix[j] = idx[c + j * CG];
 #pragma unroll
-        for (int j = 0; j < TU; ++j) lv[j] = vals[((c + j * CG) * nr + r) * MB];
+        for (int rr = 0; rr < RPL; ++rr)
+#pragma unroll
+            for (int j = 0; j < TU; ++j) lv[rr][j] = (r0 + rr * RL < nr) ? vals[((c + j * CG) * nr + r0 + rr * RL) * MB] : 0.0;
 #pragma unroll
         for (int j = 0; j < TU; ++j) yv[j] = y[ix[j] * MB + m];
 #pragma unroll
-        for (int j = 0; j < TU; ++j) a[j & 3] += lv[j] * yv[j];
+        for (int rr = 0; rr < RPL; ++rr)
+#pragma unroll
+            for (int j = 0; j < TU; ++j) a[rr][j & 1] += lv[rr][j] * yv[j];
     }
-    for (; c < cend; c += CG) a[0] += vals[(c * nr + r) * MB] * y[idx[c] * MB + m];
-    return (a[0] + a[1]) + (a[2] + a[3]);
+    for (; c < cend; c += CG) {
+        const double yc = y[idx[c] * MB + m];
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr)
+            if (r0 + rr * RL < nr) a[rr][0] += vals[(c * nr + r0 + rr * RL) * MB] * yc;
+    }
+#pragma unroll
+    for (int rr = 0; rr < RPL; ++rr) out[rr] = a[rr][0] + a[rr][1];
 }
 
 template <int MB>
@@ -1008,13 +1040,13 @@ __device__ __forceinline__ void stage_panel_wait(const BulkChan &ch, int lane)
 template <int MB>
 __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevPlan &pl, const double *rhs, double *x, double *sm)
 {
-    constexpr int LN = 32 / MB, CG = LN / PR;
-    static_assert(CG >= 1, "at most 4 members per warp tile");
+    constexpr int LN = 32 / MB;
+    constexpr int RL = LN < PR ? LN : PR, RPL = PR / RL;     // row lanes (lane ln = cg*RL + r0), rows per lane
     constexpr int AHEAD = KB2_TRI_AHEAD;
     constexpr int CAPC = 2 * PR * PR * MB;                          // column indices (ints) at the tail of the buffer
     constexpr int CAPD = (CWMAX * PR + 2 * PR * PR) * MB;            // values (doubles)
     int *cbuf = reinterpret_cast<int *>(sm + CAPD);
-    const int m = tl.m, r = tl.ln % PR, cg = tl.ln / PR;
+    const int m = tl.m, r0 = tl.ln % RL, cg = tl.ln / RL;
     const double *lu = tl.lu;
     double *y = tl.y;
     fence_proxy_async();        // the factors were written with ordinary stores and are read with bulk copies
@@ -1025,34 +1057,48 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
         const int nr = pl.p_nrows[P], next = pl.p_next[P], p0 = pl.p_row0[P];
         const int *C = pl.cols + pl.p_cptr[P];
         const double *gP = lu + (size_t)pl.p_base[P] * MB;
-        const bool rok = r < nr;
         const int ncol = next + nr;                                  // L part and diagonal block
         const bool staged = KB2_TRISTAGE && ncol * nr * MB <= CAPD && ncol <= CAPC;
         if (staged) stage_panel_cols<MB>(tl.ch, sm, cbuf, gP, C, ncol, nr, tl.lane);
         if (AHEAD >= 0 && tl.lane == 0 && P + AHEAD < pl.npanels)
             prefetch_panel_cols<MB>(pl, lu, P + AHEAD, 0, pl.p_next[P + AHEAD] + pl.p_nrows[P + AHEAD]);
-        const double bz = rok ? rhs[net.perm[p0 + r] * MB + m] : 0.0;
-        const double dinv = rok ? tl.invd[(p0 + r) * MB + m] : 0.0;
+        double z[RPL], dinv[RPL], acc[RPL];
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int row = r0 + rr * RL;
+            z[rr] = row < nr ? rhs[net.perm[p0 + row] * MB + m] : 0.0;
+            dinv[rr] = row < nr ? tl.invd[(p0 + row) * MB + m] : 0.0;
+        }
         const double *vals = staged ? (const double *)sm + m : gP + m;
-        double acc;
         if (staged) {
             stage_panel_wait<MB>(tl.ch, tl.lane);
-            acc = rok ? panel_dot<MB, true>(vals, cbuf, y, 0, next, nr, r, cg, m) : 0.0;
+            panel_dot<MB, true>(vals, cbuf, y, 0, next, nr, r0, cg, m, acc);
         } else {
-            acc = rok ? panel_dot<MB, false>(vals, C, y, 0, next, nr, r, cg, m) : 0.0;
+            panel_dot<MB, false>(vals, C, y, 0, next, nr, r0, cg, m, acc);
         }
+        double lint[RPL][PR - 1];
 #pragma unroll
-        for (int off = 16; off >= PR * MB; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
-        double z = bz - acc;
-        double lint[PR - 1];
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int row = r0 + rr * RL;
 #pragma unroll
-        for (int a = 0; a < PR - 1; ++a) lint[a] = (rok && a < r) ? vals[((next + a) * nr + r) * MB] : 0.0;
+            for (int off = 16; off >= RL * MB; off >>= 1) acc[rr] += __shfl_xor_sync(FULL, acc[rr], off);
+            z[rr] -= acc[rr];
+#pragma unroll
+            for (int a = 0; a < PR - 1; ++a) lint[rr][a] = (row < nr && a < row) ? vals[((next + a) * nr + row) * MB] : 0.0;
+        }
 #pragma unroll
         for (int a = 0; a < PR - 1; ++a) {
-            const double yv = __shfl_sync(FULL, z * dinv, (cg * PR + a) * MB + m);   // y_a is final here
-            if (r > a) z -= lint[a] * yv;
+            const int oa = a % RL, sa = a / RL;                       // owner lane and slot of row a
+            const double yv = __shfl_sync(FULL, z[sa] * dinv[sa], (cg * RL + oa) * MB + m);   // y_a is final here
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr)
+                if (r0 + rr * RL > a) z[rr] -= lint[rr][a] * yv;
         }
-        if (cg == 0 && rok) y[(p0 + r) * MB + m] = z * dinv;
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int row = r0 + rr * RL;
+            if (cg == 0 && row < nr) y[(p0 + row) * MB + m] = z[rr] * dinv[rr];
+        }
         __syncwarp();
     }
     // ---------------- backward:  U' x = y ----------------
@@ -1064,34 +1110,48 @@ __device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevP
         const int W = pl.p_width[P], nr = pl.p_nrows[P], next = pl.p_next[P], p0 = pl.p_row0[P];
         const int *C = pl.cols + pl.p_cptr[P] + next;                // from the diagonal block on
         const double *gP = lu + ((size_t)pl.p_base[P] + (size_t)next * nr) * MB;
-        const bool rok = r < nr;
         const int ncol = W - next;                                   // diagonal block and U part
         const bool staged = KB2_TRISTAGE && ncol * nr * MB <= CAPD && ncol <= CAPC;
         if (staged) stage_panel_cols<MB>(tl.ch, sm, cbuf, gP, C, ncol, nr, tl.lane);
         if (AHEAD >= 0 && tl.lane == 0 && P - AHEAD >= 0) prefetch_panel_cols<MB>(pl, lu, P - AHEAD, pl.p_next[P - AHEAD], pl.p_width[P - AHEAD]);
-        const double yz = rok ? y[(p0 + r) * MB + m] : 0.0;
+        double z[RPL], acc[RPL];
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int row = r0 + rr * RL;
+            z[rr] = row < nr ? y[(p0 + row) * MB + m] : 0.0;
+        }
         const double *vals = staged ? (const double *)sm + m : gP + m;
-        double acc;
         if (staged) {
             stage_panel_wait<MB>(tl.ch, tl.lane);
-            acc = rok ? panel_dot<MB, true>(vals, cbuf, y, nr, ncol, nr, r, cg, m) : 0.0;
+            panel_dot<MB, true>(vals, cbuf, y, nr, ncol, nr, r0, cg, m, acc);
         } else {
-            acc = rok ? panel_dot<MB, false>(vals, C, y, nr, ncol, nr, r, cg, m) : 0.0;
+            panel_dot<MB, false>(vals, C, y, nr, ncol, nr, r0, cg, m, acc);
         }
+        double uint_[RPL][PR];
 #pragma unroll
-        for (int off = 16; off >= PR * MB; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
-        double z = yz - acc;
-        double uint_[PR];
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int row = r0 + rr * RL;
 #pragma unroll
-        for (int a = 1; a < PR; ++a) uint_[a] = (rok && a > r && a < nr) ? vals[(a * nr + r) * MB] : 0.0;
+            for (int off = 16; off >= RL * MB; off >>= 1) acc[rr] += __shfl_xor_sync(FULL, acc[rr], off);
+            z[rr] -= acc[rr];
+#pragma unroll
+            for (int a = 1; a < PR; ++a) uint_[rr][a] = (row < nr && a > row && a < nr) ? vals[(a * nr + row) * MB] : 0.0;
+        }
 #pragma unroll
         for (int a = PR - 1; a > 0; --a) {
-            const double xv = __shfl_sync(FULL, z, (cg * PR + a) * MB + m);        // U' has a unit diagonal
-            if (r < a) z -= uint_[a] * xv;
+            const int oa = a % RL, sa = a / RL;
+            const double xv = __shfl_sync(FULL, z[sa], (cg * RL + oa) * MB + m);        // U' has a unit diagonal
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr)
+                if (r0 + rr * RL < a) z[rr] -= uint_[rr][a] * xv;
         }
-        if (cg == 0 && rok) {
-            y[(p0 + r) * MB + m] = z;
-            x[net.perm[p0 + r] * MB + m] = z;
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int row = r0 + rr * RL;
+            if (cg == 0 && row < nr) {
+                y[(p0 + row) * MB + m] = z[rr];
+                x[net.perm[p0 + row] * MB + m] = z[rr];
+            }
         }
         __syncwarp();
     }

@@ -4,11 +4,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import kinetica_b200 as kb
 from kinetica_b200.synthetic import synthetic_crn, synthetic_u0, SEED_BASE
-S = 1000; R = 5000
+S = int(os.environ.get('KB2_S', '1000')); R = 5 * S
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 tf = float(sys.argv[2]) if len(sys.argv) > 2 else 0.02
 maxit = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
-sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + 3)
+sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + int(os.environ.get('KB2_CID', '3')))
 calc = kb.PrecalculatedArrheniusCalculator(Ea, A, k_max=1e12)
 pars = kb.ODESimulationParams(tspan=(0.0, tf), u0=synthetic_u0(S), save_interval=tf / 2, low_k_cutoff="none",
                               solve_chunks=False, abstol=1e-8, reltol=1e-6, maxiters=maxit)

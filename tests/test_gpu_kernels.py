@@ -117,7 +117,7 @@ def test_rhs_deterministic(small):
 
 
 @pytest.mark.parametrize("S,R,ordering,B,mb", [(96, 400, 0, 19, 0), (420, 2100, 3, 9, 1), (420, 2100, 0, 16, 4), (30, 60, 1, 3, 0),
-                                               (420, 2100, 3, 10, 2), (200, 1000, 3, 37, 4), (96, 400, 4, 8, 2)])
+                                               (420, 2100, 3, 10, 2), (200, 1000, 3, 37, 4), (96, 400, 4, 8, 2), (420, 2100, 3, 19, 8), (96, 400, 0, 16, 8)])
 def test_factor_and_trisolve_panels(built, S, R, ordering, B, mb):
     """Panel LU + panel triangular solves on networks whose hub rows span several column chunks
     (S = 420: widest panel > 3 chunks), for every ordering mode and ragged member counts."""
@@ -128,7 +128,7 @@ def test_factor_and_trisolve_panels(built, S, R, ordering, B, mb):
     h = _lib.Handle(0)
     h.set_network(S, *rd.flatten())
     h.symbolic(ordering)
-    h.set_tiling(mb)        # members per warp tile: 0 auto (1 for these small ensembles), 1, 2, 4
+    h.set_tiling(mb)        # members per warp tile: 0 auto (1 for these small ensembles), 1, 2, 4, 8
     st = h.get_plan_stats()
     if S == 420:
         assert st["max_width"] > 96 and st["units"] > st["panels"]

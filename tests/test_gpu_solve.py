@@ -113,9 +113,9 @@ def test_ensemble_vs_c_oracle(ensemble_case):
         assert np.array_equal(o.umax, np.max(np.array(o.sol.u), axis=0))
 
 
-@pytest.mark.parametrize("mb", [2, 4])
+@pytest.mark.parametrize("mb", [2, 4, 8])
 def test_tile_sizes_agree(ensemble_case, monkeypatch, mb):
-    """The ensemble solved with 2 and 4 members per warp tile (the sizes large ensembles run at;
+    """The ensemble solved with 2, 4 and 8 members per warp tile (the sizes large ensembles run at;
     this small one defaults to 1) against the 1-member-per-tile solution, ragged last tile included."""
     import kinetica_b200 as kb
     from kinetica_b200.synthetic import synthetic_u0
