@@ -45,7 +45,8 @@ struct kb2_ctx {
     DevEns de{};
     int64_t ens_B = -1, ens_Ns = -1;
     size_t ens_fixed = 0;
-    int *d_counter = nullptr;
+    int *d_counter = nullptr;   // [0] tile counter of the solve, [1..2] arrival count and generation word of its alignment barrier
+    bool coop_ok = false;
     int mb_user = 0, last_ctas_per_sm = 0;
     int ens_mb = 0;               // members per warp tile of the current ensemble allocation
     double *stage = nullptr;      // device staging for layout conversion (caller rows <-> tiles)
@@ -105,10 +106,11 @@ extern "C" int32_t kb2_create(int32_t device, kb2_handle *out)
     cudaGetDeviceProperties(&prop, device);
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->coop_ok = prop.cooperativeLaunch != 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return 3; }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
-    cudaMalloc((void **)&h->d_counter, sizeof(int));
+    cudaMalloc((void **)&h->d_counter, 8 * sizeof(int));
     *out = h;
     return 0;
 }
@@ -832,7 +834,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
     const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr) + 16;
-    CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
+    CU(h, cudaMemsetAsync(h->d_counter, 0, 8 * sizeof(int), h->stream));
     CU(h, cudaEventRecord(h->ev0, h->stream));
     DISPATCH_MB(e.MB, {
         int r = set_smem(h, k_solve<MB>, smem);
@@ -842,8 +844,24 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
         if (per_sm < 1) FAIL(h, "solve kernel does not fit on an SM");
         h->last_ctas_per_sm = per_sm;
         // persistent warps: every resident slot pulls tiles from an atomic counter
-        const int grid = std::min(ntiles, per_sm * h->sm_count);
-        k_solve<MB><<<grid, 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles, h->d_counter, (int)smem - 16);
+        int grid = std::min(ntiles, per_sm * h->sm_count);
+        // phase alignment (kb2_solve.cuh, grid_align): every attempted step starts behind a
+        // grid-wide barrier, so the warps of an SM stay in the same phase of the step.  The
+        // barrier needs every CTA resident at once: cooperative launch (fails instead of hanging).
+        int align = 1;
+        if (const char *ev = getenv("KB2_ALIGN")) align = atoi(ev);
+        if (!h->coop_ok) align = 0;
+        int data_bytes = (int)smem - 16;
+        int *ctr = h->d_counter;
+        DevNet dn = h->dn; DevPlan dp = h->dp; DevEns de = e;
+        int nt = ntiles;
+        void *args[] = {&dn, &dp, &de, &nt, &ctr, &data_bytes, &align};
+        if (align) {
+            cudaError_t ce = cudaLaunchCooperativeKernel((const void *)k_solve<MB>, dim3(grid), dim3(32), args, smem, h->stream);
+            if (ce != cudaSuccess) FAIL(h, cudaGetErrorString(ce));
+        } else {
+            k_solve<MB><<<grid, 32, smem, h->stream>>>(dn, dp, de, nt, ctr, data_bytes, 0);
+        }
     });
     h->launches++;
     CU(h, cudaEventRecord(h->ev1, h->stream));

@@ -176,20 +176,14 @@ __device__ inline double profile_eval(int kind, const double *p, double t)
 // ---------------------------------------------------------------------------------------------
 // Warp-tile primitives.
 // ---------------------------------------------------------------------------------------------
-#ifndef KB2_TRISTAGE
-#define KB2_TRISTAGE 0        // 1: stage the panels of the sweeps in shared memory (faster stand-alone, slower inside the fused solve)
-#endif
 #ifndef KB2_LU_PREFETCH
 #define KB2_LU_PREFETCH 1     // U' values of the next source block are loaded while the current one is applied
 #endif
 #ifndef KB2_CHUNK_BULK
 #define KB2_CHUNK_BULK 1      // panel chunks go to shared memory with one bulk copy
 #endif
-#ifndef KB2_TRI_U
-#define KB2_TRI_U 8            // column positions per lane in flight in the triangular sweeps
-#endif
 #ifndef KB2_TRI_AHEAD
-#define KB2_TRI_AHEAD 0        // panels pulled towards L2 ahead of the sweep (0: the panel about to be read; -1: none)
+#define KB2_TRI_AHEAD 0        // >= 0: the panel two links ahead of the sweep is pulled into L2 with a bulk prefetch; -1: off
 #endif
 #ifndef KB2_LU_L2PF
 #define KB2_LU_L2PF 1         // bulk L2 prefetch of the next unit's chunk and target spans
@@ -959,201 +953,213 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
     }
 }
 
-// K5: W x = rhs over the block storage.  rhs, x in species order; y = permuted scratch.
-// Lane ln = cg*8 + r: row r of the panel, column group cg of LN/8; one column position of a
-// panel is MB*8 consecutive doubles.  A sweep is a chain over the panels, so what counts is the
-// latency of one link: the columns a panel needs (values and column indices) are copied into
-// shared memory with one burst of cp.async — every byte of the panel in flight at once — after
-// the panel two links ahead has been pulled into L2 with a bulk prefetch; a panel too wide for
-// the buffer (hub rows) is read straight from global memory, eight positions per lane in flight.
-template <int MB, bool SMEM>
-__device__ __forceinline__ void panel_dot(const double *vals, const int *idx, const double *y,
-                                          int cbeg, int cend, int nr, int r0, int cg, int m, double *out)
+// K5: W x = rhs over the block storage.  rhs, x in species order; y = the permuted intermediate.
+// A sweep is a chain over the panels, so what counts is the latency of one link.  Everything a
+// link needs that does not depend on the previous link is loaded ahead of it:
+//   * the permuted vector y lives in the warp's shared memory for both sweeps (when S*MB doubles
+//     fit; the factorisation is done with the buffer by then), so the only data-dependent loads of
+//     the chain are shared-memory reads;
+//   * during the dot products every lane of a member is a COLUMN lane: it owns the columns
+//     cb + ln, cb + ln + LN, ... of the panel and accumulates all eight rows (one index load and
+//     one y read per column instead of one per row, the eight values of a column at immediate
+//     offsets), then a reduce-scatter hands row r to lane r for the in-panel substitution;
+//   * the first batch of columns of the NEXT panel, its right-hand side, pivots and diagonal block
+//     are loaded into registers before the substitution chain of the current panel starts, the
+//     panel after that is pulled into L2 with one bulk prefetch, panel records are three deep.
+struct PanelMeta { int nr, next, p0, cptr, base, width; };
+__device__ __forceinline__ PanelMeta load_pm(const DevPlan &pl, int P)
 {
-    // vals[(c*nr + r)*MB], idx[c]: shared-memory copies (SMEM) or the global arrays.
-    // A lane accumulates its RPL rows r0 + rr*RL over the column positions of its group.
-    constexpr int LN = 32 / MB, RL = LN < PR ? LN : PR, RPL = PR / RL, CG = LN / RL, TU = KB2_TRI_U / RPL;
-    double a[RPL][2];
+    PanelMeta q;
+    const bool ok = P >= 0 && P < pl.npanels;
+    const int Pc = ok ? P : 0;
+    q.nr = ok ? pl.p_nrows[Pc] : 0;
+    q.next = ok ? pl.p_next[Pc] : 0;
+    q.p0 = ok ? pl.p_row0[Pc] : 0;
+    q.cptr = ok ? pl.p_cptr[Pc] : 0;
+    q.base = ok ? pl.p_base[Pc] : 0;
+    q.width = ok ? pl.p_width[Pc] : 0;
+    return q;
+}
+
+// acc[r] = partial sum of row r on every lane of a member -> out[rr] = total of row
+// (ln % RL) + rr*RL.  Column-group bits (LN > 8) are folded with a butterfly, the row-lane bits
+// with a reduce-scatter: at the level of bit hb a lane keeps the rows whose bit hb equals its own
+// and sends the others to its partner.  Fixed order, deterministic.
+template <int MB>
+__device__ __forceinline__ void rows_reduce(double (&acc)[PR], int ln, double (&out)[PR / ((32 / MB) < PR ? (32 / MB) : PR)])
+{
+    constexpr int LN = 32 / MB, RL = LN < PR ? LN : PR, RPL = PR / RL;
 #pragma unroll
-    for (int rr = 0; rr < RPL; ++rr) a[rr][0] = a[rr][1] = 0.0;
-    int c = cbeg + cg;
-    for (; c + (TU - 1) * CG < cend; c += TU * CG) {
-        int ix[TU];
-        double lv[RPL][TU], yv[TU];
+    for (int off = 16; off >= RL * MB; off >>= 1)
 #pragma unroll
-        for (int j = 0; j < TU; ++j) ix[j] = idx[c + j * CG];
+        for (int r = 0; r < PR; ++r) acc[r] += __shfl_xor_sync(FULL, acc[r], off);
 #pragma unroll
-        for (int rr = 0; rr < RPL; ++rr)
+    for (int hb = RL / 2; hb >= 1; hb >>= 1) {
+        const bool up = (ln & hb) != 0;
+        const int done = (RL - 1) & ~(2 * hb - 1);      // row bits already scattered
 #pragma unroll
-            for (int j = 0; j < TU; ++j) lv[rr][j] = (r0 + rr * RL < nr) ? vals[((c + j * CG) * nr + r0 + rr * RL) * MB] : 0.0;
-#pragma unroll
-        for (int j = 0; j < TU; ++j) yv[j] = y[ix[j] * MB + m];
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr)
-#pragma unroll
-            for (int j = 0; j < TU; ++j) a[rr][j & 1] += lv[rr][j] * yv[j];
+        for (int r = 0; r < PR; ++r) {
+            if ((r & hb) == 0 && (r & done) == 0) {
+                const double send = up ? acc[r] : acc[r | hb];
+                const double keep = up ? acc[r | hb] : acc[r];
+                acc[r] = keep + __shfl_xor_sync(FULL, send, hb * MB);
+            }
+        }
     }
-    for (; c < cend; c += CG) {
-        const double yc = y[idx[c] * MB + m];
 #pragma unroll
-        for (int rr = 0; rr < RPL; ++rr)
-            if (r0 + rr * RL < nr) a[rr][0] += vals[(c * nr + r0 + rr * RL) * MB] * yc;
-    }
-#pragma unroll
-    for (int rr = 0; rr < RPL; ++rr) out[rr] = a[rr][0] + a[rr][1];
+    for (int rr = 0; rr < RPL; ++rr) out[rr] = acc[rr * RL];
 }
 
-template <int MB>
-__device__ __forceinline__ void prefetch_panel_cols(const DevPlan &pl, const double *lu, int P, int c0, int c1)
-{
-    const int nr = pl.p_nrows[P];
-    const size_t a = (size_t)(lu + ((size_t)pl.p_base[P] + (size_t)c0 * nr) * MB);
-    const size_t nbytes = (size_t)(c1 - c0) * nr * MB * 8;
-    const size_t a16 = a & ~(size_t)15;
-    prefetch_l2_bulk((const void *)a16, (unsigned)((a + nbytes - a16) & ~(size_t)15));
-}
+#ifndef KB2_TRI_TU
+#define KB2_TRI_TU 4           // columns per lane in one batch of a sweep (LN*TU columns per batch)
+#endif
 
-// columns [c0, c1) of panel P -> shared memory: the values with one bulk copy (or cp.async when
-// the warp has no copy-engine channel), the column indices with cp.async
-template <int MB>
-__device__ __forceinline__ void stage_panel_cols(const BulkChan &ch, double *buf, int *cbuf, const double *gsrc, const int *csrc,
-                                                 int ncol, int nr, int lane)
+template <int MB, bool YS, bool FWD>
+__device__ __forceinline__ void tri_sweep(const WTile<MB> &tl, const DevNet &net, const DevPlan &pl, const double *rhs, double *x, double *y)
 {
-    const int n = ncol * nr * MB;
-    if (ch.bar) {
-        bulk_issue(ch, buf, gsrc, (unsigned)(n * 8), lane, false);
-    } else {
-        for (int i = lane; i < n; i += 32) cp_async8(buf + i, gsrc + i);
-    }
-    for (int i = lane; i < ncol; i += 32) cp_async4(cbuf + i, csrc + i);
-    cp_async_commit();
-}
-
-template <int MB>
-__device__ __forceinline__ void stage_panel_wait(const BulkChan &ch, int lane)
-{
-    cp_async_wait_all();
-    if (ch.bar) bulk_wait(ch, lane);
-    else __syncwarp();
-}
-
-template <int MB>
-__device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevPlan &pl, const double *rhs, double *x, double *sm)
-{
-    constexpr int LN = 32 / MB;
-    constexpr int RL = LN < PR ? LN : PR, RPL = PR / RL;     // row lanes (lane ln = cg*RL + r0), rows per lane
-    constexpr int AHEAD = KB2_TRI_AHEAD;
-    constexpr int CAPC = 2 * PR * PR * MB;                          // column indices (ints) at the tail of the buffer
-    constexpr int CAPD = (CWMAX * PR + 2 * PR * PR) * MB;            // values (doubles)
-    int *cbuf = reinterpret_cast<int *>(sm + CAPD);
-    const int m = tl.m, r0 = tl.ln % RL, cg = tl.ln / RL;
-    const double *lu = tl.lu;
-    double *y = tl.y;
-    fence_proxy_async();        // the factors were written with ordinary stores and are read with bulk copies
-    __syncwarp();
-    // ---------------- forward:  L' y = P rhs ----------------
-    if (AHEAD > 0 && tl.lane < AHEAD && tl.lane < pl.npanels) prefetch_panel_cols<MB>(pl, lu, tl.lane, 0, pl.p_next[tl.lane] + pl.p_nrows[tl.lane]);
-    for (int P = 0; P < pl.npanels; ++P) {
-        const int nr = pl.p_nrows[P], next = pl.p_next[P], p0 = pl.p_row0[P];
-        const int *C = pl.cols + pl.p_cptr[P];
-        const double *gP = lu + (size_t)pl.p_base[P] * MB;
-        const int ncol = next + nr;                                  // L part and diagonal block
-        const bool staged = KB2_TRISTAGE && ncol * nr * MB <= CAPD && ncol <= CAPC;
-        if (staged) stage_panel_cols<MB>(tl.ch, sm, cbuf, gP, C, ncol, nr, tl.lane);
-        if (AHEAD >= 0 && tl.lane == 0 && P + AHEAD < pl.npanels)
-            prefetch_panel_cols<MB>(pl, lu, P + AHEAD, 0, pl.p_next[P + AHEAD] + pl.p_nrows[P + AHEAD]);
-        double z[RPL], dinv[RPL], acc[RPL];
+    constexpr int LN = 32 / MB, RL = LN < PR ? LN : PR, RPL = PR / RL, TU = KB2_TRI_TU;
+    const int m = tl.m, ln = tl.ln, r0 = ln % RL, cg = ln / RL;
+    const double *lu = tl.lu + m;
+    const int Pbeg = FWD ? 0 : pl.npanels - 1, dP = FWD ? 1 : -1;
+    int ix[TU];
+    double lv[TU][PR];
+    double z[RPL], dinv[RPL], tri[RPL][PR - 1];
+    int prm[RPL], nprm[RPL];
+    auto col_begin = [&](const PanelMeta &q) { return FWD ? 0 : q.next + q.nr; };
+    auto col_end = [&](const PanelMeta &q) { return FWD ? q.next : q.width; };
+    auto load_perm = [&](const PanelMeta &q, int (&p)[RPL]) {
 #pragma unroll
         for (int rr = 0; rr < RPL; ++rr) {
             const int row = r0 + rr * RL;
-            z[rr] = row < nr ? rhs[net.perm[p0 + row] * MB + m] : 0.0;
-            dinv[rr] = row < nr ? tl.invd[(p0 + row) * MB + m] : 0.0;
+            p[rr] = row < q.nr ? net.perm[q.p0 + row] : 0;
         }
-        const double *vals = staged ? (const double *)sm + m : gP + m;
-        if (staged) {
-            stage_panel_wait<MB>(tl.ch, tl.lane);
-            panel_dot<MB, true>(vals, cbuf, y, 0, next, nr, r0, cg, m, acc);
+    };
+    // one batch: columns c0 + j*LN (c0 already includes the lane's offset), all eight rows of each
+    auto load_batch = [&](const PanelMeta &q, int c0, int ce) {
+#pragma unroll
+        for (int j = 0; j < TU; ++j) {
+            const int c = c0 + j * LN;
+            const bool ok = c < ce;
+            ix[j] = ok ? pl.cols[q.cptr + c] : 0;
+            const double *vp = lu + (q.base + c * q.nr) * MB;
+#pragma unroll
+            for (int r = 0; r < PR; ++r) lv[j][r] = (ok && r < q.nr) ? vp[r * MB] : 0.0;
+        }
+    };
+    auto consume = [&](int c0, int ce, double (&acc)[PR]) {
+        double yv[TU];
+#pragma unroll
+        for (int j = 0; j < TU; ++j) yv[j] = (c0 + j * LN < ce) ? y[ix[j] * MB + m] : 0.0;
+#pragma unroll
+        for (int j = 0; j < TU; ++j)
+#pragma unroll
+            for (int r = 0; r < PR; ++r) acc[r] += lv[j][r] * yv[j];
+    };
+    // everything of panel q that does not depend on the panels before it
+    auto preload = [&](const PanelMeta &q, const int (&p)[RPL]) {
+        load_batch(q, col_begin(q) + ln, col_end(q));
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int row = r0 + rr * RL;
+            const bool ok = row < q.nr;
+            const double *dp = lu + (q.base + q.next * q.nr + row) * MB;      // row `row` of the diagonal block
+            if (FWD) {
+                z[rr] = ok ? rhs[p[rr] * MB + m] : 0.0;
+                dinv[rr] = ok ? tl.invd[(q.p0 + row) * MB + m] : 0.0;
+#pragma unroll
+                for (int a = 0; a < PR - 1; ++a) tri[rr][a] = (ok && a < row) ? dp[a * q.nr * MB] : 0.0;
+            } else {
+                z[rr] = ok ? y[(q.p0 + row) * MB + m] : 0.0;
+                dinv[rr] = 0.0;
+#pragma unroll
+                for (int a = 1; a < PR; ++a) tri[rr][a - 1] = (ok && a > row && a < q.nr) ? dp[a * q.nr * MB] : 0.0;
+            }
+        }
+    };
+    PanelMeta cur = load_pm(pl, Pbeg), nxt = load_pm(pl, Pbeg + dP), nn = load_pm(pl, Pbeg + 2 * dP);
+    load_perm(cur, prm);
+    preload(cur, prm);
+    for (int P = Pbeg; FWD ? P < pl.npanels : P >= 0; P += dP) {
+        const PanelMeta pm = cur;
+        load_perm(nxt, nprm);
+        if (KB2_TRI_AHEAD >= 0 && tl.lane == 0 && col_end(nn) > col_begin(nn)) {
+            const size_t a = (size_t)(tl.lu + (size_t)(nn.base + col_begin(nn) * nn.nr) * MB);
+            const size_t nbytes = (size_t)(col_end(nn) - col_begin(nn)) * nn.nr * MB * 8;
+            const size_t a16 = a & ~(size_t)15;
+            prefetch_l2_bulk((const void *)a16, (unsigned)((a + nbytes - a16) & ~(size_t)15));
+        }
+        double acc[PR];
+#pragma unroll
+        for (int r = 0; r < PR; ++r) acc[r] = 0.0;
+        const int cb = col_begin(pm), ce = col_end(pm);
+        consume(cb + ln, ce, acc);
+        for (int cc = cb + LN * TU; cc < ce; cc += LN * TU) {       // wide panels: further batches on demand
+            load_batch(pm, cc + ln, ce);
+            consume(cc + ln, ce, acc);
+        }
+        // the finish of this panel keeps its own copies; the registers of the batch are free again
+        double cz[RPL], cdinv[RPL], ctri[RPL][PR - 1];
+        int cprm[RPL];
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+            cz[rr] = z[rr]; cdinv[rr] = dinv[rr]; cprm[rr] = prm[rr]; prm[rr] = nprm[rr];
+#pragma unroll
+            for (int a = 0; a < PR - 1; ++a) ctri[rr][a] = tri[rr][a];
+        }
+        cur = nxt; nxt = nn; nn = load_pm(pl, P + 3 * dP);
+        preload(cur, prm);
+        // ---- finish panel P: row totals, in-panel substitution with shuffles ----
+        double tot[RPL];
+        rows_reduce<MB>(acc, ln, tot);
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) cz[rr] -= tot[rr];
+        if (FWD) {
+#pragma unroll
+            for (int a = 0; a < PR - 1; ++a) {
+                const int oa = a % RL, sa = a / RL;                       // owner lane and slot of row a
+                const double yv = __shfl_sync(FULL, cz[sa] * cdinv[sa], (cg * RL + oa) * MB + m);   // y_a is final here
+#pragma unroll
+                for (int rr = 0; rr < RPL; ++rr)
+                    if (r0 + rr * RL > a) cz[rr] -= ctri[rr][a] * yv;
+            }
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr) {
+                const int row = r0 + rr * RL;
+                if (cg == 0 && row < pm.nr) y[(pm.p0 + row) * MB + m] = cz[rr] * cdinv[rr];
+            }
         } else {
-            panel_dot<MB, false>(vals, C, y, 0, next, nr, r0, cg, m, acc);
-        }
-        double lint[RPL][PR - 1];
 #pragma unroll
-        for (int rr = 0; rr < RPL; ++rr) {
-            const int row = r0 + rr * RL;
+            for (int a = PR - 1; a > 0; --a) {
+                const int oa = a % RL, sa = a / RL;
+                const double xv = __shfl_sync(FULL, cz[sa], (cg * RL + oa) * MB + m);        // U' has a unit diagonal
 #pragma unroll
-            for (int off = 16; off >= RL * MB; off >>= 1) acc[rr] += __shfl_xor_sync(FULL, acc[rr], off);
-            z[rr] -= acc[rr];
+                for (int rr = 0; rr < RPL; ++rr)
+                    if (r0 + rr * RL < a) cz[rr] -= ctri[rr][a - 1] * xv;
+            }
 #pragma unroll
-            for (int a = 0; a < PR - 1; ++a) lint[rr][a] = (row < nr && a < row) ? vals[((next + a) * nr + row) * MB] : 0.0;
-        }
-#pragma unroll
-        for (int a = 0; a < PR - 1; ++a) {
-            const int oa = a % RL, sa = a / RL;                       // owner lane and slot of row a
-            const double yv = __shfl_sync(FULL, z[sa] * dinv[sa], (cg * RL + oa) * MB + m);   // y_a is final here
-#pragma unroll
-            for (int rr = 0; rr < RPL; ++rr)
-                if (r0 + rr * RL > a) z[rr] -= lint[rr][a] * yv;
-        }
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr) {
-            const int row = r0 + rr * RL;
-            if (cg == 0 && row < nr) y[(p0 + row) * MB + m] = z[rr] * dinv[rr];
-        }
-        __syncwarp();
-    }
-    // ---------------- backward:  U' x = y ----------------
-    if (AHEAD > 0 && tl.lane < AHEAD && tl.lane < pl.npanels) {
-        const int P = pl.npanels - 1 - tl.lane;
-        prefetch_panel_cols<MB>(pl, lu, P, pl.p_next[P], pl.p_width[P]);
-    }
-    for (int P = pl.npanels - 1; P >= 0; --P) {
-        const int W = pl.p_width[P], nr = pl.p_nrows[P], next = pl.p_next[P], p0 = pl.p_row0[P];
-        const int *C = pl.cols + pl.p_cptr[P] + next;                // from the diagonal block on
-        const double *gP = lu + ((size_t)pl.p_base[P] + (size_t)next * nr) * MB;
-        const int ncol = W - next;                                   // diagonal block and U part
-        const bool staged = KB2_TRISTAGE && ncol * nr * MB <= CAPD && ncol <= CAPC;
-        if (staged) stage_panel_cols<MB>(tl.ch, sm, cbuf, gP, C, ncol, nr, tl.lane);
-        if (AHEAD >= 0 && tl.lane == 0 && P - AHEAD >= 0) prefetch_panel_cols<MB>(pl, lu, P - AHEAD, pl.p_next[P - AHEAD], pl.p_width[P - AHEAD]);
-        double z[RPL], acc[RPL];
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr) {
-            const int row = r0 + rr * RL;
-            z[rr] = row < nr ? y[(p0 + row) * MB + m] : 0.0;
-        }
-        const double *vals = staged ? (const double *)sm + m : gP + m;
-        if (staged) {
-            stage_panel_wait<MB>(tl.ch, tl.lane);
-            panel_dot<MB, true>(vals, cbuf, y, nr, ncol, nr, r0, cg, m, acc);
-        } else {
-            panel_dot<MB, false>(vals, C, y, nr, ncol, nr, r0, cg, m, acc);
-        }
-        double uint_[RPL][PR];
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr) {
-            const int row = r0 + rr * RL;
-#pragma unroll
-            for (int off = 16; off >= RL * MB; off >>= 1) acc[rr] += __shfl_xor_sync(FULL, acc[rr], off);
-            z[rr] -= acc[rr];
-#pragma unroll
-            for (int a = 1; a < PR; ++a) uint_[rr][a] = (row < nr && a > row && a < nr) ? vals[(a * nr + row) * MB] : 0.0;
-        }
-#pragma unroll
-        for (int a = PR - 1; a > 0; --a) {
-            const int oa = a % RL, sa = a / RL;
-            const double xv = __shfl_sync(FULL, z[sa], (cg * RL + oa) * MB + m);        // U' has a unit diagonal
-#pragma unroll
-            for (int rr = 0; rr < RPL; ++rr)
-                if (r0 + rr * RL < a) z[rr] -= uint_[rr][a] * xv;
-        }
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr) {
-            const int row = r0 + rr * RL;
-            if (cg == 0 && row < nr) {
-                y[(p0 + row) * MB + m] = z[rr];
-                x[net.perm[p0 + row] * MB + m] = z[rr];
+            for (int rr = 0; rr < RPL; ++rr) {
+                const int row = r0 + rr * RL;
+                if (cg == 0 && row < pm.nr) {
+                    y[(pm.p0 + row) * MB + m] = cz[rr];
+                    x[cprm[rr] * MB + m] = cz[rr];
+                }
             }
         }
         __syncwarp();
+    }
+}
+
+// ys: the warp's shared memory if S*MB doubles fit there (en.u_smem), else null (y stays in HBM)
+template <int MB>
+__device__ void tile_trisolve(const WTile<MB> &tl, const DevNet &net, const DevPlan &pl, const double *rhs, double *x, double *ys)
+{
+    __syncwarp();
+    if (ys) {
+        tri_sweep<MB, true, true>(tl, net, pl, rhs, x, ys);       // forward:  L' y = P rhs
+        tri_sweep<MB, true, false>(tl, net, pl, rhs, x, ys);      // backward: U' x = y
+    } else {
+        tri_sweep<MB, false, true>(tl, net, pl, rhs, x, tl.y);
+        tri_sweep<MB, false, false>(tl, net, pl, rhs, x, tl.y);
     }
 }
 

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(32) k_trisolve(DevNet net, DevPlan pl, DevEns 
     const BulkChan ch = chan_setup<MB>(smem, data_bytes);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en, ch);
-        tile_trisolve(tl, net, pl, tl.rv, tl.ua, smem);
+        tile_trisolve(tl, net, pl, tl.rv, tl.ua, en.u_smem ? smem : nullptr);
     }
 }
 
@@ -220,8 +220,48 @@ __device__ void tile_restart_h(const WTile<MB> &tl, const DevNet &net, const Dev
     if (upd && c.hfirst > 0.0) c.h = fmin(c.h, c.hfirst);
 }
 
+// Phase alignment.  All warps run the same sequence of phases per attempted step (assembly,
+// factorisation, six stage evaluations + sweeps), each with its own code (the factorisation alone
+// is larger than the 32 KB L1.5 instruction cache) and its own arrays.  Left alone, the seven
+// warps of an SM drift into seven different phases and thrash the instruction cache and the TLB:
+// measured on C3, the step cost grows from 33 ms (first steps, still aligned) to ~60 ms.  A
+// grid-wide barrier in front of every attempted step keeps them together.  A warp that has run
+// out of tiles keeps arriving until every warp has (the releasing warp publishes that in bit 0 of
+// the generation word, so that all warps take the same decision).  bar[0] = arrivals,
+// bar[1] = generation << 1 | all done; `done` = warps without work, counted once each.
+struct GridAlign {
+    unsigned *bar;      // null: alignment off
+    unsigned nctas;
+    int mode;           // 1: one barrier per attempted step; 2: one more in front of every stage
+};
+__device__ __forceinline__ bool grid_align(const GridAlign &ga, bool finished)
+{
+    if (!ga.bar) return finished;
+    unsigned word = 0;
+    if ((threadIdx.x & 31) == 0) {
+        volatile unsigned *vb = ga.bar;
+        const unsigned g = vb[1];
+        if (finished) atomicAdd(ga.bar + 2, 1u);
+        __threadfence();
+        if (atomicAdd(ga.bar, 1u) == ga.nctas - 1) {
+            // last to arrive: everybody's `done` increments of this round are visible here
+            const unsigned alldone = (vb[2] >= ga.nctas) ? 1u : 0u;
+            vb[2] = 0;                       // recounted every round: finished warps re-announce themselves
+            vb[0] = 0;
+            __threadfence();
+            word = ((g >> 1) + 1) << 1 | alldone;
+            vb[1] = word;
+        } else {
+            while ((word = vb[1]) == g) __nanosleep(200);
+        }
+        __threadfence();
+    }
+    word = __shfl_sync(FULL, word, 0);
+    return (word & 1u) != 0;
+}
+
 template <int MB>
-__device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en, double *Wp, const BulkChan &ch)
+__device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en, double *Wp, const BulkChan &ch, const GridAlign &ga)
 {
     constexpr int LN = 32 / MB;
     WTile<MB> tl(tile, net, pl, en, ch);
@@ -259,6 +299,7 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
             c.active = act; c.hs = hs; c.hit = hit; c.accept = 0;
         }
         if (!__any_sync(FULL, c.active)) break;
+        grid_align(ga, false);
         const double hs = c.hs;
         tile_assemble_w(tl, net, pl, tl.u, 1.0 / (hs * kGamma), su);
         {
@@ -288,9 +329,10 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
                 Us = tl.ua;
             }
             const double ih = 1.0 / hs;
+            if (ga.mode >= 2) grid_align(ga, false);
             tile_rhs(tl, net, Us, tl.rv, s, cC[s][0] * ih, cC[s][1] * ih, cC[s][2] * ih, cC[s][3] * ih, cC[s][4] * ih, su);
             double *Ks = s == 0 ? tl.K[0] : s == 1 ? tl.K[1] : s == 2 ? tl.K[2] : s == 3 ? tl.K[3] : s == 4 ? tl.K[4] : tl.K[5];
-            tile_trisolve(tl, net, pl, tl.rv, Ks, Wp);
+            tile_trisolve(tl, net, pl, tl.rv, Ks, su);
         }
         // error estimate = K6; new solution = ua + K6
         double e2 = 0.0;
@@ -353,17 +395,24 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
 #define KB2_MINB2 1           // minimum resident warps per SM requested for the MB = 2 instantiation of k_solve
 #endif
 template <int MB>
-__global__ void __launch_bounds__(32, MB == 2 ? KB2_MINB2 : 1) k_solve(DevNet net, DevPlan pl, DevEns en, int ntiles, int *tile_counter, int data_bytes)
+__global__ void __launch_bounds__(32, MB == 2 ? KB2_MINB2 : 1) k_solve(DevNet net, DevPlan pl, DevEns en, int ntiles, int *tile_counter, int data_bytes, int align)
 {
     extern __shared__ double smem[];
     const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    GridAlign ga;
+    ga.bar = align ? reinterpret_cast<unsigned *>(tile_counter) + 1 : nullptr;
+    ga.nctas = gridDim.x;
+    ga.mode = align;
     for (;;) {
         int tile = 0;
         if ((threadIdx.x & 31) == 0) tile = atomicAdd(tile_counter, 1);
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= ntiles) break;
-        solve_tile<MB>(tile, net, pl, en, smem, ch);
+        solve_tile<MB>(tile, net, pl, en, smem, ch, ga);
     }
+    // out of tiles: keep the barrier complete until every warp is
+    if (ga.bar)
+        while (!grid_align(ga, true)) { }
 }
 
 }  // namespace kb2
