@@ -203,6 +203,9 @@ static int upload_network(kb2_ctx *h)
     rc |= dev_upload(h, P, s.rhs_order.data(), s.rhs_order.size(), &d.rhs_order);
     rc |= dev_upload(h, P, s.j_order.data(), s.j_order.size(), &d.j_order);
     d.rhs_nlong = s.rhs_nlong; d.j_nlong = s.j_nlong;
+    rc |= dev_upload(h, P, s.ell_ptr.data(), s.ell_ptr.size(), &d.ell_ptr);
+    rc |= dev_upload(h, P, s.ell.data(), s.ell.size(), &d.ell);
+    d.ell_ngroups = (int)s.ell_ptr.size() - 1;
     rc |= dev_upload(h, P, pp.jslot.data(), pp.jslot.size(), &d.jslot);
     rc |= dev_upload(h, P, pp.diag_slot.data(), pp.diag_slot.size(), &d.diag_slot);
     rc |= dev_upload(h, P, perm32.data(), perm32.size(), &d.perm);

@@ -66,6 +66,10 @@ struct Symbolic {
     static constexpr int RHS_LONG = 64, JAC_LONG = 16;
     std::vector<int32_t> rhs_order, j_order;
     int32_t rhs_nlong = 0, j_nlong = 0;
+    // sliced ELL of the one-per-lane RHS rows (groups of ELL_G rows of rhs_order after the long ones):
+    // ell[ell_ptr[g] + t*ELL_G + rho] = coef << 24 | reaction
+    static constexpr int ELL_G = 64;
+    std::vector<int32_t> ell_ptr, ell;
     // reaction descriptors: up to 3 distinct reactant species + exponents packed 8 bit each
     std::vector<int32_t> rdesc;                       // 4 ints per reaction
     // Jacobian terms by J entry (CSC order): (reaction, (coef*nu_l) << 2 | reactant slot)

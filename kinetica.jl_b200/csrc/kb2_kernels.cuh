@@ -46,6 +46,8 @@ struct DevNet {
     const int *jt_ptr, *jt_rxn, *jt_pack;
     const int *rhs_order, *j_order;        // work orders, longest first; the first n_long are split across lanes
     int rhs_nlong, j_nlong;
+    const int *ell_ptr, *ell;              // sliced ELL of the one-per-lane RHS rows: ell[ell_ptr[g] + t*64 + slot] = coef << 24 | reaction
+    int ell_ngroups;
     const int *jslot, *diag_slot, *perm;   // storage slot of every Jacobian entry / pivot; perm[a] = species at pivot a
     // calculator
     int calc_mode;            // 0 Arrhenius, 1 rate table
@@ -99,22 +101,32 @@ __device__ __forceinline__ double pw(double x, int e)
     return r;
 }
 
+// x^e for e in 0..3 without branches: three selects and two multiplications
+__device__ __forceinline__ double pw3(double x, int e)
+{
+    const double a = e >= 1 ? x : 1.0, b = e >= 2 ? x : 1.0, c = e >= 3 ? x : 1.0;
+    return (a * b) * c;
+}
+
 // rate_j = k_j * prod_m u_m^nu_mj  (Catalyst mass action, combinatoric_ratelaws=false;
 // reference src/solving/solve_utils.jl:318-334).  Branch-free: an absent reactant slot reads
-// species 0 with exponent 0, so the three gathers of a reaction are always issued together.
+// species 0 with exponent 0 (its byte of d.w is 0), so the three gathers of a reaction are always
+// issued together; exponents above 3 take the general (rare) path.
 __device__ __forceinline__ double rate_of(const int4 d, const double *u, int MB, int m, double kj)
 {
     const double x0 = u[max(d.x, 0) * MB + m], x1 = u[max(d.y, 0) * MB + m], x2 = u[max(d.z, 0) * MB + m];
-    return kj * pw(x0, d.x >= 0 ? (d.w & 255) : 0) * pw(x1, d.y >= 0 ? ((d.w >> 8) & 255) : 0) *
-           pw(x2, d.z >= 0 ? ((d.w >> 16) & 255) : 0);
+    const int e0 = d.w & 255, e1 = (d.w >> 8) & 255, e2 = (d.w >> 16) & 255;
+    if (d.w & 0x00fcfcfc) return kj * pw(x0, e0) * pw(x1, e1) * pw(x2, e2);
+    return (kj * pw3(x0, e0)) * (pw3(x1, e1) * pw3(x2, e2));
 }
 
 // d(rate_j)/du_l / nu_l for the reactant in descriptor slot s (nu_l is folded into the term coefficient)
 __device__ __forceinline__ double drate_of(const int4 d, int s, const double *u, int MB, int m, double kj)
 {
     const double x0 = u[max(d.x, 0) * MB + m], x1 = u[max(d.y, 0) * MB + m], x2 = u[max(d.z, 0) * MB + m];
-    return kj * pw(x0, d.x >= 0 ? (d.w & 255) - (s == 0) : 0) * pw(x1, d.y >= 0 ? ((d.w >> 8) & 255) - (s == 1) : 0) *
-           pw(x2, d.z >= 0 ? ((d.w >> 16) & 255) - (s == 2) : 0);
+    const int e0 = (d.w & 255) - (s == 0), e1 = ((d.w >> 8) & 255) - (s == 1), e2 = ((d.w >> 16) & 255) - (s == 2);
+    if (d.w & 0x00fcfcfc) return kj * pw(x0, max(e0, 0)) * pw(x1, max(e1, 0)) * pw(x2, max(e2, 0));
+    return (kj * pw3(x0, e0)) * (pw3(x1, e1) * pw3(x2, e2));
 }
 
 // k = A*T^n*exp(-Ea/(R*T))*N_A*t_mult, optional harmonic cap — operation order of
@@ -192,7 +204,7 @@ __device__ inline double profile_eval(int kind, const double *p, double t)
 #define KB2_NC 3               // target columns per lane and pass in the LU update
 #endif
 #ifndef KB2_RHS_U
-#define KB2_RHS_U 8            // rows per lane in flight in the gather loops
+#define KB2_RHS_U 8            // entries per lane in flight in the Jacobian gather loops
 #endif
 constexpr int PR = 8;          // rows per panel (PanelPlan::PR)
 constexpr int CWMAX = 96;      // columns per chunk (PanelPlan::CW)
@@ -375,11 +387,26 @@ __device__ void tile_rates(const WTile<MB> &tl, const DevNet &net, double T, boo
 
 // K2: mass-action right-hand side in two gather passes (no atomics, fixed summation order):
 //   rate_j = k_j * prod u^nu                      (lanes over reactions, coalesced k / rate)
-//   du_i   = sum_e coef_e * rate_{j(e)}           (gather CSR of species i, ascending reactions)
-// out_i = du_i + sum_{q<nk} cs_q*K_q,i  (stage right-hand side fusion)
+//   du_i   = sum_e coef_e * rate_{j(e)}           (gather rows of species i, ascending reactions)
+// out_i = du_i (+ out_i when `accumulate`: the caller has put the stage combination there).
+constexpr int ELL_G = 64;      // Symbolic::ELL_G
+template <int U>
+__device__ __forceinline__ void ell_load(const int *p, int (&ix)[U])
+{
+    if constexpr (U >= 4) {
+#pragma unroll
+        for (int q = 0; q < U / 4; ++q) {
+            const int4 v = reinterpret_cast<const int4 *>(p)[q];
+            ix[4 * q] = v.x; ix[4 * q + 1] = v.y; ix[4 * q + 2] = v.z; ix[4 * q + 3] = v.w;
+        }
+    } else {
+        const int2 v = *reinterpret_cast<const int2 *>(p);
+        ix[0] = v.x; ix[1] = v.y;
+    }
+}
+
 template <int MB>
-__device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u, double *out, int nk,
-                         double cs0, double cs1, double cs2, double cs3, double cs4, double *su)
+__device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u, double *out, bool accumulate, double *su)
 {
     constexpr int LN = 32 / MB;
     const int m = tl.m;
@@ -417,6 +444,7 @@ __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u
     for (int z = 0; z < net.rhs_nlong; ++z) {
         const int i = net.rhs_order[z];
         const int e1 = net.rhs_ptr[i + 1];
+        const double b0 = (accumulate && tl.ln == 0) ? out[i * MB + m] : 0.0;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int e = net.rhs_ptr[i] + tl.ln;
         for (; e + 3 * LN < e1; e += 4 * LN) {
@@ -426,62 +454,49 @@ __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u
             a3 += (double)net.rhs_coef[e + 3 * LN] * tl.rate[net.rhs_rxn[e + 3 * LN] * MB + m];
         }
         for (; e < e1; e += LN) a0 += (double)net.rhs_coef[e] * tl.rate[net.rhs_rxn[e] * MB + m];
-        double a = member_sum<MB>((a0 + a1) + (a2 + a3));
-        if (tl.ln == 0) {
-            const int o = i * MB + m;
-            if (nk > 0) a += cs0 * tl.K[0][o];
-            if (nk > 1) a += cs1 * tl.K[1][o];
-            if (nk > 2) a += cs2 * tl.K[2][o];
-            if (nk > 3) a += cs3 * tl.K[3][o];
-            if (nk > 4) a += cs4 * tl.K[4][o];
-            out[o] = a;
-        }
+        const double a = member_sum<MB>((a0 + a1) + (a2 + a3));
+        if (tl.ln == 0) out[i * MB + m] = a + b0;
     }
-    // the other rows one per lane, eight at a time (independent gather chains), in order of
-    // decreasing length so that rows walked together are about equally long
-    constexpr int U = KB2_RHS_U;
-    for (int z0 = net.rhs_nlong + tl.ln; z0 < net.S; z0 += U * LN) {
-        int e[U], n[U], sp[U];
-        double acc[U];
-        int len = 0;
+    // the other rows one per lane slot, U = 64/LN slots per lane, as a sliced ELL (groups of 64
+    // rows of about equal length): the packed (coefficient, reaction) indices of a step are one
+    // or two 16-byte loads that depend on no data, so they are fetched two steps ahead and the
+    // rate gathers of step t+1 are in flight while step t is accumulated.
+    constexpr int U = ELL_G / LN;
+    for (int g = 0; g < net.ell_ngroups; ++g) {
+        const int base = net.ell_ptr[g], len = (net.ell_ptr[g + 1] - base) / ELL_G;
+        const int z0 = net.rhs_nlong + g * ELL_G + tl.ln * U;
+        int sp[U];
+        double acc[U], b0[U];
 #pragma unroll
         for (int v = 0; v < U; ++v) {
-            const int z = z0 + v * LN;
-            sp[v] = z < net.S ? net.rhs_order[z] : -1;
-            e[v] = sp[v] >= 0 ? net.rhs_ptr[sp[v]] : 0;
-            n[v] = sp[v] >= 0 ? net.rhs_ptr[sp[v] + 1] - e[v] : 0;
+            sp[v] = z0 + v < net.S ? net.rhs_order[z0 + v] : -1;
             acc[v] = 0.0;
-            len = max(len, n[v]);
-        }
-        // branch-free: a row that has run out re-reads its last entry with a zero coefficient, so
-        // the eight index loads and then the eight gathers of a step are issued back to back
-        for (int t = 0; t < len; ++t) {
-            int rx[U];
-            double cf[U], rt[U];
-#pragma unroll
-            for (int v = 0; v < U; ++v) {
-                const int ee = e[v] + min(t, max(n[v] - 1, 0));
-                rx[v] = net.rhs_rxn[ee];
-                cf[v] = t < n[v] ? (double)net.rhs_coef[ee] : 0.0;
-            }
-#pragma unroll
-            for (int v = 0; v < U; ++v) rt[v] = tl.rate[rx[v] * MB + m];
-#pragma unroll
-            for (int v = 0; v < U; ++v) acc[v] += cf[v] * rt[v];
         }
 #pragma unroll
-        for (int v = 0; v < U; ++v) {
-            if (sp[v] >= 0) {
-                const int o = sp[v] * MB + m;
-                double a = acc[v];
-                if (nk > 0) a += cs0 * tl.K[0][o];
-                if (nk > 1) a += cs1 * tl.K[1][o];
-                if (nk > 2) a += cs2 * tl.K[2][o];
-                if (nk > 3) a += cs3 * tl.K[3][o];
-                if (nk > 4) a += cs4 * tl.K[4][o];
-                out[o] = a;
+        for (int v = 0; v < U; ++v) b0[v] = (accumulate && sp[v] >= 0) ? out[sp[v] * MB + m] : 0.0;
+        if (len > 0) {
+            const int *ep = net.ell + base + tl.ln * U;
+            int ia[U], ib[U];
+            double ra[U];
+            ell_load<U>(ep, ia);
+            ell_load<U>(ep + min(1, len - 1) * ELL_G, ib);
+#pragma unroll
+            for (int v = 0; v < U; ++v) ra[v] = tl.rate[(ia[v] & 0xffffff) * MB + m];
+            for (int t = 0; t < len; ++t) {
+                int ic[U];
+                double rb[U];
+                ell_load<U>(ep + min(t + 2, len - 1) * ELL_G, ic);
+#pragma unroll
+                for (int v = 0; v < U; ++v) rb[v] = tl.rate[(ib[v] & 0xffffff) * MB + m];
+#pragma unroll
+                for (int v = 0; v < U; ++v) acc[v] += (double)(ia[v] >> 24) * ra[v];
+#pragma unroll
+                for (int v = 0; v < U; ++v) { ia[v] = ib[v]; ra[v] = rb[v]; ib[v] = ic[v]; }
             }
         }
+#pragma unroll
+        for (int v = 0; v < U; ++v)
+            if (sp[v] >= 0) out[sp[v] * MB + m] = acc[v] + b0[v];
     }
     __syncwarp();
 }

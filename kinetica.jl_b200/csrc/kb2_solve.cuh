@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(32) k_rhs(DevNet net, DevPlan pl, DevEns en, i
     const BulkChan ch = chan_setup<MB>(smem, data_bytes);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en, ch);
-        tile_rhs(tl, net, tl.u, tl.rv, 0, 0.0, 0.0, 0.0, 0.0, 0.0, en.u_smem ? smem : nullptr);
+        tile_rhs(tl, net, tl.u, tl.rv, false, en.u_smem ? smem : nullptr);
     }
 }
 
@@ -178,7 +178,7 @@ __device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns 
 {
     constexpr int LN = 32 / MB;
     const int m = tl.m;
-    tile_rhs(tl, net, tl.u, tl.rv, 0, 0.0, 0.0, 0.0, 0.0, 0.0, su);
+    tile_rhs(tl, net, tl.u, tl.rv, false, su);
     double d0 = 0, d1 = 0;
     for (int i = tl.ln; i < net.S; i += LN) {
         const double ui = tl.u[i * MB + m], fi = tl.rv[i * MB + m];
@@ -190,7 +190,7 @@ __device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns 
     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
     for (int i = tl.ln; i < net.S; i += LN) tl.ua[i * MB + m] = tl.u[i * MB + m] + h0 * tl.rv[i * MB + m];
     __syncwarp();
-    tile_rhs(tl, net, tl.ua, tl.y, 0, 0.0, 0.0, 0.0, 0.0, 0.0, su);
+    tile_rhs(tl, net, tl.ua, tl.y, false, su);
     double d2 = 0;
     for (int i = tl.ln; i < net.S; i += LN) {
         const double sc = en.abstol + en.reltol * fabs(tl.u[i * MB + m]);
@@ -314,23 +314,29 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
         for (int s = 0; s < 6; ++s) {
             const double *Us = tl.u;
             if (s > 0) {
-                // ua = u + sum_{q<s} a_sq K_q  (stage 6 shares stage 5's coefficients plus K5)
+                // ua = u + sum_{q<s} a_sq K_q  (stage 6 shares stage 5's coefficients plus K5) and, from
+                // the same loads, the stage combination rv = sum_{q<s} (C_sq/h) K_q that the right-hand
+                // side is added to
+                const double ih = 1.0 / hs;
                 const double a0 = cA[s][0], a1 = cA[s][1], a2 = cA[s][2], a3 = cA[s][3], a4 = cA[s][4];
+                const double c0 = cC[s][0] * ih, c1 = cC[s][1] * ih, c2 = cC[s][2] * ih, c3 = cC[s][3] * ih, c4 = cC[s][4] * ih;
+#pragma unroll 4
                 for (int i = ln; i < net.S; i += LN) {
                     const int o = i * MB + m;
-                    double a = tl.u[o] + a0 * tl.K[0][o];
-                    if (s > 1) a += a1 * tl.K[1][o];
-                    if (s > 2) a += a2 * tl.K[2][o];
-                    if (s > 3) a += a3 * tl.K[3][o];
-                    if (s > 4) a += a4 * tl.K[4][o];
+                    const double k0 = tl.K[0][o];
+                    double a = tl.u[o] + a0 * k0, r = c0 * k0;
+                    if (s > 1) { const double kq = tl.K[1][o]; a += a1 * kq; r += c1 * kq; }
+                    if (s > 2) { const double kq = tl.K[2][o]; a += a2 * kq; r += c2 * kq; }
+                    if (s > 3) { const double kq = tl.K[3][o]; a += a3 * kq; r += c3 * kq; }
+                    if (s > 4) { const double kq = tl.K[4][o]; a += a4 * kq; r += c4 * kq; }
                     tl.ua[o] = a;
+                    tl.rv[o] = r;
                 }
                 __syncwarp();
                 Us = tl.ua;
             }
-            const double ih = 1.0 / hs;
             if (ga.mode >= 2) grid_align(ga, false);
-            tile_rhs(tl, net, Us, tl.rv, s, cC[s][0] * ih, cC[s][1] * ih, cC[s][2] * ih, cC[s][3] * ih, cC[s][4] * ih, su);
+            tile_rhs(tl, net, Us, tl.rv, s > 0, su);
             double *Ks = s == 0 ? tl.K[0] : s == 1 ? tl.K[1] : s == 2 ? tl.K[2] : s == 3 ? tl.K[3] : s == 4 ? tl.K[4] : tl.K[5];
             tile_trisolve(tl, net, pl, tl.rv, Ks, su);
         }

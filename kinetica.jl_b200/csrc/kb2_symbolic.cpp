@@ -271,6 +271,46 @@ std::string build_symbolic(const Network &net, int ordering, Symbolic &sym)
         order_by_len(sym.rhs_ptr, S, Symbolic::RHS_LONG, sym.rhs_order, sym.rhs_nlong);
         order_by_len(sym.jt_ptr, sym.nnzJ, Symbolic::JAC_LONG, sym.j_order, sym.j_nlong);
     }
+    // ---- sliced ELL of the RHS gather rows that go one per lane ----
+    // The rows after the first rhs_nlong of rhs_order are cut into groups of ELL_G consecutive
+    // rows (about equally long: the order is by decreasing length).  Group g stores, for every
+    // step t < len_g and every row slot rho < ELL_G, one int  coef << 24 | reaction  at
+    // ell[ell_ptr[g] + t*ELL_G + rho]; a row that has run out repeats its last reaction with
+    // coefficient 0 (reaction 0 for an empty row).  A lane owns ELL_G/LN consecutive slots, so the
+    // indices of one step are one or two 16-byte loads that do not depend on any data.
+    {
+        const int G = Symbolic::ELL_G;
+        const int64_t nrows = S - sym.rhs_nlong;
+        const int64_t ng = (nrows + G - 1) / G;
+        sym.ell_ptr.assign(ng + 1, 0);
+        sym.ell.clear();
+        for (int64_t g = 0; g < ng; ++g) {
+            int32_t len = 0;
+            for (int rho = 0; rho < G; ++rho) {
+                const int64_t z = sym.rhs_nlong + g * G + rho;
+                if (z < S) len = std::max(len, sym.rhs_ptr[sym.rhs_order[z] + 1] - sym.rhs_ptr[sym.rhs_order[z]]);
+            }
+            const size_t base = sym.ell.size();
+            sym.ell.resize(base + (size_t)len * G, 0);
+            for (int rho = 0; rho < G; ++rho) {
+                const int64_t z = sym.rhs_nlong + g * G + rho;
+                if (z >= S) continue;
+                const int32_t i = sym.rhs_order[z], e0 = sym.rhs_ptr[i], n = sym.rhs_ptr[i + 1] - e0;
+                for (int32_t t = 0; t < len; ++t) {
+                    int32_t v = 0;
+                    if (n > 0) {
+                        const int32_t e = e0 + std::min(t, n - 1);
+                        const int32_t coef = t < n ? sym.rhs_coef[e] : 0;
+                        if (coef < -128 || coef > 127 || sym.rhs_rxn[e] >= (1 << 24)) return "stoichiometry or reaction count out of range for the packed gather table";
+                        v = (int32_t)(((uint32_t)(coef & 0xff) << 24) | (uint32_t)sym.rhs_rxn[e]);
+                    }
+                    sym.ell[base + (size_t)t * G + rho] = v;
+                }
+            }
+            sym.ell_ptr[g + 1] = (int32_t)sym.ell.size();
+        }
+        if (sym.ell.empty()) sym.ell.assign(4, 0);
+    }
     sym.ready = true;
     return "";
 }
