@@ -854,6 +854,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
         int align = 1;
         if (const char *ev = getenv("KB2_ALIGN")) align = atoi(ev);
         if (!h->coop_ok) align = 0;
+        if (align) align = (align & 3) | (h->sm_count << 2);
         int data_bytes = (int)smem - 16;
         int *ctr = h->d_counter;
         DevNet dn = h->dn; DevPlan dp = h->dp; DevEns de = e;

@@ -793,8 +793,10 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
 #pragma unroll
                         for (int q = 0; q < PR; ++q) cu[c][q] = q < nq ? ld_hint(up + q * MB, pol_last) : 0.0;
                     }
+                    // rows >= nr of w and of the L' block are whatever follows in shared memory: they are
+                    // computed but never stored, and rows do not mix in the update
 #pragma unroll
-                    for (int r = 0; r < PR; ++r) w[c][r] = r < nr ? wp[c][r * MB] : 0.0;
+                    for (int r = 0; r < PR; ++r) w[c][r] = wp[c][r * MB];
                 }
                 // U' values of source k+1 fly while source k is applied
 #pragma unroll
@@ -803,16 +805,26 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
 #pragma unroll
                     for (int q = 0; q < PR; ++q) xu[c][q] = (KB2_LU_PREFETCH && has_next && xa.z > 0 && q < xb.x) ? ld_hint(up + q * MB, pol_last) : 0.0;
                 }
+                {
+                    // L' column q+1 is loaded while column q is applied
+                    double l[PR], ln1[PR];
 #pragma unroll
-                for (int q = 0; q < PR; ++q) {
-                    if (q < nq) {
-                        double l[PR];
+                    for (int r = 0; r < PR; ++r) l[r] = ls[r * MB];
 #pragma unroll
-                        for (int r = 0; r < PR; ++r) l[r] = r < nr ? ls[(q * nr + r) * MB] : 0.0;
+                    for (int q = 0; q < PR; ++q) {
+                        if (q < nq) {
+                            if (q + 1 < PR) {
+                                const double *lq = ls + min(q + 1, nq - 1) * nr * MB;
 #pragma unroll
-                        for (int c = 0; c < NC; ++c)
+                                for (int r = 0; r < PR; ++r) ln1[r] = lq[r * MB];
+                            }
 #pragma unroll
-                            for (int r = 0; r < PR; ++r) w[c][r] -= l[r] * cu[c][q];
+                            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                                for (int r = 0; r < PR; ++r) w[c][r] -= l[r] * cu[c][q];
+#pragma unroll
+                            for (int r = 0; r < PR; ++r) l[r] = ln1[r];
+                        }
                     }
                 }
 #pragma unroll
@@ -846,13 +858,13 @@ __device__ void tile_lu(const WTile<MB> &tl, const DevPlan &pl, double *Wp)
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
 #pragma unroll
-                    for (int r = 0; r < PR; ++r) w[c][r] = r < nr ? wp[c][r * MB] : 0.0;
+                    for (int r = 0; r < PR; ++r) w[c][r] = wp[c][r * MB];
 #pragma unroll
                 for (int q = 0; q < PR; ++q) {
                     if (q < nq) {
                         double l[PR];
 #pragma unroll
-                        for (int r = 0; r < PR; ++r) l[r] = r < nr ? ls[(q * nr + r) * MB] : 0.0;
+                        for (int r = 0; r < PR; ++r) l[r] = ls[(q * nr + r) * MB];
 #pragma unroll
                         for (int c = 0; c < NC; ++c)
 #pragma unroll

@@ -232,7 +232,9 @@ __device__ void tile_restart_h(const WTile<MB> &tl, const DevNet &net, const Dev
 struct GridAlign {
     unsigned *bar;      // null: alignment off
     unsigned nctas;
-    int mode;           // 1: one barrier per attempted step; 2: one more in front of every stage
+    int mode;           // 1: one barrier per attempted step; 2: one more in front of every stage;
+                        // 3: two half steps (assembly + factorisation | stages), the two groups of warps half a step apart
+    int group;          // mode 3: warps of group 1 run half a step behind those of group 0
 };
 __device__ __forceinline__ bool grid_align(const GridAlign &ga, bool finished)
 {
@@ -281,6 +283,7 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
     tile_process_stop(tl, net, en, c, true);
     tile_hinit(tl, net, en, c, true, su);
     const size_t sb = (size_t)b * en.nstops;
+    if (ga.mode == 3 && ga.group == 1) grid_align(ga, false);      // half a step behind group 0
     // ---- main loop ----
     for (;;) {
         {
@@ -311,6 +314,7 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
             const WTile<MB> tlu(tile_lu_, net, pl, en, ch);
             tile_lu(tlu, pl, Wp);
         }
+        if (ga.mode == 3) grid_align(ga, false);
         for (int s = 0; s < 6; ++s) {
             const double *Us = tl.u;
             if (s > 0) {
@@ -408,7 +412,8 @@ __global__ void __launch_bounds__(32, MB == 2 ? KB2_MINB2 : 1) k_solve(DevNet ne
     GridAlign ga;
     ga.bar = align ? reinterpret_cast<unsigned *>(tile_counter) + 1 : nullptr;
     ga.nctas = gridDim.x;
-    ga.mode = align;
+    ga.mode = align & 3;
+    ga.group = (align & 3) == 3 ? ((blockIdx.x / max(align >> 2, 1)) & 1) : 0;    // align >> 2 = number of SMs
     for (;;) {
         int tile = 0;
         if ((threadIdx.x & 31) == 0) tile = atomicAdd(tile_counter, 1);
