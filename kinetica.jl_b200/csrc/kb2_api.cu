@@ -198,8 +198,11 @@ static int upload_network(kb2_ctx *h)
     rc |= dev_upload(h, P, s.rdesc.data(), s.rdesc.size(), &rd);
     d.rdesc = (const int4 *)rd;
     rc |= dev_upload(h, P, s.jt_ptr.data(), s.jt_ptr.size(), &d.jt_ptr);
-    rc |= dev_upload(h, P, s.jt_rxn.data(), s.jt_rxn.size(), &d.jt_rxn);
-    rc |= dev_upload(h, P, s.jt_pack.data(), s.jt_pack.size(), &d.jt_pack);
+    rc |= dev_upload(h, P, s.jt_pk.data(), s.jt_pk.size(), &d.jt_pk);
+    rc |= dev_upload(h, P, s.jell_ptr.data(), s.jell_ptr.size(), &d.jell_ptr);
+    rc |= dev_upload(h, P, s.jell.data(), s.jell.size(), &d.jell);
+    d.jell_ngroups = (int)s.jell_ptr.size() - 1;
+    d.jslots = s.jslots;
     rc |= dev_upload(h, P, s.rhs_order.data(), s.rhs_order.size(), &d.rhs_order);
     rc |= dev_upload(h, P, s.j_order.data(), s.j_order.size(), &d.j_order);
     d.rhs_nlong = s.rhs_nlong; d.j_nlong = s.j_nlong;
@@ -451,6 +454,7 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
     for (int q = 0; q < 6; ++q) rc |= dev_alloc(h, P, S * Bt, &e.K[q]);
     rc |= dev_alloc(h, P, R * Bt, &e.k);
     rc |= dev_alloc(h, P, R * Bt, &e.rate);
+    rc |= dev_alloc(h, P, R * Bt * (size_t)h->sym.jslots, &e.drate);
     rc |= dev_alloc(h, P, (size_t)h->sym.panels.padded * Bt, &e.lu);
     rc |= dev_alloc(h, P, S * Bt, &e.invd);
     rc |= dev_alloc(h, P, (size_t)std::max<int64_t>(Ns, 1) * S * Bt, &e.out_u);

@@ -70,6 +70,10 @@ struct Symbolic {
     // ell[ell_ptr[g] + t*ELL_G + rho] = coef << 24 | reaction
     static constexpr int ELL_G = 64;
     std::vector<int32_t> ell_ptr, ell;
+    // Jacobian: derivative-table slots per reaction (max distinct reactants), terms as
+    // (index j*jslots + slot, coefficient), packed coef << 24 | index, and their sliced ELL
+    int32_t jslots = 1;
+    std::vector<int32_t> jt_idx, jt_coef, jt_pk, jell_ptr, jell;
     // reaction descriptors: up to 3 distinct reactant species + exponents packed 8 bit each
     std::vector<int32_t> rdesc;                       // 4 ints per reaction
     // Jacobian terms by J entry (CSC order): (reaction, (coef*nu_l) << 2 | reactant slot)

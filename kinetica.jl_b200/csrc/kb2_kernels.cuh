@@ -43,7 +43,9 @@ struct DevNet {
     int S, R, nnzJ;
     const int *rhs_ptr, *rhs_rxn, *rhs_coef;
     const int4 *rdesc;
-    const int *jt_ptr, *jt_rxn, *jt_pack;
+    const int *jt_ptr, *jt_pk;             // Jacobian terms by entry (CSC order): coef << 24 | (reaction*jslots + reactant slot)
+    const int *jell_ptr, *jell;            // their sliced ELL (entries of j_order after the first j_nlong)
+    int jell_ngroups, jslots;
     const int *rhs_order, *j_order;        // work orders, longest first; the first n_long are split across lanes
     int rhs_nlong, j_nlong;
     const int *ell_ptr, *ell;              // sliced ELL of the one-per-lane RHS rows: ell[ell_ptr[g] + t*64 + slot] = coef << 24 | reaction
@@ -72,7 +74,7 @@ struct DevPlan {
 struct DevEns {
     int B, Bp, MB;
     int u_smem;               // 1: a tile's state vector (S*MB doubles) fits the warp's shared memory and is staged there for the gathers
-    double *u, *ua, *rv, *y, *K[6], *k, *rate, *lu, *invd;
+    double *u, *ua, *rv, *y, *K[6], *k, *rate, *drate, *lu, *invd;
     // conditions
     int nstops;               // row length of the per-member stop tables
     const double *stop_t;     // [b*nstops + s]
@@ -276,7 +278,7 @@ template <int MB>
 struct WTile {
     static constexpr int LN = 32 / MB;
     int lane, m, ln, b;
-    double *u, *ua, *rv, *y, *K[6], *k, *rate, *lu, *invd, *out_u, *out_umax;
+    double *u, *ua, *rv, *y, *K[6], *k, *rate, *drate, *lu, *invd, *out_u, *out_umax;
     BulkChan ch;
     __device__ WTile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en, const BulkChan &chan)
     {
@@ -291,6 +293,7 @@ struct WTile {
         for (int q = 0; q < 6; ++q) K[q] = en.K[q] + vs;
         k = en.k + (size_t)tile * net.R * MB;
         rate = en.rate + (size_t)tile * net.R * MB;
+        drate = en.drate + (size_t)tile * net.R * net.jslots * MB;
         lu = en.lu + (size_t)tile * pl.padded * MB;
         out_u = en.out_u + (size_t)tile * en.Ns * net.S * MB;
         out_umax = en.out_umax + vs;
@@ -405,6 +408,88 @@ __device__ __forceinline__ void ell_load(const int *p, int (&ix)[U])
     }
 }
 
+// Gather-sum over a sliced ELL:  for every item i = order[nlong + slot] (slot = g*64 + ln*U + v)
+//   put(i, pre(i), sum_t coef_t * src[index_t])      (terms in ascending t: fixed order)
+// src is tile-major [index][MB]; pre(i) is evaluated a group ahead (whatever the output needs
+// that is a load: a base value, a storage slot).  The packed indices of a step depend on no
+// data: inside a group they are fetched two steps ahead and the gathers of step t+1 are in flight
+// while step t is accumulated; across groups the group record is three ahead, and the items,
+// the first two index steps and the first gathers of group g+1 are issued while group g finishes
+// (most Jacobian entries have one or two terms: there the group turnaround is what counts).
+template <int MB, class Pre, class Put>
+__device__ __forceinline__ void ell_gather(const WTile<MB> &tl, const int *order, int n, int nlong, const int *ell_ptr, const int *ell,
+                                           int ngroups, const double *src, Pre pre, Put put)
+{
+    constexpr int LN = 32 / MB, U = ELL_G / LN;
+    typedef decltype(pre(0)) H;
+    const int m = tl.m, lo = tl.ln * U;
+    if (ngroups <= 0) return;
+    int q0 = ell_ptr[0], q1 = ell_ptr[1], q2 = ell_ptr[min(2, ngroups)];
+    int sp[U], ia[U], ib[U];
+    double ra[U];
+    H hh[U];
+#pragma unroll
+    for (int v = 0; v < U; ++v) {
+        sp[v] = nlong + lo + v < n ? order[nlong + lo + v] : -1;
+        ia[v] = ib[v] = 0; ra[v] = 0.0;
+    }
+    if (q1 > q0) {
+        ell_load<U>(ell + q0 + lo, ia);
+        ell_load<U>(ell + q0 + lo + min(1, (q1 - q0) / ELL_G - 1) * ELL_G, ib);
+    }
+#pragma unroll
+    for (int v = 0; v < U; ++v) hh[v] = sp[v] >= 0 ? pre(sp[v]) : H();
+    if (q1 > q0) {
+#pragma unroll
+        for (int v = 0; v < U; ++v) ra[v] = src[(ia[v] & 0xffffff) * MB + m];
+    }
+    for (int g = 0; g < ngroups; ++g) {
+        const int len = (q1 - q0) / ELL_G, lenN = (q2 - q1) / ELL_G;
+        const int q3 = ell_ptr[min(g + 3, ngroups)];
+        // group g+1: items and the first two index steps
+        const int zn = nlong + (g + 1) * ELL_G + lo;
+        int spn[U], ja[U], jb[U];
+#pragma unroll
+        for (int v = 0; v < U; ++v) {
+            spn[v] = zn + v < n ? order[zn + v] : -1;
+            ja[v] = jb[v] = 0;
+        }
+        if (lenN > 0) {
+            ell_load<U>(ell + q1 + lo, ja);
+            ell_load<U>(ell + q1 + lo + min(1, lenN - 1) * ELL_G, jb);
+        }
+        // group g
+        double acc[U];
+#pragma unroll
+        for (int v = 0; v < U; ++v) acc[v] = 0.0;
+        const int *ep = ell + q0 + lo;
+        for (int t = 0; t < len; ++t) {
+            int ic[U];
+            double rb[U];
+            ell_load<U>(ep + min(t + 2, len - 1) * ELL_G, ic);
+#pragma unroll
+            for (int v = 0; v < U; ++v) rb[v] = src[(ib[v] & 0xffffff) * MB + m];
+#pragma unroll
+            for (int v = 0; v < U; ++v) acc[v] += (double)(ia[v] >> 24) * ra[v];
+#pragma unroll
+            for (int v = 0; v < U; ++v) { ia[v] = ib[v]; ra[v] = rb[v]; ib[v] = ic[v]; }
+        }
+        // group g+1: what its outputs need, and its first gathers
+        H hn[U];
+        double rn[U];
+#pragma unroll
+        for (int v = 0; v < U; ++v) hn[v] = spn[v] >= 0 ? pre(spn[v]) : H();
+#pragma unroll
+        for (int v = 0; v < U; ++v) rn[v] = lenN > 0 ? src[(ja[v] & 0xffffff) * MB + m] : 0.0;
+#pragma unroll
+        for (int v = 0; v < U; ++v)
+            if (sp[v] >= 0) put(sp[v], hh[v], acc[v]);
+#pragma unroll
+        for (int v = 0; v < U; ++v) { sp[v] = spn[v]; hh[v] = hn[v]; ia[v] = ja[v]; ib[v] = jb[v]; ra[v] = rn[v]; }
+        q0 = q1; q1 = q2; q2 = q3;
+    }
+}
+
 template <int MB>
 __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u, double *out, bool accumulate, double *su)
 {
@@ -457,118 +542,90 @@ __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u
         const double a = member_sum<MB>((a0 + a1) + (a2 + a3));
         if (tl.ln == 0) out[i * MB + m] = a + b0;
     }
-    // the other rows one per lane slot, U = 64/LN slots per lane, as a sliced ELL (groups of 64
-    // rows of about equal length): the packed (coefficient, reaction) indices of a step are one
-    // or two 16-byte loads that depend on no data, so they are fetched two steps ahead and the
-    // rate gathers of step t+1 are in flight while step t is accumulated.
-    constexpr int U = ELL_G / LN;
-    for (int g = 0; g < net.ell_ngroups; ++g) {
-        const int base = net.ell_ptr[g], len = (net.ell_ptr[g + 1] - base) / ELL_G;
-        const int z0 = net.rhs_nlong + g * ELL_G + tl.ln * U;
-        int sp[U];
-        double acc[U], b0[U];
-#pragma unroll
-        for (int v = 0; v < U; ++v) {
-            sp[v] = z0 + v < net.S ? net.rhs_order[z0 + v] : -1;
-            acc[v] = 0.0;
-        }
-#pragma unroll
-        for (int v = 0; v < U; ++v) b0[v] = (accumulate && sp[v] >= 0) ? out[sp[v] * MB + m] : 0.0;
-        if (len > 0) {
-            const int *ep = net.ell + base + tl.ln * U;
-            int ia[U], ib[U];
-            double ra[U];
-            ell_load<U>(ep, ia);
-            ell_load<U>(ep + min(1, len - 1) * ELL_G, ib);
-#pragma unroll
-            for (int v = 0; v < U; ++v) ra[v] = tl.rate[(ia[v] & 0xffffff) * MB + m];
-            for (int t = 0; t < len; ++t) {
-                int ic[U];
-                double rb[U];
-                ell_load<U>(ep + min(t + 2, len - 1) * ELL_G, ic);
-#pragma unroll
-                for (int v = 0; v < U; ++v) rb[v] = tl.rate[(ib[v] & 0xffffff) * MB + m];
-#pragma unroll
-                for (int v = 0; v < U; ++v) acc[v] += (double)(ia[v] >> 24) * ra[v];
-#pragma unroll
-                for (int v = 0; v < U; ++v) { ia[v] = ib[v]; ra[v] = rb[v]; ib[v] = ic[v]; }
-            }
-        }
-#pragma unroll
-        for (int v = 0; v < U; ++v)
-            if (sp[v] >= 0) out[sp[v] * MB + m] = acc[v] + b0[v];
-    }
+    // the other rows one per lane slot as a sliced ELL (groups of 64 rows of about equal length)
+    ell_gather<MB>(tl, net.rhs_order, net.S, net.rhs_nlong, net.ell_ptr, net.ell, net.ell_ngroups, tl.rate,
+                   [&](int i) { return accumulate ? out[i * MB + m] : 0.0; },
+                   [&](int i, double b0, double a) { out[i * MB + m] = a + b0; });
     __syncwarp();
 }
 
 // K3: analytic Jacobian entries  J_p = sum_t coef_t * k_j * d(prod)/du_l  for every entry p of
-// the fixed CSC pattern, handed to `put(p, J_p)`.  Entries with many terms (hub columns) are
-// split across the lanes of the member; the others go one per lane, KB2_RHS_U in flight, longest
-// first, branch-free (an exhausted entry re-reads its last term with coefficient 0).
-template <int MB, class Put>
-__device__ __forceinline__ void tile_jac_entries(const WTile<MB> &tl, const DevNet &net, const double *u, Put put)
+// the fixed CSC pattern, handed to `put(p, J_p)`.  Two passes like the right-hand side:
+//   d[j][s] = k_j * d(prod_j)/du_(slot s) / nu_s     (lanes over reactions: k, descriptors and
+//                                                      the table itself are coalesced streams)
+//   J_p     = sum_t coef_t * d[index_t]               (gather-sum: entries with many terms (hub
+//             columns) are split across the lanes of the member, the others go through the ELL)
+template <int MB, class Pre, class Put>
+__device__ __forceinline__ void tile_jac_entries(const WTile<MB> &tl, const DevNet &net, const double *u, Pre pre, Put put)
 {
     constexpr int LN = 32 / MB;
-    const int m = tl.m;
+    const int m = tl.m, ns = net.jslots;
+    {
+        constexpr int UR = 4;
+        for (int j0 = tl.ln; j0 < net.R; j0 += UR * LN) {
+            int4 d[UR];
+            double kj[UR];
+#pragma unroll
+            for (int v = 0; v < UR; ++v) {
+                const int j = min(j0 + v * LN, net.R - 1);
+                d[v] = net.rdesc[j];
+                kj[v] = tl.k[j * MB + m];
+            }
+#pragma unroll
+            for (int v = 0; v < UR; ++v) {
+                const int j = j0 + v * LN;
+                const double x0 = u[max(d[v].x, 0) * MB + m], x1 = u[max(d[v].y, 0) * MB + m], x2 = u[max(d[v].z, 0) * MB + m];
+                const int e0 = d[v].w & 255, e1 = (d[v].w >> 8) & 255, e2 = (d[v].w >> 16) & 255;
+                double g0, g1, g2;
+                if (d[v].w & 0x00fcfcfc) {
+                    g0 = kj[v] * pw(x0, max(e0 - 1, 0)) * pw(x1, e1) * pw(x2, e2);
+                    g1 = kj[v] * pw(x0, e0) * pw(x1, max(e1 - 1, 0)) * pw(x2, e2);
+                    g2 = kj[v] * pw(x0, e0) * pw(x1, e1) * pw(x2, max(e2 - 1, 0));
+                } else {
+                    // full powers p_s and powers reduced by one q_s: d/du_s = k * q_s * prod_{r != s} p_r
+                    const double q0 = pw3(x0, e0 - 1), q1 = pw3(x1, e1 - 1), q2 = pw3(x2, e2 - 1);
+                    const double p0 = e0 >= 1 ? q0 * x0 : 1.0, p1 = e1 >= 1 ? q1 * x1 : 1.0, p2 = e2 >= 1 ? q2 * x2 : 1.0;
+                    g0 = (kj[v] * q0) * (p1 * p2);
+                    g1 = (kj[v] * q1) * (p0 * p2);
+                    g2 = (kj[v] * q2) * (p0 * p1);
+                }
+                if (j < net.R) {
+                    double *dp = tl.drate + (size_t)(j * ns) * MB + m;
+                    dp[0] = g0;
+                    if (ns > 1) dp[MB] = g1;
+                    if (ns > 2) dp[2 * MB] = g2;
+                }
+            }
+        }
+    }
+    __syncwarp();
     for (int z = 0; z < net.j_nlong; ++z) {
         const int p = net.j_order[z];
         const int t1 = net.jt_ptr[p + 1];
-        double a0 = 0.0, a1 = 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int t = net.jt_ptr[p] + tl.ln;
-        for (; t + LN < t1; t += 2 * LN) {
-            const int j0 = net.jt_rxn[t], pk0 = net.jt_pack[t], j1 = net.jt_rxn[t + LN], pk1 = net.jt_pack[t + LN];
-            a0 += (double)(pk0 >> 2) * drate_of(net.rdesc[j0], pk0 & 3, u, MB, m, tl.k[j0 * MB + m]);
-            a1 += (double)(pk1 >> 2) * drate_of(net.rdesc[j1], pk1 & 3, u, MB, m, tl.k[j1 * MB + m]);
+        for (; t + 3 * LN < t1; t += 4 * LN) {
+            const int k0 = net.jt_pk[t], k1 = net.jt_pk[t + LN], k2 = net.jt_pk[t + 2 * LN], k3 = net.jt_pk[t + 3 * LN];
+            a0 += (double)(k0 >> 24) * tl.drate[(k0 & 0xffffff) * MB + m];
+            a1 += (double)(k1 >> 24) * tl.drate[(k1 & 0xffffff) * MB + m];
+            a2 += (double)(k2 >> 24) * tl.drate[(k2 & 0xffffff) * MB + m];
+            a3 += (double)(k3 >> 24) * tl.drate[(k3 & 0xffffff) * MB + m];
         }
         for (; t < t1; t += LN) {
-            const int j0 = net.jt_rxn[t], pk0 = net.jt_pack[t];
-            a0 += (double)(pk0 >> 2) * drate_of(net.rdesc[j0], pk0 & 3, u, MB, m, tl.k[j0 * MB + m]);
+            const int k0 = net.jt_pk[t];
+            a0 += (double)(k0 >> 24) * tl.drate[(k0 & 0xffffff) * MB + m];
         }
-        const double a = member_sum<MB>(a0 + a1);
-        if (tl.ln == 0) put(p, a);
+        const double a = member_sum<MB>((a0 + a1) + (a2 + a3));
+        if (tl.ln == 0) put(p, pre(p), a);
     }
-    constexpr int U = KB2_RHS_U;
-    for (int z0 = net.j_nlong + tl.ln; z0 < net.nnzJ; z0 += U * LN) {
-        int t[U], n[U], pe[U];
-        double v[U];
-        int len = 0;
-#pragma unroll
-        for (int x = 0; x < U; ++x) {
-            const int z = z0 + x * LN;
-            pe[x] = z < net.nnzJ ? net.j_order[z] : -1;
-            t[x] = pe[x] >= 0 ? net.jt_ptr[pe[x]] : 0;
-            n[x] = pe[x] >= 0 ? net.jt_ptr[pe[x] + 1] - t[x] : 0;
-            v[x] = 0.0;
-            len = max(len, n[x]);
-        }
-        for (int z = 0; z < len; ++z) {
-            int jj[U], pk[U];
-            int4 d[U];
-            double kj[U], dr[U];
-#pragma unroll
-            for (int x = 0; x < U; ++x) {
-                const int tt = t[x] + min(z, max(n[x] - 1, 0));
-                jj[x] = net.jt_rxn[tt];
-                pk[x] = z < n[x] ? net.jt_pack[tt] : (net.jt_pack[tt] & 3);     // exhausted entry: coefficient 0
-            }
-#pragma unroll
-            for (int x = 0; x < U; ++x) { d[x] = net.rdesc[jj[x]]; kj[x] = tl.k[jj[x] * MB + m]; }
-#pragma unroll
-            for (int x = 0; x < U; ++x) dr[x] = drate_of(d[x], pk[x] & 3, u, MB, m, kj[x]);
-#pragma unroll
-            for (int x = 0; x < U; ++x) v[x] += (double)(pk[x] >> 2) * dr[x];
-        }
-#pragma unroll
-        for (int x = 0; x < U; ++x)
-            if (pe[x] >= 0) put(pe[x], v[x]);
-    }
+    ell_gather<MB>(tl, net.j_order, net.nnzJ, net.j_nlong, net.jell_ptr, net.jell, net.jell_ngroups, tl.drate, pre, put);
 }
 
 template <int MB>
 __device__ void tile_jac_csc(const WTile<MB> &tl, const DevNet &net, const double *u, double *Jval)
 {
     const int m = tl.m;
-    tile_jac_entries<MB>(tl, net, u, [&](int p, double v) { Jval[p * MB + m] = v; });
+    tile_jac_entries<MB>(tl, net, u, [](int p) { return p; }, [&](int, int p, double v) { Jval[p * MB + m] = v; });
     __syncwarp();
 }
 
@@ -599,7 +656,7 @@ __device__ void tile_assemble_w(const WTile<MB> &tl, const DevNet &net, const De
         for (int i = tl.lane; i < n2; i += 32) st2_hint(z + i, make_double2(0.0, 0.0), pol);
     }
     __syncwarp();
-    tile_jac_entries<MB>(tl, net, u, [&](int p, double v) { tl.lu[(size_t)net.jslot[p] * MB + m] = -v; });
+    tile_jac_entries<MB>(tl, net, u, [&](int p) { return net.jslot[p]; }, [&](int, int slot, double v) { tl.lu[(size_t)slot * MB + m] = -v; });
     __syncwarp();
     for (int i = tl.ln; i < net.S; i += LN) tl.lu[(size_t)net.diag_slot[i] * MB + m] += hg_inv;
     fence_proxy_async();        // the factorisation reads these values with bulk copies

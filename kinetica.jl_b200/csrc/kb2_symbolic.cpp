@@ -271,45 +271,70 @@ std::string build_symbolic(const Network &net, int ordering, Symbolic &sym)
         order_by_len(sym.rhs_ptr, S, Symbolic::RHS_LONG, sym.rhs_order, sym.rhs_nlong);
         order_by_len(sym.jt_ptr, sym.nnzJ, Symbolic::JAC_LONG, sym.j_order, sym.j_nlong);
     }
-    // ---- sliced ELL of the RHS gather rows that go one per lane ----
-    // The rows after the first rhs_nlong of rhs_order are cut into groups of ELL_G consecutive
-    // rows (about equally long: the order is by decreasing length).  Group g stores, for every
-    // step t < len_g and every row slot rho < ELL_G, one int  coef << 24 | reaction  at
-    // ell[ell_ptr[g] + t*ELL_G + rho]; a row that has run out repeats its last reaction with
-    // coefficient 0 (reaction 0 for an empty row).  A lane owns ELL_G/LN consecutive slots, so the
+    // ---- sliced ELL of the gather rows that go one per lane (RHS rows, Jacobian entries) ----
+    // The items after the first `nlong` of `order` are cut into groups of ELL_G consecutive items
+    // (about equally long: the order is by decreasing length).  Group g stores, for every step
+    // t < len_g and every slot rho < ELL_G, one int  coef << 24 | index  at
+    // ell[ell_ptr[g] + t*ELL_G + rho]; an item that has run out repeats its last index with
+    // coefficient 0 (index 0 for an empty item).  A lane owns ELL_G/LN consecutive slots, so the
     // indices of one step are one or two 16-byte loads that do not depend on any data.
-    {
+    auto build_ell = [&](const std::vector<int32_t> &ptr, const std::vector<int32_t> &order, int64_t n, int32_t nlong,
+                         const std::vector<int32_t> &idx, const std::vector<int32_t> &coef,
+                         std::vector<int32_t> &ell_ptr, std::vector<int32_t> &ell) -> std::string {
         const int G = Symbolic::ELL_G;
-        const int64_t nrows = S - sym.rhs_nlong;
+        const int64_t nrows = n - nlong;
         const int64_t ng = (nrows + G - 1) / G;
-        sym.ell_ptr.assign(ng + 1, 0);
-        sym.ell.clear();
+        ell_ptr.assign(ng + 1, 0);
+        ell.clear();
         for (int64_t g = 0; g < ng; ++g) {
             int32_t len = 0;
             for (int rho = 0; rho < G; ++rho) {
-                const int64_t z = sym.rhs_nlong + g * G + rho;
-                if (z < S) len = std::max(len, sym.rhs_ptr[sym.rhs_order[z] + 1] - sym.rhs_ptr[sym.rhs_order[z]]);
+                const int64_t z = nlong + g * G + rho;
+                if (z < n) len = std::max(len, ptr[order[z] + 1] - ptr[order[z]]);
             }
-            const size_t base = sym.ell.size();
-            sym.ell.resize(base + (size_t)len * G, 0);
+            const size_t base = ell.size();
+            ell.resize(base + (size_t)len * G, 0);
             for (int rho = 0; rho < G; ++rho) {
-                const int64_t z = sym.rhs_nlong + g * G + rho;
-                if (z >= S) continue;
-                const int32_t i = sym.rhs_order[z], e0 = sym.rhs_ptr[i], n = sym.rhs_ptr[i + 1] - e0;
+                const int64_t z = nlong + g * G + rho;
+                if (z >= n) continue;
+                const int32_t i = order[z], e0 = ptr[i], cnt = ptr[i + 1] - e0;
                 for (int32_t t = 0; t < len; ++t) {
                     int32_t v = 0;
-                    if (n > 0) {
-                        const int32_t e = e0 + std::min(t, n - 1);
-                        const int32_t coef = t < n ? sym.rhs_coef[e] : 0;
-                        if (coef < -128 || coef > 127 || sym.rhs_rxn[e] >= (1 << 24)) return "stoichiometry or reaction count out of range for the packed gather table";
-                        v = (int32_t)(((uint32_t)(coef & 0xff) << 24) | (uint32_t)sym.rhs_rxn[e]);
+                    if (cnt > 0) {
+                        const int32_t e = e0 + std::min(t, cnt - 1);
+                        const int32_t c = t < cnt ? coef[e] : 0;
+                        if (c < -128 || c > 127 || idx[e] < 0 || idx[e] >= (1 << 24)) return "coefficient or index out of range for the packed gather table";
+                        v = (int32_t)(((uint32_t)(c & 0xff) << 24) | (uint32_t)idx[e]);
                     }
-                    sym.ell[base + (size_t)t * G + rho] = v;
+                    ell[base + (size_t)t * G + rho] = v;
                 }
             }
-            sym.ell_ptr[g + 1] = (int32_t)sym.ell.size();
+            ell_ptr[g + 1] = (int32_t)ell.size();
         }
-        if (sym.ell.empty()) sym.ell.assign(4, 0);
+        if (ell.empty()) ell.assign(4, 0);
+        return "";
+    };
+    {
+        std::string err = build_ell(sym.rhs_ptr, sym.rhs_order, S, sym.rhs_nlong, sym.rhs_rxn, sym.rhs_coef, sym.ell_ptr, sym.ell);
+        if (!err.empty()) return err;
+    }
+    // Jacobian terms address the derivative table  d[j*jslots + s] = d(rate_j)/du_(slot s) / nu_s
+    // that the device fills per reaction; coefficient = net coefficient * nu_s
+    {
+        int32_t ns = 1;
+        for (int64_t j = 0; j < R; ++j) ns = std::max(ns, net.sub_ptr[j + 1] - net.sub_ptr[j]);
+        if (ns > 3) return "more than three distinct reactants in one reaction";
+        sym.jslots = ns;
+        const size_t nt = sym.jt_rxn.size();
+        sym.jt_idx.resize(nt); sym.jt_coef.resize(nt); sym.jt_pk.resize(std::max<size_t>(nt, 1), 0);
+        for (size_t t = 0; t < nt; ++t) {
+            sym.jt_idx[t] = sym.jt_rxn[t] * ns + (sym.jt_pack[t] & 3);
+            sym.jt_coef[t] = sym.jt_pack[t] >> 2;
+            if (sym.jt_coef[t] < -128 || sym.jt_coef[t] > 127 || sym.jt_idx[t] >= (1 << 24)) return "Jacobian term out of range for the packed gather table";
+            sym.jt_pk[t] = (int32_t)(((uint32_t)(sym.jt_coef[t] & 0xff) << 24) | (uint32_t)sym.jt_idx[t]);
+        }
+        std::string err = build_ell(sym.jt_ptr, sym.j_order, sym.nnzJ, sym.j_nlong, sym.jt_idx, sym.jt_coef, sym.jell_ptr, sym.jell);
+        if (!err.empty()) return err;
     }
     sym.ready = true;
     return "";
