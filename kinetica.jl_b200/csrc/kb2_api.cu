@@ -193,7 +193,9 @@ static int upload_network(kb2_ctx *h)
     const int32_t *rd = nullptr;
     std::vector<int32_t> perm32(s.perm.begin(), s.perm.end());
     rc |= dev_upload(h, P, s.rhs_ptr.data(), s.rhs_ptr.size(), &d.rhs_ptr);
-    rc |= dev_upload(h, P, s.rhs_rxn.data(), s.rhs_rxn.size(), &d.rhs_rxn);
+    rc |= dev_upload(h, P, s.rhs_src.data(), s.rhs_src.size(), &d.rhs_rxn);      // positions in the first-touch rate table
+    rc |= dev_upload(h, P, s.rate_pos.data(), s.rate_pos.size(), &d.rate_pos);
+    rc |= dev_upload(h, P, s.drate_pos.data(), s.drate_pos.size(), &d.drate_pos);
     rc |= dev_upload(h, P, s.rhs_coef.data(), s.rhs_coef.size(), &d.rhs_coef);
     rc |= dev_upload(h, P, s.rdesc.data(), s.rdesc.size(), &rd);
     d.rdesc = (const int4 *)rd;

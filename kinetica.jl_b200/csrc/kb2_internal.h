@@ -74,6 +74,9 @@ struct Symbolic {
     // (index j*jslots + slot, coefficient), packed coef << 24 | index, and their sliced ELL
     int32_t jslots = 1;
     std::vector<int32_t> jt_idx, jt_coef, jt_pk, jell_ptr, jell;
+    // first-touch layouts of the gathered tables: rate of reaction j at rate_pos[j], derivative
+    // (j, s) at drate_pos[j*jslots + s]; rhs_src = rhs_rxn mapped through rate_pos
+    std::vector<int32_t> rate_pos, drate_pos, rhs_src;
     // reaction descriptors: up to 3 distinct reactant species + exponents packed 8 bit each
     std::vector<int32_t> rdesc;                       // 4 ints per reaction
     // Jacobian terms by J entry (CSC order): (reaction, (coef*nu_l) << 2 | reactant slot)

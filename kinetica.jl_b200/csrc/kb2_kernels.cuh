@@ -41,7 +41,8 @@ __constant__ double cC[6][6] = {
 
 struct DevNet {
     int S, R, nnzJ;
-    const int *rhs_ptr, *rhs_rxn, *rhs_coef;
+    const int *rhs_ptr, *rhs_rxn, *rhs_coef;   // gather CSR by species; rhs_rxn holds positions in the rate table
+    const int *rate_pos, *drate_pos;           // first-touch layouts: rate of reaction j at rate_pos[j], derivative (j, s) at drate_pos[j*jslots + s]
     const int4 *rdesc;
     const int *jt_ptr, *jt_pk;             // Jacobian terms by entry (CSC order): coef << 24 | (reaction*jslots + reactant slot)
     const int *jell_ptr, *jell;            // their sliced ELL (entries of j_order after the first j_nlong)
@@ -205,6 +206,9 @@ __device__ inline double profile_eval(int kind, const double *p, double t)
 #ifndef KB2_NC
 #define KB2_NC 3               // target columns per lane and pass in the LU update
 #endif
+#ifndef KB2_K_STREAM
+#define KB2_K_STREAM 0         // k is loaded with an L2 evict_first policy in the per-reaction passes
+#endif
 #ifndef KB2_RHS_U
 #define KB2_RHS_U 8            // entries per lane in flight in the Jacobian gather loops
 #endif
@@ -363,6 +367,18 @@ __device__ __forceinline__ double2 ld2_hint(const double2 *a, unsigned long long
     asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(p) : "memory");
     return v;
 }
+// streamed once per pass (k): keep it from displacing the rate / derivative tables that the
+// gather pass is about to re-read from L2
+__device__ __forceinline__ double ld_stream(const double *a, unsigned long long p)
+{
+#if KB2_K_STREAM
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(p) : "memory");
+    return v;
+#else
+    (void)p; return *a;
+#endif
+}
 __device__ __forceinline__ void cp_async16_hint(void *smem_dst, const void *gsrc, unsigned long long p)
 {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "l"(p) : "memory");
@@ -507,6 +523,7 @@ __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u
     }
     {
         constexpr int UR = 4;
+        const unsigned long long pol_k = l2_policy_first();
         for (int j0 = tl.ln; j0 < net.R; j0 += UR * LN) {
             int4 d[UR];
             double kj[UR];
@@ -514,14 +531,17 @@ __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u
             for (int v = 0; v < UR; ++v) {
                 const int j = min(j0 + v * LN, net.R - 1);
                 d[v] = net.rdesc[j];
-                kj[v] = tl.k[j * MB + m];
+                kj[v] = ld_stream(tl.k + j * MB + m, pol_k);
             }
             double rt[UR];
+            int ps[UR];
+#pragma unroll
+            for (int v = 0; v < UR; ++v) ps[v] = net.rate_pos[min(j0 + v * LN, net.R - 1)];
 #pragma unroll
             for (int v = 0; v < UR; ++v) rt[v] = rate_of(d[v], u, MB, m, kj[v]);
 #pragma unroll
             for (int v = 0; v < UR; ++v)
-                if (j0 + v * LN < net.R) tl.rate[(j0 + v * LN) * MB + m] = rt[v];
+                if (j0 + v * LN < net.R) tl.rate[ps[v] * MB + m] = rt[v];
         }
     }
     __syncwarp();
@@ -562,6 +582,7 @@ __device__ __forceinline__ void tile_jac_entries(const WTile<MB> &tl, const DevN
     const int m = tl.m, ns = net.jslots;
     {
         constexpr int UR = 4;
+        const unsigned long long pol_k = l2_policy_first();
         for (int j0 = tl.ln; j0 < net.R; j0 += UR * LN) {
             int4 d[UR];
             double kj[UR];
@@ -569,7 +590,7 @@ __device__ __forceinline__ void tile_jac_entries(const WTile<MB> &tl, const DevN
             for (int v = 0; v < UR; ++v) {
                 const int j = min(j0 + v * LN, net.R - 1);
                 d[v] = net.rdesc[j];
-                kj[v] = tl.k[j * MB + m];
+                kj[v] = ld_stream(tl.k + j * MB + m, pol_k);
             }
 #pragma unroll
             for (int v = 0; v < UR; ++v) {
@@ -590,10 +611,10 @@ __device__ __forceinline__ void tile_jac_entries(const WTile<MB> &tl, const DevN
                     g2 = (kj[v] * q2) * (p0 * p1);
                 }
                 if (j < net.R) {
-                    double *dp = tl.drate + (size_t)(j * ns) * MB + m;
-                    dp[0] = g0;
-                    if (ns > 1) dp[MB] = g1;
-                    if (ns > 2) dp[2 * MB] = g2;
+                    const int *dq = net.drate_pos + j * ns;
+                    tl.drate[dq[0] * MB + m] = g0;
+                    if (ns > 1) tl.drate[dq[1] * MB + m] = g1;
+                    if (ns > 2) tl.drate[dq[2] * MB + m] = g2;
                 }
             }
         }

@@ -314,9 +314,38 @@ std::string build_symbolic(const Network &net, int ordering, Symbolic &sym)
         if (ell.empty()) ell.assign(4, 0);
         return "";
     };
+    // First-touch layout of a gathered table: position of every source index in the order in which the
+    // device's traversal (long items first, lanes striding over their terms; then group by group,
+    // step by step, slot by slot) touches it first.  What the 64 slots of a warp gather in one
+    // step is then mostly consecutive sectors of new data instead of 64 random ones, and re-touches
+    // go to sectors that were read a few steps earlier.
+    auto first_touch = [&](const std::vector<int32_t> &ptr, const std::vector<int32_t> &order, int64_t n, int32_t nlong,
+                           const std::vector<int32_t> &idx, int64_t nsrc, std::vector<int32_t> &pos) {
+        const int G = Symbolic::ELL_G;
+        pos.assign(nsrc, -1);
+        int32_t next = 0;
+        auto touch = [&](int32_t j) { if (pos[j] < 0) pos[j] = next++; };
+        for (int32_t z = 0; z < nlong; ++z)
+            for (int32_t e = ptr[order[z]]; e < ptr[order[z] + 1]; ++e) touch(idx[e]);
+        for (int64_t z0 = nlong; z0 < n; z0 += G) {
+            int32_t len = 0;
+            for (int64_t z = z0; z < std::min<int64_t>(z0 + G, n); ++z) len = std::max(len, ptr[order[z] + 1] - ptr[order[z]]);
+            for (int32_t t = 0; t < len; ++t)
+                for (int64_t z = z0; z < std::min<int64_t>(z0 + G, n); ++z) {
+                    const int32_t e0 = ptr[order[z]], cnt = ptr[order[z] + 1] - e0;
+                    if (t < cnt) touch(idx[e0 + t]);
+                }
+        }
+        for (int64_t j = 0; j < nsrc; ++j) touch((int32_t)j);
+    };
     {
-        std::string err = build_ell(sym.rhs_ptr, sym.rhs_order, S, sym.rhs_nlong, sym.rhs_rxn, sym.rhs_coef, sym.ell_ptr, sym.ell);
+        // the rate table is stored in first-touch order: rate_pos[j] = where reaction j's rate lives
+        first_touch(sym.rhs_ptr, sym.rhs_order, S, sym.rhs_nlong, sym.rhs_rxn, R, sym.rate_pos);
+        sym.rhs_src.resize(sym.rhs_rxn.size());
+        for (size_t e = 0; e < sym.rhs_rxn.size(); ++e) sym.rhs_src[e] = sym.rate_pos[sym.rhs_rxn[e]];
+        std::string err = build_ell(sym.rhs_ptr, sym.rhs_order, S, sym.rhs_nlong, sym.rhs_src, sym.rhs_coef, sym.ell_ptr, sym.ell);
         if (!err.empty()) return err;
+        if (sym.rate_pos.empty()) sym.rate_pos.assign(1, 0);
     }
     // Jacobian terms address the derivative table  d[j*jslots + s] = d(rate_j)/du_(slot s) / nu_s
     // that the device fills per reaction; coefficient = net coefficient * nu_s
@@ -333,6 +362,13 @@ std::string build_symbolic(const Network &net, int ordering, Symbolic &sym)
             if (sym.jt_coef[t] < -128 || sym.jt_coef[t] > 127 || sym.jt_idx[t] >= (1 << 24)) return "Jacobian term out of range for the packed gather table";
             sym.jt_pk[t] = (int32_t)(((uint32_t)(sym.jt_coef[t] & 0xff) << 24) | (uint32_t)sym.jt_idx[t]);
         }
+        // same first-touch layout for the derivative table: drate_pos[j*jslots + s]
+        first_touch(sym.jt_ptr, sym.j_order, sym.nnzJ, sym.j_nlong, sym.jt_idx, R * ns, sym.drate_pos);
+        for (size_t t = 0; t < nt; ++t) {
+            sym.jt_idx[t] = sym.drate_pos[sym.jt_idx[t]];
+            sym.jt_pk[t] = (int32_t)(((uint32_t)(sym.jt_coef[t] & 0xff) << 24) | (uint32_t)sym.jt_idx[t]);
+        }
+        if (sym.drate_pos.empty()) sym.drate_pos.assign(1, 0);
         std::string err = build_ell(sym.jt_ptr, sym.j_order, sym.nnzJ, sym.j_nlong, sym.jt_idx, sym.jt_coef, sym.jell_ptr, sym.jell);
         if (!err.empty()) return err;
     }
