@@ -261,13 +261,15 @@ def main():
     alg_bytes = algorithmic_bytes_per_attempt(S, R, es.nnzJ, es.nnzLU) * attempts
     solve_ms = float(np.mean(dev_ms))
     achieved = alg_bytes / (solve_ms * 1e-3) / 1e9
-    # measured DRAM traffic of k_solve: dram__bytes_read.sum + dram__bytes_write.sum of one
-    # `ncu --set full` capture of the same kernel on the same network (C3, 4096 members, 8 attempted
-    # steps per member: profiles/r01_k_solve_8attempts_full.txt), per member and attempted step,
-    # scaled to this launch's attempts; only quoted for the workload it was captured on
+    # measured DRAM traffic of k_solve: dram__bytes_read.sum + dram__bytes_write.sum of an ncu capture
+    # of the same kernel on the same network (C3, 4096 members, 8 attempted steps per member:
+    # profiles/r01_k_solve_8attempts_final_dram.csv for this build; the `--set full` capture one
+    # commit earlier, profiles/r01_k_solve_8attempts_aligned_full.txt, has 486.7 + 86.4 GB), per
+    # member and attempted step, scaled to this launch's attempts; only quoted for the workload
+    # it was captured on
     traffic = None
     if args.workload == "c3" and B == 4096:
-        traffic = (534.934735e9 + 85.512056e9) / (4096 * 8) * attempts
+        traffic = (465.597729e9 + 86.312270e9) / (4096 * 8) * attempts
     kern = {}
     try:
         per = {"arrhenius": 8 * (R + 1), "rhs": 8 * (R + 2 * S), "jacobian": 8 * (R + S + es.nnzJ),

@@ -119,6 +119,11 @@ int32_t kb2_solve(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, 
 int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, double t0,
                           double abstol, double reltol, double dtmin, int64_t maxiters,
                           int32_t ban_negatives, int64_t Ns);
+/* `run` launches ONE kernel (the fused solve).  It is a cooperative launch: all of its warps are
+ * resident at once and meet at a grid-wide barrier in front of every attempted step (phase
+ * alignment), so the handle's GPU should not be shared with other long-running
+ * kernels while it runs.  Environment switch for experiments: KB2_ALIGN=0 (no barrier, plain
+ * launch), 1 (default), 2 (a barrier per stage as well), 3 (two half-step groups). */
 int32_t kb2_solve_run(kb2_handle h, float *ms_device);
 int32_t kb2_solve_fetch(kb2_handle h, double *out_u, double *out_umax, int32_t *status, int64_t *stats);
 /* device-side results for the multi-GPU allgather: packs final concentrations and per-species
