@@ -78,7 +78,11 @@ int32_t kb2_get_lu_pattern(kb2_handle h, int64_t *rowptr, int64_t *colidx, int64
 int32_t kb2_get_plan_stats(kb2_handle h, int64_t *out);
 /* raw plan tables for host-side verification; which: 0 p_row0, 1 p_nrows, 2 p_width, 3 p_next,
  * 4 p_base, 5 p_cptr, 6 cols, 7 u_info (12 per unit), 8 t_info (12 per task), 9 map, 10 slot_of,
- * 11 jslot, 12 diag_slot.  Returns the length (copies when cap is large enough), -1 on error. */
+ * 11 jslot, 12 diag_slot; gather tables of the right-hand side and the Jacobian: 13 rhs_ptr,
+ * 14 rhs_rxn, 15 rhs_coef, 16 rhs_order, 17 rate_pos, 18 ell_ptr, 19 ell, 20 jt_ptr, 21 jt_rxn,
+ * 22 jt_pack, 23 j_order, 24 drate_pos, 25 jell_ptr, 26 jell, 27 jt_pk,
+ * 28 {rhs_nlong, j_nlong, jslots, ELL group size}.
+ * Returns the length (copies when cap is large enough), -1 on error. */
 int64_t kb2_get_plan_array(kb2_handle h, int32_t which, int32_t *out, int64_t cap);
 
 /* ---- calculators: PrecalculatedArrheniusCalculator (calculator.jl:164-238);

@@ -8,5 +8,6 @@ from .conditions import (ConditionSet, DoubleRampGradientProfile, LinearDirectPr
                          StaticConditionProfile, create_savepoints, tconvert)
 from .network import RxData, SpeciesData
 from .params import B200Rodas4, ODESimulationParams
+from .seeds import identify_next_seeds, identify_next_seeds_ensemble
 from .solve import (B200EnsembleODESolve, EnsembleSolver, ODESolveOutput, RxFilter, StaticODESolve,
                     VariableODESolve, solve_network)

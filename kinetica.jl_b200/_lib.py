@@ -172,6 +172,25 @@ class Handle:
         out["t_info"] = out["t_info"].reshape(-1, 12)
         return out
 
+    GATHER_ARRAYS = ["rhs_ptr", "rhs_rxn", "rhs_coef", "rhs_order", "rate_pos", "ell_ptr", "ell", "jt_ptr", "jt_rxn",
+                     "jt_pack", "j_order", "drate_pos", "jell_ptr", "jell", "jt_pk", "meta"]
+
+    def get_gather_tables(self):
+        """The gather tables of the right-hand side and the Jacobian (host-side verification):
+        CSR rows, work orders, first-touch layouts and the sliced ELLs the device walks."""
+        out = {}
+        for k, name in enumerate(self.GATHER_ARRAYS):
+            which = 13 + k
+            n = int(self._lib.kb2_get_plan_array(self._h, which, None, 0))
+            if n < 0:
+                raise Kb2Error("gather table %s unavailable" % name)
+            a = np.zeros(max(n, 1), dtype=np.int32)
+            self._lib.kb2_get_plan_array(self._h, which, a.ctypes.data_as(_pi32), n)
+            out[name] = a[:n]
+        m = out.pop("meta")
+        out.update(rhs_nlong=int(m[0]), j_nlong=int(m[1]), jslots=int(m[2]), ell_g=int(m[3]))
+        return out
+
     def get_launch_info(self):
         a, b = _i32(), _i32()
         self._ck(self._lib.kb2_get_launch_info(self._h, C.byref(a), C.byref(b)))

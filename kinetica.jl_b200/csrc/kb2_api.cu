@@ -297,6 +297,27 @@ extern "C" int64_t kb2_get_plan_array(kb2_handle h, int32_t which, int32_t *out,
     case 10: v = &pp.slot_of; break;
     case 11: v = &pp.jslot; break;
     case 12: v = &pp.diag_slot; break;
+    // gather tables of the right-hand side and the Jacobian (kb2_symbolic.cpp)
+    case 13: v = &h->sym.rhs_ptr; break;
+    case 14: v = &h->sym.rhs_rxn; break;
+    case 15: v = &h->sym.rhs_coef; break;
+    case 16: v = &h->sym.rhs_order; break;
+    case 17: v = &h->sym.rate_pos; break;
+    case 18: v = &h->sym.ell_ptr; break;
+    case 19: v = &h->sym.ell; break;
+    case 20: v = &h->sym.jt_ptr; break;
+    case 21: v = &h->sym.jt_rxn; break;
+    case 22: v = &h->sym.jt_pack; break;
+    case 23: v = &h->sym.j_order; break;
+    case 24: v = &h->sym.drate_pos; break;
+    case 25: v = &h->sym.jell_ptr; break;
+    case 26: v = &h->sym.jell; break;
+    case 27: v = &h->sym.jt_pk; break;
+    case 28: {
+        const int32_t meta[4] = {h->sym.rhs_nlong, h->sym.j_nlong, h->sym.jslots, Symbolic::ELL_G};
+        if (out && cap >= 4) std::copy(meta, meta + 4, out);
+        return 4;
+    }
     default: return -1;
     }
     if (out && cap >= (int64_t)v->size()) std::copy(v->begin(), v->end(), out);
