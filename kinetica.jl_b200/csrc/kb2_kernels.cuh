@@ -1,15 +1,16 @@
 // CUDA kernels of the kinetic-solve hot path (sm_100a).
 //
 // Execution model: ONE WARP integrates one tile of MB consecutive ensemble members (MB in
-// {1,2,4}) from t0 to the end; lane = ln * MB + m with m the member inside the tile and ln one of
-// LN = 32/MB work lanes of that member.  Warps never synchronise with each other: no block
-// barriers anywhere on the path, only __syncwarp and shuffles, and a CTA is a single warp so the
-// scheduler can keep every tile of the ensemble resident at once.
+// {1,2,4,8}) from t0 to the end; lane = ln * MB + m with m the member inside the tile and ln one
+// of LN = 32/MB work lanes of that member.  A CTA is a single warp and the data path has no block
+// barrier, only __syncwarp and shuffles, so the scheduler can keep every tile of the ensemble
+// resident at once; the one place where warps wait for each other is the grid-wide phase
+// alignment in front of every attempted step (kb2_solve.cuh, grid_align).
 // Layout: every per-member array is tile-major [tile][index][MB] — species / reaction / LU-slot
 // major, member minor — so the lanes of a warp that work on the same index touch one MB*8-byte
 // segment (a full 32-byte sector for MB = 4) and consecutive indices are consecutive in memory.
 // All index tables are shared by every member, control flow is uniform inside a warp.  No atomics
-// on the data path (gather CSR), results are deterministic run to run.
+// on the data path (gather tables), results are deterministic run to run.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -123,15 +124,6 @@ __device__ __forceinline__ double rate_of(const int4 d, const double *u, int MB,
     return (kj * pw3(x0, e0)) * (pw3(x1, e1) * pw3(x2, e2));
 }
 
-// d(rate_j)/du_l / nu_l for the reactant in descriptor slot s (nu_l is folded into the term coefficient)
-__device__ __forceinline__ double drate_of(const int4 d, int s, const double *u, int MB, int m, double kj)
-{
-    const double x0 = u[max(d.x, 0) * MB + m], x1 = u[max(d.y, 0) * MB + m], x2 = u[max(d.z, 0) * MB + m];
-    const int e0 = (d.w & 255) - (s == 0), e1 = ((d.w >> 8) & 255) - (s == 1), e2 = ((d.w >> 16) & 255) - (s == 2);
-    if (d.w & 0x00fcfcfc) return kj * pw(x0, max(e0, 0)) * pw(x1, max(e1, 0)) * pw(x2, max(e2, 0));
-    return (kj * pw3(x0, e0)) * (pw3(x1, e1) * pw3(x2, e2));
-}
-
 // k = A*T^n*exp(-Ea/(R*T))*N_A*t_mult, optional harmonic cap — operation order of
 // reference src/solving/calculator.jl:223-232 (T^n is this build's extension, n = 0 by default).
 __device__ __forceinline__ double arrhenius(const DevNet &net, int r, double T)
@@ -208,9 +200,6 @@ __device__ inline double profile_eval(int kind, const double *p, double t)
 #endif
 #ifndef KB2_K_STREAM
 #define KB2_K_STREAM 0         // k is loaded with an L2 evict_first policy in the per-reaction passes
-#endif
-#ifndef KB2_RHS_U
-#define KB2_RHS_U 8            // entries per lane in flight in the Jacobian gather loops
 #endif
 constexpr int PR = 8;          // rows per panel (PanelPlan::PR)
 constexpr int CWMAX = 96;      // columns per chunk (PanelPlan::CW)
@@ -335,13 +324,6 @@ __device__ __forceinline__ unsigned long long l2_policy_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ void st_hint(double *a, double v, unsigned long long p)
-{
-#ifndef KB2_L2_HINTS
-    (void)p; *a = v; return;
-#endif
-    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(p) : "memory");
-}
 __device__ __forceinline__ void st2_hint(double2 *a, double2 v, unsigned long long p)
 {
 #ifndef KB2_L2_HINTS
@@ -358,15 +340,6 @@ __device__ __forceinline__ double ld_hint(const double *a, unsigned long long p)
     asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ double2 ld2_hint(const double2 *a, unsigned long long p)
-{
-    double2 v;
-#ifndef KB2_L2_HINTS
-    (void)p; return *a;
-#endif
-    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(p) : "memory");
-    return v;
-}
 // streamed once per pass (k): keep it from displacing the rate / derivative tables that the
 // gather pass is about to re-read from L2
 __device__ __forceinline__ double ld_stream(const double *a, unsigned long long p)
@@ -378,14 +351,6 @@ __device__ __forceinline__ double ld_stream(const double *a, unsigned long long 
 #else
     (void)p; return *a;
 #endif
-}
-__device__ __forceinline__ void cp_async16_hint(void *smem_dst, const void *gsrc, unsigned long long p)
-{
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "l"(p) : "memory");
-}
-__device__ __forceinline__ void cp_async8_hint(void *smem_dst, const void *gsrc, unsigned long long p)
-{
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "l"(p) : "memory");
 }
 
 // K1: k[r][m] for the member's current condition value T (masked by `upd`)
@@ -687,14 +652,6 @@ __device__ void tile_assemble_w(const WTile<MB> &tl, const DevNet &net, const De
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
