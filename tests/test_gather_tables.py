@@ -36,15 +36,32 @@ def ell_gather(order, n, nlong, ell_ptr, ell, G, src, put):
                 put(int(order[z]), acc)
 
 
+def handmade():
+    """Edge cases the synthetic generator never produces: three distinct reactants (third slot of the
+    derivative table), a collision partner that nets out, a stoichiometry above 3 (general power
+    path), a species that takes part in nothing."""
+    import kinetica_b200 as kb
+    #        A+B+C -> D      A+M -> B+M    4A -> E     D -> A+B     2E -> 3A + C
+    reacs = [[0, 1, 2],      [0, 6],       [0],        [3],         [4]]
+    prods = [[3],            [1, 6],       [4],        [0, 1],      [0, 2]]
+    sr    = [[1, 1, 1],      [1, 1],       [4],        [1],         [2]]
+    sp    = [[1],            [1, 1],       [1],        [1, 1],      [3, 1]]
+    return kb.RxData(reacs, prods, sr, sp)           # species 5 is inert, species 6 = M
+
+
 def walk(S, R, seed):
-    sd, rd, Ea, A = synthetic_crn(S, R, seed)
+    if seed is None:
+        rd = handmade()
+    else:
+        sd, rd, Ea, A = synthetic_crn(S, R, seed)
     h = _lib.Handle(-1)
     h.set_network(S, *rd.flatten())
     h.symbolic(4)
     return rd, h, h.get_gather_tables()
 
 
-@pytest.mark.parametrize("S,R,seed", [(64, 256, SEED_BASE + 100), (300, 1500, SEED_BASE + 3), (40, 90, SEED_BASE + 7)])
+@pytest.mark.parametrize("S,R,seed", [(64, 256, SEED_BASE + 100), (300, 1500, SEED_BASE + 3), (40, 90, SEED_BASE + 7),
+                                      (200, 3000, SEED_BASE + 9), (7, 5, None)])
 def test_rhs_tables_reproduce_mass_action(S, R, seed):
     rd, h, T = walk(S, R, seed)
     net = ko.Network(S, rd.id_reacs, rd.id_prods, rd.stoic_reacs, rd.stoic_prods)
@@ -93,7 +110,8 @@ def test_rhs_tables_reproduce_mass_action(S, R, seed):
                     touch(int(pos[rxn[ptr[r] + t]]))
 
 
-@pytest.mark.parametrize("S,R,seed", [(64, 256, SEED_BASE + 100), (300, 1500, SEED_BASE + 3)])
+@pytest.mark.parametrize("S,R,seed", [(64, 256, SEED_BASE + 100), (300, 1500, SEED_BASE + 3), (200, 3000, SEED_BASE + 9),
+                                      (7, 5, None)])
 def test_jacobian_tables_reproduce_analytic_jacobian(S, R, seed):
     rd, h, T = walk(S, R, seed)
     net = ko.Network(S, rd.id_reacs, rd.id_prods, rd.stoic_reacs, rd.stoic_prods)
