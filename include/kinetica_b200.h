@@ -114,7 +114,7 @@ int32_t kb2_set_member_stops(kb2_handle h, int64_t B, int64_t nstops_max, const 
  * solve_utils.jl:376-424) for B members at once.
  *   u0[u0_stride*b + i]  (u0_stride = 0 broadcasts one vector; else u0_stride = S)
  *   out_u[(s*S + i)*B + b]  s = save index;  out_umax[i*B + b] = max over saves (NULL to skip)
- *   status[b];  stats[b*8] = {accepted, rejected, lu, rhs, 0,0,0,0} ---- */
+ *   status[b];  stats[b*8] = {accepted, rejected, lu, rhs, saves, stops passed, attempts, 0} ---- */
 int32_t kb2_solve(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, double t0,
                   double abstol, double reltol, double dtmin, int64_t maxiters,
                   int32_t ban_negatives, int64_t Ns, double *out_u, double *out_umax,
@@ -123,13 +123,16 @@ int32_t kb2_solve(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, 
 int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, double t0,
                           double abstol, double reltol, double dtmin, int64_t maxiters,
                           int32_t ban_negatives, int64_t Ns);
-/* `run` launches ONE kernel (the fused solve).  It is a cooperative launch: all of its warps are
- * resident at once and meet at a grid-wide barrier in front of every attempted step (phase
- * alignment), so the handle's GPU should not be shared with other long-running
- * kernels while it runs.  Environment switch for experiments: KB2_ALIGN=0 (no barrier, plain
- * launch), 1 (default), 2 (a barrier per stage as well), 3 (two half-step groups). */
+/* `run` drives the phase kernels of the solve from a host loop: per attempted
+ * step  W assembly + LU | 6 x (stage right-hand side | triangular sweeps) | error control + stop
+ * handling, launched back to back on the handle's stream; the loop reads a "members still running"
+ * word back every 16 rounds.  ms_device = CUDA-event time from the first to the last launch. */
 int32_t kb2_solve_run(kb2_handle h, float *ms_device);
 int32_t kb2_solve_fetch(kb2_handle h, double *out_u, double *out_umax, int32_t *status, int64_t *stats);
+/* phase timing of the last kb2_solve_run, from CUDA events around every kernel of the sampled
+ * rounds (one round in 16): ms_avg[5] = average launch duration of {LU, stage right-hand side,
+ * stage sweeps, step end, Jacobian values}, launches_sampled[5], rounds = rounds the loop ran */
+int32_t kb2_get_phase_times(kb2_handle h, double *ms_avg, int64_t *launches_sampled, int64_t *rounds);
 /* device-side results for the multi-GPU allgather: packs final concentrations and per-species
  * maxima member-major into caller-provided DEVICE buffers final_bs[b*S+i], umax_bs[b*S+i] */
 int32_t kb2_pack_results_device(kb2_handle h, double *final_bs_dev, double *umax_bs_dev);
@@ -143,7 +146,9 @@ int32_t kb2_factor(kb2_handle h, int64_t B, const double *u, const double *k,
                    const double *hg_inv, double *lu_out);
 int32_t kb2_trisolve(kb2_handle h, int64_t B, const double *rhs, double *x);
 /* time `iters` launches of one standalone kernel on resident data; which: 0 arrhenius, 1 rhs,
- * 2 jacobian, 3 W-assembly+LU, 4 trisolve */
+ * 2 jacobian values, 3 factorisation as the solve runs it (Jacobian values + window LU, or the
+ * block-plan assembly + LU when the window does not fit), 4 trisolve, 5 block-plan W assembly,
+ * 6 block-plan LU, 7 window LU alone, 8 block-plan assembly + LU */
 int32_t kb2_time_kernel(kb2_handle h, int32_t which, int64_t B, int32_t iters, float *ms_avg);
 
 /* tuning: members per warp tile (1, 2 or 4; 0 = auto); the second argument is reserved (pass 0) */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "kb2_solve_prepare": (_i32, [_H, _i64, _pf64, _i64, _f64, _f64, _f64, _f64, _i64, _i32, _i64]),
     "kb2_solve_run": (_i32, [_H, C.POINTER(C.c_float)]),
     "kb2_solve_fetch": (_i32, [_H, _pf64, _pf64, _pi32, _pi64]),
+    "kb2_get_phase_times": (_i32, [_H, _pf64, _pi64, _pi64]),
     "kb2_pack_results_device": (_i32, [_H, C.c_void_p, C.c_void_p]),
     "kb2_eval_k": (_i32, [_H, _i64, _pf64, _pf64]),
     "kb2_eval_profile": (_i32, [_H, _i64, _i64, _pf64, _pf64]),
@@ -191,6 +192,22 @@ class Handle:
         out.update(rhs_nlong=int(m[0]), j_nlong=int(m[1]), jslots=int(m[2]), ell_g=int(m[3]))
         return out
 
+    def get_front_plan(self):
+        """The front plan of the window LU (host-side verification)."""
+        out = {}
+        for which, name in ((29, "f_info"), (30, "lists"), (31, "init"), (32, "meta")):
+            n = int(self._lib.kb2_get_plan_array(self._h, which, None, 0))
+            if n < 0:
+                raise Kb2Error("front plan table %s unavailable" % name)
+            a = np.zeros(max(n, 1), dtype=np.int32)
+            self._lib.kb2_get_plan_array(self._h, which, a.ctypes.data_as(_pi32), n)
+            out[name] = a[:n]
+        m = out.pop("meta")
+        out.update(NF=int(m[0]), Wr=int(m[1]), Wc=int(m[2]), max_nl=int(m[3]), max_nu=int(m[4]), max_init=int(m[5]))
+        out["f_info"] = out["f_info"].reshape(-1, 12)
+        out["init"] = out["init"].reshape(-1, 2)
+        return out
+
     def get_launch_info(self):
         a, b = _i32(), _i32()
         self._ck(self._lib.kb2_get_launch_info(self._h, C.byref(a), C.byref(b)))
@@ -256,6 +273,17 @@ class Handle:
         ms = C.c_float()
         self._ck(self._lib.kb2_solve_run(self._h, C.byref(ms)))
         return float(ms.value)
+
+    PHASES = ["lu", "stage_rhs", "stage_sweeps", "step_end", "jacobian"]
+
+    def get_phase_times(self):
+        """Average duration (ms) of each phase kernel of the last solve, from CUDA events around every
+        launch of the sampled rounds; launches sampled per phase; rounds the host loop ran."""
+        ms = np.zeros(5)
+        n = np.zeros(5, dtype=np.int64)
+        r = _i64()
+        self._ck(self._lib.kb2_get_phase_times(self._h, _f(ms), _i(n), C.byref(r)))
+        return {nm: {"ms": float(ms[q]), "sampled_launches": int(n[q])} for q, nm in enumerate(self.PHASES)}, int(r.value)
 
     def solve_fetch(self, out_u=None, out_umax=None, want_umax=True):
         B, Ns, S = self._B, self._Ns, self.S

@@ -3,6 +3,7 @@
 // kb2_kernels.cuh.  There is no CPU fallback: without a usable CUDA device every compute entry
 // point fails with a non-zero status.
 #include "kb2_solve.cuh"
+#include "kb2_front.cuh"
 #include "kb2_internal.h"
 #include "../../include/kinetica_b200.h"
 
@@ -39,20 +40,26 @@ struct kb2_ctx {
     std::vector<int32_t> stop_flags, stop_cnt;     // stop_cnt empty = one list shared by all members
     int64_t Bprof = 0, Btab = 0, ns_row = 0, Bstops = 0;
     // device
-    std::vector<void *> net_allocs, ens_allocs;
+    std::vector<void *> net_allocs, calc_allocs, ens_allocs;
     DevNet dn{};
     DevPlan dp{};
+    DevFront df{};
+    bool window_ok = false;       // the front plan's window fits the shared memory of an SM for the current tile size
     DevEns de{};
     int64_t ens_B = -1, ens_Ns = -1;
     size_t ens_fixed = 0;
-    int *d_counter = nullptr;   // [0] tile counter of the solve, [1..2] arrival count and generation word of its alignment barrier
-    bool coop_ok = false;
     int mb_user = 0, last_ctas_per_sm = 0;
     int ens_mb = 0;               // members per warp tile of the current ensemble allocation
     double *stage = nullptr;      // device staging for layout conversion (caller rows <-> tiles)
     size_t stage_cap = 0;
     double *scal = nullptr;       // [Bp] per-member scalars of the kernel-level entry points
     bool prepared = false;
+    // phase timing of the last solve (sampled rounds), and its host loop
+    std::vector<cudaEvent_t> phase_ev;
+    double phase_ms[5] = {0, 0, 0, 0, 0};
+    long long phase_n[5] = {0, 0, 0, 0, 0};
+    long long rounds = 0;
+    int *h_flag = nullptr;        // pinned
 };
 
 #define FAIL(h, msg) do { (h)->err = (msg); return 1; } while (0)
@@ -106,11 +113,14 @@ extern "C" int32_t kb2_create(int32_t device, kb2_handle *out)
     cudaGetDeviceProperties(&prop, device);
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
-    h->coop_ok = prop.cooperativeLaunch != 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return 3; }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
-    cudaMalloc((void **)&h->d_counter, 8 * sizeof(int));
+    if (cudaMallocHost((void **)&h->h_flag, KB2_FLAG_SLOTS * sizeof(int)) != cudaSuccess) {
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return 3;
+    }
     *out = h;
     return 0;
 }
@@ -122,9 +132,11 @@ extern "C" int32_t kb2_destroy(kb2_handle h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_pool(h->net_allocs);
+    free_pool(h->calc_allocs);
     free_pool(h->ens_allocs);
     cudaFree(h->stage);
-    cudaFree(h->d_counter);
+    cudaFreeHost(h->h_flag);
+    for (auto &ev : h->phase_ev) cudaEventDestroy(ev);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -139,7 +151,7 @@ extern "C" int32_t kb2_set_tiling(kb2_handle h, int32_t mb, int32_t reserved)
 {
     if (!h) return 1;
     (void)reserved;
-    if (mb != 0 && mb != 1 && mb != 2 && mb != 4 && mb != 8) FAIL(h, "members_per_tile must be 0 (auto), 1, 2, 4 or 8");
+    if (mb != 0 && mb != 1 && mb != 2 && mb != 4) FAIL(h, "members_per_tile must be 0 (auto), 1, 2 or 4");
     h->mb_user = mb;
     h->ens_B = -1;            // the tile size is baked into the device layout
     h->prepared = false;
@@ -232,10 +244,22 @@ static int upload_network(kb2_ctx *h)
         rc |= dev_upload(h, P, pp.map.data(), pp.map.size(), &q.map);
         q.u_info = (const int4 *)ui; q.t_info = (const int4 *)ti;
     }
+    {
+        const FrontPlan &f = s.fronts;
+        DevFront &q = h->df;
+        q = DevFront{};
+        q.NF = f.NF; q.Wr = f.Wr; q.Wc = f.Wc; q.max_nl = f.max_nl; q.max_nu = f.max_nu;
+        const int32_t *ini = nullptr;
+        rc |= dev_upload(h, P, f.f_info.data(), f.f_info.size(), &q.f_info);
+        rc |= dev_upload(h, P, f.lists.data(), f.lists.size(), &q.lists);
+        rc |= dev_upload(h, P, f.init.data(), f.init.size(), &ini);
+        q.init = (const int2 *)ini;
+    }
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
+    free_pool(h->calc_allocs);
     h->net_on_device = true;
-    h->calc_mode = -1;          // calculator tables live in the same pool
+    h->calc_mode = -1;          // a new network needs its calculator set again
     return 0;
 }
 
@@ -260,6 +284,8 @@ extern "C" int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, i
         e = build_panels(h->sym, h->net.S);
         if (!e.empty()) FAIL(h, e);
     }
+    e = build_fronts(h->sym, h->net.S);
+    if (!e.empty()) FAIL(h, e);
     if (nnzJ) *nnzJ = h->sym.nnzJ;
     if (nnzLU) *nnzLU = h->sym.nnzLU;
     if (n_fma) *n_fma = h->sym.n_fma;
@@ -318,6 +344,16 @@ extern "C" int64_t kb2_get_plan_array(kb2_handle h, int32_t which, int32_t *out,
         if (out && cap >= 4) std::copy(meta, meta + 4, out);
         return 4;
     }
+    // front plan of the window LU (kb2_front.cpp)
+    case 29: v = &h->sym.fronts.f_info; break;
+    case 30: v = &h->sym.fronts.lists; break;
+    case 31: v = &h->sym.fronts.init; break;
+    case 32: {
+        const FrontPlan &f = h->sym.fronts;
+        const int32_t meta[6] = {f.NF, f.Wr, f.Wc, f.max_nl, f.max_nu, f.max_init};
+        if (out && cap >= 6) std::copy(meta, meta + 6, out);
+        return 6;
+    }
     default: return -1;
     }
     if (out && cap >= (int64_t)v->size()) std::copy(v->begin(), v->end(), out);
@@ -359,10 +395,13 @@ extern "C" int32_t kb2_set_arrhenius(kb2_handle h, const double *A, const double
     if (n) h->nexp.assign(n, n + R);
     h->k_max = k_max; h->t_mult = t_mult;
     CU(h, cudaSetDevice(h->device));
-    int rc = dev_upload(h, h->net_allocs, h->A.data(), (size_t)R, &h->dn.A);
-    rc |= dev_upload(h, h->net_allocs, h->Ea.data(), (size_t)R, &h->dn.Ea);
+    CU(h, cudaStreamSynchronize(h->stream));
+    free_pool(h->calc_allocs);          // the previous calculator's tables
+    h->prepared = false;
+    int rc = dev_upload(h, h->calc_allocs, h->A.data(), (size_t)R, &h->dn.A);
+    rc |= dev_upload(h, h->calc_allocs, h->Ea.data(), (size_t)R, &h->dn.Ea);
     h->dn.n = nullptr;
-    if (n) rc |= dev_upload(h, h->net_allocs, h->nexp.data(), (size_t)R, &h->dn.n);
+    if (n) rc |= dev_upload(h, h->calc_allocs, h->nexp.data(), (size_t)R, &h->dn.n);
     if (rc) return rc;
     h->dn.k_max = k_max; h->dn.t_mult = t_mult; h->dn.calc_mode = 0;
     h->calc_mode = 0;
@@ -376,8 +415,11 @@ extern "C" int32_t kb2_set_rate_table(kb2_handle h, int64_t n_rate_stops, const 
     const int64_t R = h->net.R;
     h->n_rate_stops = n_rate_stops;
     CU(h, cudaSetDevice(h->device));
-    int rc = dev_upload(h, h->net_allocs, k_table, (size_t)(n_rate_stops * R), &h->dn.ktab);
-    rc |= dev_upload(h, h->net_allocs, k_init, (size_t)R, &h->dn.kinit);
+    CU(h, cudaStreamSynchronize(h->stream));
+    free_pool(h->calc_allocs);          // the previous calculator's tables
+    h->prepared = false;
+    int rc = dev_upload(h, h->calc_allocs, k_table, (size_t)(n_rate_stops * R), &h->dn.ktab);
+    rc |= dev_upload(h, h->calc_allocs, k_init, (size_t)R, &h->dn.kinit);
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     h->dn.calc_mode = 1;
@@ -444,7 +486,7 @@ static int pick_mb(kb2_ctx *h, int64_t B)
     if (h->mb_user) return h->mb_user;
     if (const char *ev = getenv("KB2_MB")) {       // testing / tuning knob, same meaning as kb2_set_tiling
         const int v = atoi(ev);
-        if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+        if (v == 1 || v == 2 || v == 4) return v;
     }
     // four members per warp tile (32-byte sectors fully used) unless the ensemble is too small to
     // give every SM a few warps
@@ -460,8 +502,10 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
     if (B <= 0 || B >= (1 << 30)) FAIL(h, "bad ensemble size");
     if (h->ens_B == B && h->ens_Ns >= Ns) return 0;
     CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
     free_pool(h->ens_allocs);
     h->ens_B = -1;
+    h->prepared = false;          // the stop / profile tables of a prepared solve lived in this pool
     DevEns &e = h->de;
     e = DevEns{};
     e.B = (int)B;
@@ -479,12 +523,15 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
     rc |= dev_alloc(h, P, R * Bt, &e.rate);
     rc |= dev_alloc(h, P, R * Bt * (size_t)h->sym.jslots, &e.drate);
     rc |= dev_alloc(h, P, (size_t)h->sym.panels.padded * Bt, &e.lu);
+    rc |= dev_alloc(h, P, (size_t)std::max<int64_t>(h->sym.nnzJ, 1) * Bt, &e.jv);
     rc |= dev_alloc(h, P, S * Bt, &e.invd);
     rc |= dev_alloc(h, P, (size_t)std::max<int64_t>(Ns, 1) * S * Bt, &e.out_u);
     rc |= dev_alloc(h, P, S * Bt, &e.out_umax);
     rc |= dev_alloc(h, P, Bp, &e.status);
     rc |= dev_alloc(h, P, Bp * 8, &e.stats);
     rc |= dev_alloc(h, P, Bp, &h->scal);
+    rc |= dev_alloc(h, P, Bp, &e.ctl);
+    rc |= dev_alloc(h, P, (size_t)KB2_FLAG_SLOTS, &e.flags);
     if (rc) { free_pool(h->ens_allocs); return rc; }
     e.Ns = (int)Ns;
     {
@@ -495,6 +542,13 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
         e.u_smem = 0;
 #endif
     }
+    {
+        // window LU: one CTA per tile with the active submatrix in shared memory, if it fits
+        const FrontPlan &f = h->sym.fronts;
+        const size_t need = wl_smem_bytes(e.MB, f.Wr, f.Wc, f.max_nl, f.max_nu);
+        h->window_ok = f.ready && need <= h->smem_optin;
+        if (const char *ev = getenv("KB2_LU")) if (!strcmp(ev, "panel")) h->window_ok = false;   // A/B switch: left-looking block plan
+    }
     h->ens_B = B; h->ens_Ns = Ns; h->ens_mb = e.MB;
     h->ens_fixed = P.size();
     return 0;
@@ -504,7 +558,6 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
     switch (mb) {                                                     \
     case 1: { constexpr int MB = 1; __VA_ARGS__; } break;             \
     case 2: { constexpr int MB = 2; __VA_ARGS__; } break;             \
-    case 8: { constexpr int MB = 8; __VA_ARGS__; } break;             \
     default: { constexpr int MB = 4; __VA_ARGS__; } break;            \
     }
 
@@ -609,6 +662,7 @@ static int upload_uk(kb2_ctx *h, int64_t B, const double *u, const double *k)
 {
     DevEns &e = h->de;
     int rc = 0;
+    h->prepared = false;          // the kernel-level entry points overwrite the state of a prepared solve
     if (u) rc |= up_tiles(h, e.u, u, h->net.S, B);
     if (k) rc |= up_tiles(h, e.k, k, h->net.R, B);
     return rc;
@@ -643,6 +697,40 @@ extern "C" int32_t kb2_eval_rhs(kb2_handle h, int64_t B, const double *u, const 
     return 0;
 }
 
+static int launch_jac(kb2_ctx *h, int use_ctl)
+{
+    DevEns &e = h->de;
+    const int ntiles = n_tiles(e);
+    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr) + 16;
+    DISPATCH_MB(e.MB, {
+        int r = set_smem(h, k_step_jac<MB>, smem);
+        if (r) return r;
+        k_step_jac<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles, (int)smem - 16, use_ctl);
+    });
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return 0;
+}
+
+// hg: per-member 1/(h*gamma) on the device, or null (taken from the control state of the solve)
+static int launch_window_lu(kb2_ctx *h, const double *d_hg)
+{
+    DevEns &e = h->de;
+    const int ntiles = n_tiles(e);
+    const size_t smem = wl_smem_bytes(e.MB, h->df.Wr, h->df.Wc, h->df.max_nl, h->df.max_nu);
+    DISPATCH_MB(e.MB, {
+        int r = set_smem(h, k_lu_window<MB>, smem);
+        if (r) return r;
+        int per_sm = 0;
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lu_window<MB>, WL_NT, smem));
+        if (per_sm < 1) FAIL(h, "the window LU kernel does not fit on an SM");
+        k_lu_window<MB><<<std::min(ntiles, per_sm * h->sm_count), WL_NT, smem, h->stream>>>(h->dn, h->dp, h->df, e, d_hg, ntiles);
+    });
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return 0;
+}
+
 extern "C" int32_t kb2_eval_jac(kb2_handle h, int64_t B, const double *u, const double *k, double *Jval)
 {
     if (!h) return 1;
@@ -650,16 +738,9 @@ extern "C" int32_t kb2_eval_jac(kb2_handle h, int64_t B, const double *u, const 
     if (rc) return rc;
     if ((rc = upload_uk(h, B, u, k))) return rc;
     DevEns &e = h->de;
-    const int ntiles = n_tiles(e);
-    // nnzJ <= padded: the LU value storage of a tile doubles as scratch for its CSC values; the
-    // tile stride is the LU stride, so bring the whole storage back and keep the first nnzJ rows
-    DISPATCH_MB(e.MB, (k_jac<MB><<<std::min(ntiles, 32 * h->sm_count), 32, 0, h->stream>>>(h->dn, h->dp, e, ntiles)));
-    h->launches++;
-    CU(h, cudaGetLastError());
-    std::vector<double> tmp((size_t)h->sym.panels.padded * B);
-    if ((rc = down_tiles(h, tmp.data(), e.lu, (size_t)h->sym.panels.padded, B))) return rc;
+    if ((rc = launch_jac(h, 0))) return rc;
+    if ((rc = down_tiles(h, Jval, e.jv, (size_t)h->sym.nnzJ, B))) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
-    std::copy(tmp.begin(), tmp.begin() + (size_t)h->sym.nnzJ * B, Jval);
     return 0;
 }
 
@@ -702,7 +783,10 @@ extern "C" int32_t kb2_factor(kb2_handle h, int64_t B, const double *u, const do
     if ((rc = upload_uk(h, B, u, k))) return rc;
     DevEns &e = h->de;
     if ((rc = up_scal(h, hg_inv, B, 1.0))) return rc;
-    if ((rc = launch_factor(h, h->scal))) return rc;
+    if (h->window_ok) {
+        if ((rc = launch_jac(h, 0))) return rc;
+        if ((rc = launch_window_lu(h, h->scal))) return rc;
+    } else if ((rc = launch_factor(h, h->scal))) return rc;
     if (lu_out) {
         // device storage is the padded block layout: bring it back and gather the exact pattern
         const PanelPlan &pp = h->sym.panels;
@@ -736,7 +820,7 @@ extern "C" int32_t kb2_time_kernel(kb2_handle h, int32_t which, int64_t B, int32
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
     const int grid = std::min(ntiles, 32 * h->sm_count);
-    if (which == 0 || which == 3 || which == 5 || which == 6) {
+    if (which == 0 || which == 3 || (which >= 5 && which <= 8)) {
         std::vector<double> c(e.Bp, which == 0 ? 1000.0 : 1.0e6);
         int rc = up_scal(h, c.data(), e.Bp, 1.0);
         if (rc) return rc;
@@ -747,11 +831,13 @@ extern "C" int32_t kb2_time_kernel(kb2_handle h, int32_t which, int64_t B, int32
         switch (which) {
         case 0: DISPATCH_MB(e.MB, (k_rates<MB><<<grid, 32, 0, h->stream>>>(h->dn, h->dp, e, h->scal, ntiles))); h->launches++; break;
         case 1: rc = launch_rhs(h); break;
-        case 2: DISPATCH_MB(e.MB, (k_jac<MB><<<grid, 32, 0, h->stream>>>(h->dn, h->dp, e, ntiles))); h->launches++; break;
-        case 3: rc = launch_factor(h, h->scal); break;
+        case 2: rc = launch_jac(h, 0); break;
+        case 3: rc = h->window_ok ? (launch_jac(h, 0) || launch_window_lu(h, h->scal)) : launch_factor(h, h->scal); break;
         case 4: rc = launch_trisolve(h); break;
         case 5: rc = launch_factor(h, h->scal, 1); break;   // W assembly only
-        case 6: rc = launch_factor(h, h->scal, 2); break;   // LU only (on whatever the storage holds)
+        case 6: rc = launch_factor(h, h->scal, 2); break;   // block-plan LU only (on whatever the storage holds)
+        case 7: if (!h->window_ok) FAIL(h, "the window LU does not fit"); rc = launch_window_lu(h, h->scal); break;   // window LU only
+        case 8: rc = launch_factor(h, h->scal); break;      // block-plan W assembly + LU (the fallback path)
         default: FAIL(h, "unknown kernel id");
         }
         if (rc) return rc;
@@ -856,6 +942,21 @@ extern "C" int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, 
     return 0;
 }
 
+// launch shape of a phase kernel: one warp per CTA, every tile resident when the grid allows it
+template <class K>
+static int phase_grid(kb2_ctx *h, K kern, size_t smem, int ntiles, int *grid)
+{
+    int r = set_smem(h, kern, smem);
+    if (r) return r;
+    int per_sm = 0;
+    CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    if (per_sm < 1) FAIL(h, "a phase kernel does not fit on an SM");
+    *grid = std::min(ntiles, per_sm * h->sm_count);
+    return 0;
+}
+
+enum { PH_LU = 0, PH_RHS = 1, PH_SWEEP = 2, PH_END = 3, PH_JAC = 4, PH_COUNT = 5 };
+
 extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
 {
     if (!h) return 1;
@@ -864,44 +965,120 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
     const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr) + 16;
-    CU(h, cudaMemsetAsync(h->d_counter, 0, 8 * sizeof(int), h->stream));
-    CU(h, cudaEventRecord(h->ev0, h->stream));
+    const int data_bytes = (int)smem - 16;
+    int g_init = 0, g_lu = 0, g_rhs = 0, g_sweep = 0, g_end = 0, g_jac = 0, g_wl = 0;
+    const bool window = h->window_ok;
+    const size_t smem_wl = wl_smem_bytes(e.MB, h->df.Wr, h->df.Wc, h->df.max_nl, h->df.max_nu);
     DISPATCH_MB(e.MB, {
-        int r = set_smem(h, k_solve<MB>, smem);
-        if (r) return r;
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve<MB>, 32, smem);
-        if (per_sm < 1) FAIL(h, "solve kernel does not fit on an SM");
-        h->last_ctas_per_sm = per_sm;
-        // persistent warps: every resident slot pulls tiles from an atomic counter
-        int grid = std::min(ntiles, per_sm * h->sm_count);
-        // phase alignment (kb2_solve.cuh, grid_align): every attempted step starts behind a
-        // grid-wide barrier, so the warps of an SM stay in the same phase of the step.  The
-        // barrier needs every CTA resident at once: cooperative launch (fails instead of hanging).
-        int align = 1;
-        if (const char *ev = getenv("KB2_ALIGN")) align = atoi(ev);
-        if (!h->coop_ok) align = 0;
-        if (align) align = (align & 3) | (h->sm_count << 2);
-        int data_bytes = (int)smem - 16;
-        int *ctr = h->d_counter;
-        DevNet dn = h->dn; DevPlan dp = h->dp; DevEns de = e;
-        int nt = ntiles;
-        void *args[] = {&dn, &dp, &de, &nt, &ctr, &data_bytes, &align};
-        if (align) {
-            cudaError_t ce = cudaLaunchCooperativeKernel((const void *)k_solve<MB>, dim3(grid), dim3(32), args, smem, h->stream);
-            if (ce != cudaSuccess) FAIL(h, cudaGetErrorString(ce));
-        } else {
-            k_solve<MB><<<grid, 32, smem, h->stream>>>(dn, dp, de, nt, ctr, data_bytes, 0);
+        int r = phase_grid(h, k_solve_init<MB>, smem, ntiles, &g_init);
+        if (!r) r = phase_grid(h, k_step_lu<MB>, smem, ntiles, &g_lu);
+        if (!r) r = phase_grid(h, k_step_jac<MB>, smem, ntiles, &g_jac);
+        if (!r && window) {
+            r = set_smem(h, k_lu_window<MB>, smem_wl);
+            int per_sm = 0;
+            if (!r) CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lu_window<MB>, WL_NT, smem_wl));
+            if (!r && per_sm < 1) FAIL(h, "the window LU kernel does not fit on an SM");
+            g_wl = std::min(ntiles, per_sm * h->sm_count);
         }
+        if (!r) r = phase_grid(h, k_stage_rhs<MB>, smem, ntiles, &g_rhs);
+        if (!r) r = phase_grid(h, k_stage_sweep<MB>, smem, ntiles, &g_sweep);
+        if (!r) r = phase_grid(h, k_step_end<MB>, smem, ntiles, &g_end);
+        if (r) return r;
     });
+    h->last_ctas_per_sm = (g_lu + h->sm_count - 1) / h->sm_count;
+    cudaStream_t st = h->stream;
+    // phase timing: every TSAMPLE-th round is bracketed with events, kernel by kernel
+    const int TSAMPLE = 16;
+    if (h->phase_ev.empty()) {
+        h->phase_ev.resize(16);
+        for (auto &ev : h->phase_ev) CU(h, cudaEventCreate(&ev));
+    }
+    for (int q = 0; q < PH_COUNT; ++q) { h->phase_ms[q] = 0.0; h->phase_n[q] = 0; }
+    h->rounds = 0;
+    CU(h, cudaMemsetAsync(e.flags, 0, KB2_FLAG_SLOTS * sizeof(int), st));
+    CU(h, cudaEventRecord(h->ev0, st));
+    DISPATCH_MB(e.MB, (k_solve_init<MB><<<g_init, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes)));
     h->launches++;
-    CU(h, cudaEventRecord(h->ev1, h->stream));
+    CU(h, cudaGetLastError());
+    // rounds are launched in batches; flags[j] of a batch = some member is still running after
+    // round j of it.  A round on a finished ensemble is thirteen empty kernels.
+    const int NB = 16;
+    const long long max_rounds = e.maxiters + 2;       // every running member counts each round against maxiters
+    int *hflag = h->h_flag;
+    bool running = true;
+    {
+        CU(h, cudaMemcpyAsync(hflag, e.flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        running = hflag[0] != 0;
+    }
+    while (running && h->rounds < max_rounds) {
+        CU(h, cudaMemsetAsync(e.flags, 0, KB2_FLAG_SLOTS * sizeof(int), st));
+        bool sampled = false;
+        for (int j = 0; j < NB; ++j) {
+            const bool tm = !sampled && ((h->rounds + j) % TSAMPLE == TSAMPLE / 2);
+            int evi = 0;
+            if (tm) { sampled = true; CU(h, cudaEventRecord(h->phase_ev[evi++], st)); }
+            DISPATCH_MB(e.MB, {
+                if (window) {
+                    k_step_jac<MB><<<g_jac, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, 1);
+                    if (tm) cudaEventRecord(h->phase_ev[evi++], st);
+                    k_lu_window<MB><<<g_wl, WL_NT, smem_wl, st>>>(h->dn, h->dp, h->df, e, (const double *)nullptr, ntiles);
+                } else {
+                    if (tm) cudaEventRecord(h->phase_ev[evi++], st);
+                    k_step_lu<MB><<<g_lu, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes);
+                }
+                if (tm) cudaEventRecord(h->phase_ev[evi++], st);
+                for (int s = 0; s < 6; ++s) {
+                    k_stage_rhs<MB><<<g_rhs, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, s);
+                    if (tm) cudaEventRecord(h->phase_ev[evi++], st);
+                    k_stage_sweep<MB><<<g_sweep, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, s);
+                    if (tm) cudaEventRecord(h->phase_ev[evi++], st);
+                }
+                k_step_end<MB><<<g_end, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, j);
+                if (tm) cudaEventRecord(h->phase_ev[evi++], st);
+            });
+            h->launches += window ? 15 : 14;
+        }
+        CU(h, cudaGetLastError());
+        CU(h, cudaMemcpyAsync(hflag, e.flags, NB * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        int used = NB;
+        for (int j = 0; j < NB; ++j) if (!hflag[j]) { used = j + 1; break; }
+        h->rounds += used;
+        running = hflag[NB - 1] != 0 && used == NB;
+        if (sampled) {
+            float ms = 0;
+            const int map[15] = {PH_JAC, PH_LU, PH_RHS, PH_SWEEP, PH_RHS, PH_SWEEP, PH_RHS, PH_SWEEP, PH_RHS, PH_SWEEP,
+                                 PH_RHS, PH_SWEEP, PH_RHS, PH_SWEEP, PH_END};
+            for (int q = window ? 0 : 1; q < 15; ++q) {
+                CU(h, cudaEventElapsedTime(&ms, h->phase_ev[q], h->phase_ev[q + 1]));
+                h->phase_ms[map[q]] += ms;
+                h->phase_n[map[q]]++;
+            }
+        }
+    }
+    if (running) {
+        k_mark_unfinished<<<(e.B + 255) / 256, 256, 0, st>>>(e);
+        h->launches++;
+    }
+    CU(h, cudaEventRecord(h->ev1, st));
     CU(h, cudaGetLastError());
     CU(h, cudaEventSynchronize(h->ev1));
     float ms = 0;
     CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     if (ms_device) *ms_device = ms;
     h->prepared = false;      // u has been advanced in place: prepare again before another run
+    return 0;
+}
+
+extern "C" int32_t kb2_get_phase_times(kb2_handle h, double *ms_avg, int64_t *launches_sampled, int64_t *rounds)
+{
+    if (!h) return 1;
+    for (int q = 0; q < PH_COUNT; ++q) {
+        if (ms_avg) ms_avg[q] = h->phase_n[q] ? h->phase_ms[q] / (double)h->phase_n[q] : 0.0;
+        if (launches_sampled) launches_sampled[q] = h->phase_n[q];
+    }
+    if (rounds) *rounds = h->rounds;
     return 0;
 }
 

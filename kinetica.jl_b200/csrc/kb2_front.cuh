@@ -1,0 +1,306 @@
+// Window LU (sm_100a): right-looking block LU with the active submatrix in shared memory.
+//
+// One CTA of 256 threads factorises one tile of MB members at a time.  The plan (kb2_front.cpp)
+// walks the panels of the block plan in order; front P consists of the pivot block of panel P, the
+// rows below it that have P as a source block (Lrows) and its U-part columns (Ucols).  Rows and
+// columns own a slot of the window  Win[row slot][column slot][member]  from the first front that
+// touches them until they are eliminated, so the Schur complement never leaves the SM:
+//   init(P)   window entries that become live at P (row and column both active) receive their
+//             original value from the compact Jacobian values: W = I/(h*gamma) - J is never
+//             materialised in HBM; inactive entries are kept at zero
+//   B(P)      warp 0: Crout LU of the nr x nr pivot block with shuffles (pivots on L', unit U')
+//   C(P)      U strip  U'[:, j] = inv(L'_PP) w[:, j]   (one thread per column and member), and
+//             L strip  L'[i, :] = x inv(U'_PP)          (one thread per row and member), in place
+//             in the window and, once, to the panel storage in HBM that the sweeps read
+//   D(P)      W[i, j] -= sum_k L'[i, k] U'[k, j]  over Lrows x Ucols, 8 x 4 register blocks
+//   clear(P)  the slots of the pivot rows and columns are zeroed, then init(P+1) (behind one more
+//             barrier in the rare front that re-uses a slot given up by the front before it)
+// Four block barriers per front.  HBM traffic of a factorisation = the compact Jacobian values in,
+// the factors out; nothing is read twice.  Every entry receives the same updates in the same order
+// as in the left-looking block plan (tile_lu), so the two kernels agree bit for bit.
+#pragma once
+#include "kb2_kernels.cuh"
+
+namespace kb2 {
+
+struct DevFront {
+    int NF, Wr, Wc, max_nl, max_nu;
+    const int *f_info;      // FrontPlan::FREC ints per front
+    const int *lists;
+    const int2 *init;       // {window position, (J entry + 1) << 1 | is_diagonal}
+};
+
+constexpr int WL_NT = 256;          // threads per CTA
+constexpr int WL_CB = 4;            // columns of a register block of the update (rows: 8)
+constexpr int WL_PF = 4;            // original values of the next front a thread fetches ahead
+
+__host__ __device__ inline int wl_list_cap(int max_nl, int max_nu) { return 16 + 2 * max_nu + 2 * max_nl; }
+__host__ __device__ inline size_t wl_smem_bytes(int mb, int Wr, int Wc, int max_nl, int max_nu)
+{
+    return (size_t)8 * mb * ((size_t)Wr * Wc + 64 + 8) + (size_t)8 * WL_PF * WL_NT + (size_t)2 * wl_list_cap(max_nl, max_nu) * 4;
+}
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// rank-nr update of one 8 x WL_CB register block of the window.  The pivot loop is unrolled by
+// KU only: the strip values of KU pivots are in flight while the previous ones are applied (fully
+// unrolled, the compiler hoists all 8 x 12 loads and runs out of registers).
+#ifndef KB2_WL_KU
+#define KB2_WL_KU 2
+#endif
+constexpr int WL_KU = KB2_WL_KU;
+template <int MB>
+__device__ __forceinline__ void wl_update_block(double *WinM, const int *prs, const int *pcs, const int (&ro)[8], const int (&co)[WL_CB],
+                                                const bool (&rok)[8], const bool (&cok)[WL_CB], int nr, int Wc)
+{
+    // WinM = Win + m; ro[i] = row slot * Wc * MB, co[c] = column slot * MB
+    double acc[8][WL_CB];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < WL_CB; ++c) acc[i][c] = WinM[ro[i] + co[c]];
+#pragma unroll WL_KU
+    for (int k = 0; k < nr; ++k) {
+        const int pc = pcs[k] * MB, pr = prs[k] * Wc * MB;
+        double l[8], u[WL_CB];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) l[i] = WinM[ro[i] + pc];
+#pragma unroll
+        for (int c = 0; c < WL_CB; ++c) u[c] = WinM[pr + co[c]];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < WL_CB; ++c) acc[i][c] -= l[i] * u[c];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < WL_CB; ++c)
+            if (rok[i] && cok[c]) WinM[ro[i] + co[c]] = acc[i][c];
+}
+
+// hg: per-member 1/(h*gamma) (kernel-level entry point), or null: taken from the control state,
+// tiles without a running member are skipped
+template <int MB>
+__global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, DevFront fr, DevEns en, const double *hg, int ntiles)
+{
+    extern __shared__ double smem[];
+    constexpr int NX = WL_NT / MB, FREC = 12;
+    constexpr int NXL = (WL_NT - 32) / MB;                // x-threads outside warp 0: they fetch the next front's values
+    const int Wc = fr.Wc, Wr = fr.Wr;
+    double *Win = smem;                                   // [Wr*Wc][MB]
+    double *Dl = Win + (size_t)Wr * Wc * MB;              // [8][8][MB]: L'_PP (lower + pivots) and U'_PP (strict upper) of the front
+    double *dinv = Dl + 64 * MB;                          // [8][MB]
+    const int LCAP = wl_list_cap(fr.max_nl, fr.max_nu);
+    double *stage = dinv + 8 * MB;                        // [WL_PF][WL_NT]: Jacobian values of the next front's new entries
+    int *lst = reinterpret_cast<int *>(stage + WL_PF * WL_NT);   // [2][LCAP]: lists of this front and the next
+    const int tid = threadIdx.x, m = tid % MB, x = tid / MB, lane = tid & 31, warp = tid >> 5;
+    const int xl = x - 32 / MB;                           // index among the x-threads outside warp 0 (negative in warp 0)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile * MB + m;
+        double hgi;
+        if (hg) hgi = hg[b];
+        else {
+            const Ctl *c = en.ctl + b;
+            if (!__syncthreads_or(c->active)) continue;
+            hgi = 1.0 / (c->hs * kGamma);
+        }
+        const double *jv = en.jv + (size_t)tile * net.nnzJ * MB;
+        double *lu = en.lu + (size_t)tile * pl.padded * MB;
+        double *invd = en.invd + (size_t)tile * net.S * MB;
+        auto init_value = [&](int src) {
+            double v = (src >> 1) ? -jv[(size_t)((src >> 1) - 1) * MB + m] : 0.0;
+            if (src & 1) v += hgi;
+            return v;
+        };
+        // ---- prologue: clear the window (inactive entries are zero from here on), lists and
+        // original values of front 0 ----
+        {
+            const int n = Wr * Wc * MB;
+            if (MB >= 2) {
+                double2 *z = reinterpret_cast<double2 *>(Win);
+                for (int i = tid; i < n / 2; i += WL_NT) z[i] = make_double2(0.0, 0.0);
+                if (tid == 0 && (n & 1)) Win[n - 1] = 0.0;
+            } else {
+                for (int i = tid; i < n; i += WL_NT) Win[i] = 0.0;
+            }
+            const int *f = fr.f_info;
+            const int len = 16 + 2 * f[2] + 2 * f[3];
+            for (int i = tid; i < len; i += WL_NT) lst[i] = fr.lists[f[6] + i];
+            __syncthreads();
+            for (int e = x; e < f[8]; e += NX) {
+                const int2 ent = fr.init[f[7] + e];
+                Win[ent.x * MB + m] = init_value(ent.y);
+            }
+        }
+        __syncthreads();
+        for (int P = 0; P < fr.NF; ++P) {
+            const int *f = fr.f_info + (size_t)P * FREC;
+            const int nr = f[0], p0 = f[1], nu = f[2], nl = f[3], base = f[4], next = f[5];
+            const int *L0 = lst + (P & 1) * LCAP;
+            const int *prs = L0, *pcs = L0 + 8, *ucs = L0 + 16, *ujj = ucs + nu, *lrs = ujj + nu, *lgs = lrs + nl;
+            const bool has_next = P + 1 < fr.NF;
+            const int *fn = f + (has_next ? FREC : 0);
+            const int ni = has_next ? fn[8] : 0, ioff = fn[7], hot = has_next ? fn[9] : 0;
+            // ---- look ahead: the next front's lists go to the other buffer (cp.async); its original
+            // values are fetched by the warps that wait for the pivot block anyway ----
+            if (has_next) {
+                int *L1 = lst + ((P + 1) & 1) * LCAP;
+                const int len = 16 + 2 * fn[2] + 2 * fn[3];
+                for (int i = tid; i < len; i += WL_NT) cp_async4(L1 + i, fr.lists + fn[6] + i);
+            }
+            int ppos[WL_PF], psrc[WL_PF];
+#pragma unroll
+            for (int q = 0; q < WL_PF; ++q) { ppos[q] = -1; psrc[q] = 0; }
+            if (warp == 0) {
+                cp_async_commit();
+                // ---- B: pivot block (lane = row * MB + member) ----
+                const int ln = lane / MB;
+                const bool own = ln < nr;
+                double D[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) D[j] = (own && j < nr) ? Win[(prs[ln] * Wc + pcs[j]) * MB + m] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < nr) {
+                        const double piv = __shfl_sync(FULL, D[j], j * MB + m);
+                        const double inv = 1.0 / piv;
+                        if (ln == j) { invd[(p0 + j) * MB + m] = inv; dinv[j * MB + m] = inv; }
+#pragma unroll
+                        for (int i = j + 1; i < 8; ++i) {
+                            const double uji = __shfl_sync(FULL, D[i], j * MB + m) * inv;
+                            if (ln == j) D[i] = uji;
+                            else if (ln > j && ln < 8) D[i] -= D[j] * uji;
+                        }
+                    }
+                }
+                if (own) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < nr) {
+                            Dl[(ln * 8 + j) * MB + m] = D[j];
+                            lu[((size_t)base + (size_t)(next + j) * nr + ln) * MB + m] = D[j];
+                        }
+                }
+            } else {
+                // the Jacobian values of the next front's new entries fly straight into shared memory
+                // (cp.async: no register waits for them) and are consumed after the update
+#pragma unroll
+                for (int q = 0; q < WL_PF; ++q) {
+                    const int e = xl + q * NXL;
+                    int2 ent = make_int2(-1, 0);
+                    if (e < ni) ent = fr.init[ioff + e];
+                    ppos[q] = ent.x; psrc[q] = ent.y;
+                }
+#pragma unroll
+                for (int q = 0; q < WL_PF; ++q)
+                    if (ppos[q] >= 0 && (psrc[q] >> 1)) cp_async8(stage + q * WL_NT + tid, jv + (size_t)((psrc[q] >> 1) - 1) * MB + m);
+                cp_async_commit();
+            }
+            __syncthreads();
+            // ---- C: strips, in place ----
+            for (int t = x; t < nu + nl; t += NX) {
+                if (t < nu) {
+                    const int col = ucs[t];
+                    double w[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) w[r] = r < nr ? Win[(prs[r] * Wc + col) * MB + m] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        if (r < nr) {
+#pragma unroll
+                            for (int a = 0; a < r; ++a) w[r] -= Dl[(r * 8 + a) * MB + m] * w[a];
+                            w[r] *= dinv[r * MB + m];
+                        }
+                    }
+                    double *g = lu + ((size_t)base + (size_t)(next + nr + ujj[t]) * nr) * MB + m;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if (r < nr) { Win[(prs[r] * Wc + col) * MB + m] = w[r]; g[r * MB] = w[r]; }
+                } else {
+                    const int ii = t - nu, row = lrs[ii] * Wc, gs = lgs[ii];
+                    double X[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) X[q] = q < nr ? Win[(row + pcs[q]) * MB + m] : 0.0;
+#pragma unroll
+                    for (int a = 0; a < 7; ++a)
+#pragma unroll
+                        for (int q = a + 1; q < 8; ++q)
+                            if (q < nr) X[q] -= X[a] * Dl[(a * 8 + q) * MB + m];
+                    double *g = lu + (size_t)(gs & 0x0fffffff) * MB + m;
+                    const int stride = ((gs >> 28) + 1) * MB;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q < nr) { Win[(row + pcs[q]) * MB + m] = X[q]; g[q * stride] = X[q]; }
+                }
+            }
+            __syncthreads();
+            // ---- D: rank-nr update of Lrows x Ucols ----
+            if (nu > 0 && nl > 0) {
+                const int ncb = (nu + WL_CB - 1) / WL_CB, nrb = (nl + 7) / 8;
+                for (int t = x; t < nrb * ncb; t += NX) {
+                    const int rb = t / ncb, cb = t - rb * ncb;
+                    int ro[8], co[WL_CB];
+                    bool rok[8], cok[WL_CB];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { rok[i] = rb * 8 + i < nl; ro[i] = lrs[min(rb * 8 + i, nl - 1)] * Wc * MB; }
+#pragma unroll
+                    for (int c = 0; c < WL_CB; ++c) { cok[c] = cb + c * ncb < nu; co[c] = ucs[min(cb + c * ncb, nu - 1)] * MB; }
+                    wl_update_block<MB>(Win + m, prs, pcs, ro, co, rok, cok, nr, Wc);
+                }
+            }
+            __syncthreads();
+            // ---- the pivot rows and columns of P are dead: clear their slots (inactive entries stay
+            // zero), then the next front's original values (which may land in those slots) ----
+            for (int r = 0; r < nr; ++r) {
+                double *row = Win + (size_t)prs[r] * Wc * MB + m, *col = Win + (size_t)pcs[r] * MB + m;
+                for (int z = x; z < Wc; z += NX) row[z * MB] = 0.0;
+                for (int z = x; z < Wr; z += NX) col[(size_t)z * Wc * MB] = 0.0;
+            }
+            cp_async_wait_all();
+            if (hot) __syncthreads();
+#pragma unroll
+            for (int q = 0; q < WL_PF; ++q)
+                if (ppos[q] >= 0) {
+                    double v = (psrc[q] >> 1) ? -stage[q * WL_NT + tid] : 0.0;
+                    if (psrc[q] & 1) v += hgi;
+                    Win[ppos[q] * MB + m] = v;
+                }
+            if (xl >= 0)
+                for (int e = xl + WL_PF * NXL; e < ni; e += NXL) {
+                    const int2 ent = fr.init[ioff + e];
+                    Win[ent.x * MB + m] = init_value(ent.y);
+                }
+            __syncthreads();
+        }
+    }
+}
+
+// compact Jacobian values of every tile, CSC order, tile-major [tile][nnzJ][MB] (input of the window LU)
+template <int MB>
+__global__ void __launch_bounds__(32) k_step_jac(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes, int use_ctl)
+{
+    extern __shared__ double smem[];
+    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        WTile<MB> tl(tile, net, pl, en, ch);
+        if (use_ctl && !__any_sync(FULL, en.ctl[tl.b].active)) continue;
+        const double *u = tl.u;
+        if (en.u_smem) {
+            if (tl.ch.bar) {
+                bulk_issue(tl.ch, smem, u, (unsigned)(net.S * MB * 8), tl.lane, true);
+                bulk_wait(tl.ch, tl.lane);
+            } else {
+                for (int i = tl.lane; i < net.S * MB; i += 32) smem[i] = u[i];
+                __syncwarp();
+            }
+            u = smem;
+        }
+        tile_jac_csc(tl, net, u, en.jv + (size_t)tile * net.nnzJ * MB);
+    }
+}
+
+}  // namespace kb2

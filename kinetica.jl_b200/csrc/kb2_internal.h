@@ -49,6 +49,29 @@ struct PanelPlan {
     int64_t n_tasks() const { return (int64_t)t_info.size() / TREC; }
 };
 
+// Front plan of the window LU (kb2_front.cpp): the same factorisation as the block plan, right-
+// looking, with the active submatrix (rows and columns that have received or will receive
+// updates and are not eliminated yet) resident in shared memory.  Front P = panel P: its pivot
+// block, the rows below it that have P as a source block (Lrows) and its U-part columns (Ucols).
+// Rows and columns own a window slot from their first touch until they are eliminated.
+struct FrontPlan {
+    bool ready = false;
+    int32_t NF = 0, Wr = 0, Wc = 0, max_nl = 0, max_nu = 0, max_init = 0;
+    static constexpr int FREC = 12;
+    // per front: {nr, first pivot row, nu, nl, base slot of the panel, position of the diagonal block,
+    //             offset into `lists`, offset into `init` (entries), init entries,
+    //             1 if a row/column of this front takes a slot that the previous front gave up, 0, 0}
+    std::vector<int32_t> f_info;
+    // per front, at its offset: prs[8] pcs[8] (window slots of the pivot rows / columns, -1 beyond nr),
+    // ucs[nu] (column slots of Ucols, ascending), ujj[nu] (position of that column in the panel's U
+    // part), lrs[nl] (row slots of Lrows), lgs[nl] (storage slot of L'(row, first pivot column) |
+    // (rows of that row's panel - 1) << 28: the stride between pivots)
+    std::vector<int32_t> lists;
+    // window entries that become live when front P starts and have an original value (inactive
+    // entries are zero): {window position rslot*Wc + cslot, (J entry + 1) << 1 | is_diagonal}
+    std::vector<int32_t> init;
+};
+
 // Everything the kernels need that depends only on the network (shared by all members).
 struct Symbolic {
     bool ready = false;
@@ -86,6 +109,7 @@ struct Symbolic {
     std::vector<int32_t> lu_rowptr, lu_colidx, lu_diagpos;
     int32_t max_rowlen = 0;
     PanelPlan panels;
+    FrontPlan fronts;
 };
 
 // Builds derived stoichiometry; returns "" or an error message.
@@ -93,5 +117,6 @@ std::string build_network(Network &net);
 // ordering: 0 min degree, 1 natural, 2 user (sym.perm preset)
 std::string build_symbolic(const Network &net, int ordering, Symbolic &sym);
 std::string build_panels(Symbolic &sym, int64_t S);
+std::string build_fronts(Symbolic &sym, int64_t S);
 
 }  // namespace kb2

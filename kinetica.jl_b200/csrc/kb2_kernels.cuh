@@ -1,7 +1,7 @@
 // CUDA kernels of the kinetic-solve hot path (sm_100a).
 //
 // Execution model: ONE WARP integrates one tile of MB consecutive ensemble members (MB in
-// {1,2,4,8}) from t0 to the end; lane = ln * MB + m with m the member inside the tile and ln one
+// {1,2,4}) from t0 to the end; lane = ln * MB + m with m the member inside the tile and ln one
 // of LN = 32/MB work lanes of that member.  A CTA is a single warp and the data path has no block
 // barrier, only __syncwarp and shuffles, so the scheduler can keep every tile of the ensemble
 // resident at once; the one place where warps wait for each other is the grid-wide phase
@@ -23,7 +23,7 @@ constexpr double kNA = 6.02214076e23;    // reference src/constants.jl:5
 constexpr double kGamma = 0.25;          // Rodas4
 
 // Rodas4 (Hairer & Wanner RODAS) in transformed K-form; verified against the order
-// conditions in tests/test_rodas_tableau.py.
+// conditions in tests/test_oracle_golden.py::test_rodas4_tableau_order_conditions.
 __constant__ double cA[6][6] = {
     {0, 0, 0, 0, 0, 0},
     {0.1544000000000000e+01, 0, 0, 0, 0, 0},
@@ -70,6 +70,14 @@ struct DevPlan {
     const int *map;           // (column position in Q) | (column position in the chunk << 16)
 };
 
+// Control state of one member between the phase kernels of a step (kb2_solve.cuh).
+struct Ctl {
+    double t, h, hs, hold, errold, T, hfirst;
+    long long iters;
+    int ns, si, isave, status, hit, active, rejlast, firstacc, accept, upd, ridx, sav, fresh;
+    int nacc, nrej, nlu, nrhs;
+};
+
 // Ensemble state.  Every per-member array is TILE-MAJOR: [tile][index][MB] with MB members per
 // tile (species / reaction / LU-slot major, member minor inside the tile), so one warp owns one
 // contiguous block per array and every access of the warp covers whole MB*8-byte segments.
@@ -77,6 +85,7 @@ struct DevEns {
     int B, Bp, MB;
     int u_smem;               // 1: a tile's state vector (S*MB doubles) fits the warp's shared memory and is staged there for the gathers
     double *u, *ua, *rv, *y, *K[6], *k, *rate, *drate, *lu, *invd;
+    double *jv;               // compact Jacobian values, CSC order: [tile][nnzJ][MB]
     // conditions
     int nstops;               // row length of the per-member stop tables
     const double *stop_t;     // [b*nstops + s]
@@ -89,6 +98,8 @@ struct DevEns {
     double *out_u, *out_umax; // [tile][s][i][MB], [tile][i][MB]
     int *status;
     long long *stats;
+    Ctl *ctl;                 // [Bp]
+    int *flags;               // [KB2_FLAG_SLOTS] members still running at the start of a round (host loop control)
     // controls
     double t0, abstol, reltol, dtmin;
     long long maxiters;

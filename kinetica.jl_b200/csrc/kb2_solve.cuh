@@ -78,17 +78,6 @@ __global__ void __launch_bounds__(32) k_rhs(DevNet net, DevPlan pl, DevEns en, i
     }
 }
 
-// Jacobian values in CSC order, written tile-major into the (larger) LU storage of the tile
-template <int MB>
-__global__ void __launch_bounds__(32) k_jac(DevNet net, DevPlan pl, DevEns en, int ntiles)
-{
-    BulkChan ch; ch.bar = 0; ch.par = nullptr;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        WTile<MB> tl(tile, net, pl, en, ch);
-        tile_jac_csc(tl, net, tl.u, tl.lu);
-    }
-}
-
 template <int MB>
 __global__ void __launch_bounds__(32) k_factor(DevNet net, DevPlan pl, DevEns en, const double *hg_inv, int ntiles, int mode, int data_bytes)
 {
@@ -121,21 +110,21 @@ __global__ void k_profile(int B, int nt, const int *kind, const double *params, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// The fused solve: one warp integrates one tile of MB members from t0 to the last stop.
-// Rodas4 with per-member adaptive h; accept/reject and stop handling are masked per member while
-// the tile moves in lock-step.  The control state of a member is replicated in the registers of
-// its LN lanes (same inputs, same arithmetic, same decisions).  Replaces init/solve!/reinit! of
-// `pars.solver` and the PresetTimeCallback rate update (reference src/solving/methods.jl:655-714,
-// src/solving/solve_utils.jl:376-450).
+// The solve: Rodas4 with per-member adaptive h, as a sequence of PHASE KERNELS per attempted step
+//     k_step_lu | 6 x ( k_stage_rhs(s) | k_stage_sweep(s) ) | k_step_end
+// launched back to back on one stream by the host loop of kb2_solve_run.  Every kernel walks the
+// tiles of the ensemble (one warp-tile of MB members at a time); the control state of a member
+// (Ctl) lives in global memory between kernels and is replicated in the registers of the member's
+// lanes inside one (same inputs, same arithmetic, same decisions on every lane).  Accept/reject
+// and stop handling are masked per member while a tile moves in lock-step; a tile without a
+// running member is skipped by every kernel.  Kernel boundaries keep all tiles in the same phase
+// of the step (each phase has its own code and arrays: instruction cache, L2 and TLB see one
+// working set at a time) and give every phase its own launch shape, registers and shared memory.
+// Replaces init/solve!/reinit! of `pars.solver` and the PresetTimeCallback rate update
+// (reference src/solving/methods.jl:655-714, src/solving/solve_utils.jl:376-450).
 // ---------------------------------------------------------------------------------------------
-struct Ctl {
-    double t, h, hs, hold, errold, T, hfirst;
-    long long iters;
-    int ns, si, isave, status, hit, active, rejlast, firstacc, accept, upd, ridx, sav, fresh;
-    int nacc, nrej, nlu, nrhs;
-};
-
 enum { ST_RUNNING = -1 };
+constexpr int KB2_FLAG_SLOTS = 64;
 
 template <int MB>
 __device__ void tile_process_stop(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, bool at_start)
@@ -220,131 +209,150 @@ __device__ void tile_restart_h(const WTile<MB> &tl, const DevNet &net, const Dev
     if (upd && c.hfirst > 0.0) c.h = fmin(c.h, c.hfirst);
 }
 
-// Phase alignment.  All warps run the same sequence of phases per attempted step (assembly,
-// factorisation, six stage evaluations + sweeps), each with its own code (the factorisation alone
-// is larger than the 32 KB L1.5 instruction cache) and its own arrays.  Left alone, the seven
-// warps of an SM drift into seven different phases and thrash the instruction cache and the TLB:
-// measured on C3, the step cost grows from 33 ms (first steps, still aligned) to ~60 ms.  A
-// grid-wide barrier in front of every attempted step keeps them together.  A warp that has run
-// out of tiles keeps arriving until every warp has (the releasing warp publishes that in bit 0 of
-// the generation word, so that all warps take the same decision).  bar[0] = arrivals,
-// bar[1] = generation << 1 | all done; `done` = warps without work, counted once each.
-struct GridAlign {
-    unsigned *bar;      // null: alignment off
-    unsigned nctas;
-    int mode;           // 1: one barrier per attempted step; 2: one more in front of every stage;
-                        // 3: two half steps (assembly + factorisation | stages), the two groups of warps half a step apart
-    int group;          // mode 3: warps of group 1 run half a step behind those of group 0
-};
-__device__ __forceinline__ bool grid_align(const GridAlign &ga, bool finished)
+// What the next attempted step of a member is: its size hs (cut at the next stop), whether it
+// ends on the stop, or why the member stops running (maxiters, dtmin: methods.jl:164-165).
+__device__ __forceinline__ void plan_attempt(const DevEns &en, Ctl &c, int b)
 {
-    if (!ga.bar) return finished;
-    unsigned word = 0;
-    if ((threadIdx.x & 31) == 0) {
-        volatile unsigned *vb = ga.bar;
-        const unsigned g = vb[1];
-        if (finished) atomicAdd(ga.bar + 2, 1u);
-        __threadfence();
-        if (atomicAdd(ga.bar, 1u) == ga.nctas - 1) {
-            // last to arrive: everybody's `done` increments of this round are visible here
-            const unsigned alldone = (vb[2] >= ga.nctas) ? 1u : 0u;
-            vb[2] = 0;                       // recounted every round: finished warps re-announce themselves
-            vb[0] = 0;
-            __threadfence();
-            word = ((g >> 1) + 1) << 1 | alldone;
-            vb[1] = word;
-        } else {
-            while ((word = vb[1]) == g) __nanosleep(200);
+    int act = (c.status == ST_RUNNING);
+    double hs = 1.0;
+    int hit = 0;
+    if (act) {
+        if (++c.iters > en.maxiters) { c.status = 1; act = 0; }
+        else {
+            const double tstop = en.stop_t[(size_t)b * en.nstops + c.si];
+            hs = c.h;
+            if (c.t + 1.01 * hs >= tstop) { hs = tstop - c.t; hit = 1; }
+            if (hs < en.dtmin && !hit) { c.status = 2; act = 0; hs = 1.0; }
         }
-        __threadfence();
     }
-    word = __shfl_sync(FULL, word, 0);
-    return (word & 1u) != 0;
+    c.active = act; c.hs = hs; c.hit = hit; c.accept = 0;
+}
+
+// end of a kernel that changes the control state: one lane per member writes it back, results of
+// finished members are published, and the tile reports whether it still has work
+template <int MB>
+__device__ __forceinline__ void store_ctl(const WTile<MB> &tl, const DevEns &en, const Ctl &c, int slot)
+{
+    if (tl.ln == 0) {
+        en.ctl[tl.b] = c;
+        if (tl.b < en.B && c.status != ST_RUNNING) {
+            en.status[tl.b] = c.status;
+            long long *st = en.stats + (size_t)tl.b * 8;
+            st[0] = c.nacc; st[1] = c.nrej; st[2] = c.nlu; st[3] = c.nrhs;
+            st[4] = c.isave; st[5] = c.si; st[6] = c.iters; st[7] = 0;
+        }
+    }
+    if (__any_sync(FULL, c.active) && tl.lane == 0) en.flags[slot] = 1;
 }
 
 template <int MB>
-__device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en, double *Wp, const BulkChan &ch, const GridAlign &ga)
+__global__ void __launch_bounds__(32) k_solve_init(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes)
 {
+    extern __shared__ double smem[];
+    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    double *su = en.u_smem ? smem : nullptr;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        WTile<MB> tl(tile, net, pl, en, ch);
+        const int b = tl.b;
+        Ctl c;
+        c.t = en.t0; c.si = 0; c.isave = 0; c.iters = 0;
+        c.ns = en.stop_cnt[b];
+        c.status = (b < en.B && c.ns > 0) ? ST_RUNNING : 0;
+        c.nacc = c.nrej = c.nlu = c.nrhs = 0;
+        c.rejlast = 0; c.firstacc = 1; c.accept = 0; c.hit = 0; c.active = 0; c.upd = 0; c.ridx = -1; c.sav = -1;
+        c.errold = 1.0; c.h = 0.0; c.hs = 1.0; c.hold = 0.0; c.hfirst = 0.0; c.fresh = 0;
+        // initial conditions: static -> value, variable -> X_start (condition_set.jl:111-121); both sit
+        // in the profile's X(0) for every supported kind
+        c.T = (net.calc_mode == 0) ? profile_eval(en.pkind[b], en.pparams + (size_t)b * 16, -1.0) : 0.0;
+        tile_rates(tl, net, c.T, true, -1);     // k(initial conditions), methods.jl:668
+        tile_process_stop(tl, net, en, c, true);
+        tile_hinit(tl, net, en, c, true, su);
+        plan_attempt(en, c, b);
+        store_ctl(tl, en, c, 0);
+    }
+}
+
+// W = I/(hs*gamma) - J(u) assembled and factorised
+template <int MB>
+__global__ void __launch_bounds__(32) k_step_lu(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes)
+{
+    extern __shared__ double smem[];
+    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        WTile<MB> tl(tile, net, pl, en, ch);
+        const Ctl *c = en.ctl + tl.b;
+        if (!__any_sync(FULL, c->active)) continue;
+        tile_assemble_w(tl, net, pl, tl.u, 1.0 / (c->hs * kGamma), en.u_smem ? smem : nullptr);
+        tile_lu(tl, pl, smem);
+    }
+}
+
+// stage s: argument ua = u + sum_{q<s} a_sq K_q (stage 6 shares stage 5's coefficients plus K5) and,
+// from the same loads, the stage combination rv = sum_{q<s} (C_sq/h) K_q; then rv += f(ua)
+template <int MB>
+__global__ void __launch_bounds__(32) k_stage_rhs(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes, int s)
+{
+    extern __shared__ double smem[];
     constexpr int LN = 32 / MB;
-    WTile<MB> tl(tile, net, pl, en, ch);
-    const int m = tl.m, b = tl.b, ln = tl.ln;
-    double *su = en.u_smem ? Wp : nullptr;      // the gathers of RHS / Jacobian read the state from shared memory
-    Ctl c;
-    c.t = en.t0; c.si = 0; c.isave = 0; c.iters = 0;
-    c.ns = en.stop_cnt[b];
-    c.status = (b < en.B && c.ns > 0) ? ST_RUNNING : 0;
-    c.nacc = c.nrej = c.nlu = c.nrhs = 0;
-    c.rejlast = 0; c.firstacc = 1; c.accept = 0; c.hit = 0; c.active = 0; c.upd = 0; c.ridx = -1; c.sav = -1;
-    c.errold = 1.0; c.h = 0.0; c.hs = 1.0; c.hold = 0.0; c.hfirst = 0.0; c.fresh = 0;
-    // initial conditions: static -> value, variable -> X_start (condition_set.jl:111-121); both sit
-    // in the profile's X(0) for every supported kind
-    c.T = (net.calc_mode == 0) ? profile_eval(en.pkind[b], en.pparams + (size_t)b * 16, -1.0) : 0.0;
-    tile_rates(tl, net, c.T, true, -1);     // k(initial conditions), methods.jl:668
-    tile_process_stop(tl, net, en, c, true);
-    tile_hinit(tl, net, en, c, true, su);
-    const size_t sb = (size_t)b * en.nstops;
-    if (ga.mode == 3 && ga.group == 1) grid_align(ga, false);      // half a step behind group 0
-    // ---- main loop ----
-    for (;;) {
-        {
-            int act = (c.status == ST_RUNNING);
-            double hs = 1.0;
-            int hit = 0;
-            if (act) {
-                if (++c.iters > en.maxiters) { c.status = 1; act = 0; }
-                else {
-                    const double tstop = en.stop_t[sb + c.si];
-                    hs = c.h;
-                    if (c.t + 1.01 * hs >= tstop) { hs = tstop - c.t; hit = 1; }
-                    if (hs < en.dtmin && !hit) { c.status = 2; act = 0; hs = 1.0; }
-                }
-            }
-            c.active = act; c.hs = hs; c.hit = hit; c.accept = 0;
-        }
-        if (!__any_sync(FULL, c.active)) break;
-        grid_align(ga, false);
-        const double hs = c.hs;
-        tile_assemble_w(tl, net, pl, tl.u, 1.0 / (hs * kGamma), su);
-        {
-            // the factorisation needs every register it can get: give it a tile view of its own,
-            // recomputed behind an optimisation barrier, so that the pointers of the other phases
-            // are not kept alive across it
-            int tile_lu_ = tile;
-            asm volatile("" : "+r"(tile_lu_));
-            const WTile<MB> tlu(tile_lu_, net, pl, en, ch);
-            tile_lu(tlu, pl, Wp);
-        }
-        if (ga.mode == 3) grid_align(ga, false);
-        for (int s = 0; s < 6; ++s) {
-            const double *Us = tl.u;
-            if (s > 0) {
-                // ua = u + sum_{q<s} a_sq K_q  (stage 6 shares stage 5's coefficients plus K5) and, from
-                // the same loads, the stage combination rv = sum_{q<s} (C_sq/h) K_q that the right-hand
-                // side is added to
-                const double ih = 1.0 / hs;
-                const double a0 = cA[s][0], a1 = cA[s][1], a2 = cA[s][2], a3 = cA[s][3], a4 = cA[s][4];
-                const double c0 = cC[s][0] * ih, c1 = cC[s][1] * ih, c2 = cC[s][2] * ih, c3 = cC[s][3] * ih, c4 = cC[s][4] * ih;
+    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        WTile<MB> tl(tile, net, pl, en, ch);
+        const Ctl *c = en.ctl + tl.b;
+        if (!__any_sync(FULL, c->active)) continue;
+        const int m = tl.m, ln = tl.ln;
+        const double *Us = tl.u;
+        if (s > 0) {
+            const double ih = 1.0 / c->hs;
+            const double a0 = cA[s][0], a1 = cA[s][1], a2 = cA[s][2], a3 = cA[s][3], a4 = cA[s][4];
+            const double c0 = cC[s][0] * ih, c1 = cC[s][1] * ih, c2 = cC[s][2] * ih, c3 = cC[s][3] * ih, c4 = cC[s][4] * ih;
 #pragma unroll 4
-                for (int i = ln; i < net.S; i += LN) {
-                    const int o = i * MB + m;
-                    const double k0 = tl.K[0][o];
-                    double a = tl.u[o] + a0 * k0, r = c0 * k0;
-                    if (s > 1) { const double kq = tl.K[1][o]; a += a1 * kq; r += c1 * kq; }
-                    if (s > 2) { const double kq = tl.K[2][o]; a += a2 * kq; r += c2 * kq; }
-                    if (s > 3) { const double kq = tl.K[3][o]; a += a3 * kq; r += c3 * kq; }
-                    if (s > 4) { const double kq = tl.K[4][o]; a += a4 * kq; r += c4 * kq; }
-                    tl.ua[o] = a;
-                    tl.rv[o] = r;
-                }
-                __syncwarp();
-                Us = tl.ua;
+            for (int i = ln; i < net.S; i += LN) {
+                const int o = i * MB + m;
+                const double k0 = tl.K[0][o];
+                double a = tl.u[o] + a0 * k0, r = c0 * k0;
+                if (s > 1) { const double kq = tl.K[1][o]; a += a1 * kq; r += c1 * kq; }
+                if (s > 2) { const double kq = tl.K[2][o]; a += a2 * kq; r += c2 * kq; }
+                if (s > 3) { const double kq = tl.K[3][o]; a += a3 * kq; r += c3 * kq; }
+                if (s > 4) { const double kq = tl.K[4][o]; a += a4 * kq; r += c4 * kq; }
+                tl.ua[o] = a;
+                tl.rv[o] = r;
             }
-            if (ga.mode >= 2) grid_align(ga, false);
-            tile_rhs(tl, net, Us, tl.rv, s > 0, su);
-            double *Ks = s == 0 ? tl.K[0] : s == 1 ? tl.K[1] : s == 2 ? tl.K[2] : s == 3 ? tl.K[3] : s == 4 ? tl.K[4] : tl.K[5];
-            tile_trisolve(tl, net, pl, tl.rv, Ks, su);
+            __syncwarp();
+            Us = tl.ua;
         }
-        // error estimate = K6; new solution = ua + K6
+        tile_rhs(tl, net, Us, tl.rv, s > 0, en.u_smem ? smem : nullptr);
+    }
+}
+
+// stage s: K_s = W^-1 rv
+template <int MB>
+__global__ void __launch_bounds__(32) k_stage_sweep(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes, int s)
+{
+    extern __shared__ double smem[];
+    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        WTile<MB> tl(tile, net, pl, en, ch);
+        if (!__any_sync(FULL, en.ctl[tl.b].active)) continue;
+        tile_trisolve(tl, net, pl, tl.rv, tl.K[s], en.u_smem ? smem : nullptr);
+    }
+}
+
+// error estimate (= K6), controller, commit, stop handling (rate update, saves), and the plan of
+// the next attempt
+template <int MB>
+__global__ void __launch_bounds__(32) k_step_end(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes, int slot)
+{
+    extern __shared__ double smem[];
+    constexpr int LN = 32 / MB;
+    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    double *su = en.u_smem ? smem : nullptr;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        WTile<MB> tl(tile, net, pl, en, ch);
+        if (!__any_sync(FULL, en.ctl[tl.b].active)) continue;
+        Ctl c = en.ctl[tl.b];
+        const int m = tl.m, ln = tl.ln;
+        const double hs = c.hs;
+        const size_t sb = (size_t)tl.b * en.nstops;
         double e2 = 0.0;
         int neg = 0;
         for (int i = ln; i < net.S; i += LN) {
@@ -391,39 +399,22 @@ __device__ void solve_tile(int tile, const DevNet &net, const DevPlan &pl, const
         __syncwarp();
         tile_process_stop(tl, net, en, c, false);
         if (__any_sync(FULL, c.upd)) tile_restart_h(tl, net, en, c, su);
+        plan_attempt(en, c, tl.b);
+        store_ctl(tl, en, c, slot);
     }
-    if (ln == 0 && b < en.B) {
-        en.status[b] = c.status == ST_RUNNING ? 5 : c.status;
-        long long *st = en.stats + (size_t)b * 8;
-        st[0] = c.nacc; st[1] = c.nrej; st[2] = c.nlu; st[3] = c.nrhs;
-        st[4] = c.isave; st[5] = c.si; st[6] = 0; st[7] = 0;
-    }
-    __syncwarp();
 }
 
-#ifndef KB2_MINB2
-#define KB2_MINB2 1           // minimum resident warps per SM requested for the MB = 2 instantiation of k_solve
-#endif
-template <int MB>
-__global__ void __launch_bounds__(32, MB == 2 ? KB2_MINB2 : 1) k_solve(DevNet net, DevPlan pl, DevEns en, int ntiles, int *tile_counter, int data_bytes, int align)
+// members the loop gave up on (host-side round limit): status 5
+__global__ void k_mark_unfinished(DevEns en)
 {
-    extern __shared__ double smem[];
-    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
-    GridAlign ga;
-    ga.bar = align ? reinterpret_cast<unsigned *>(tile_counter) + 1 : nullptr;
-    ga.nctas = gridDim.x;
-    ga.mode = align & 3;
-    ga.group = (align & 3) == 3 ? ((blockIdx.x / max(align >> 2, 1)) & 1) : 0;    // align >> 2 = number of SMs
-    for (;;) {
-        int tile = 0;
-        if ((threadIdx.x & 31) == 0) tile = atomicAdd(tile_counter, 1);
-        tile = __shfl_sync(FULL, tile, 0);
-        if (tile >= ntiles) break;
-        solve_tile<MB>(tile, net, pl, en, smem, ch, ga);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= en.B) return;
+    const Ctl &c = en.ctl[b];
+    if (c.status == ST_RUNNING) {
+        en.status[b] = 5;
+        long long *st = en.stats + (size_t)b * 8;
+        st[0] = c.nacc; st[1] = c.nrej; st[2] = c.nlu; st[3] = c.nrhs; st[4] = c.isave; st[5] = c.si; st[6] = c.iters; st[7] = 0;
     }
-    // out of tiles: keep the barrier complete until every warp is
-    if (ga.bar)
-        while (!grid_align(ga, true)) { }
 }
 
 }  // namespace kb2

@@ -1,4 +1,4 @@
-"""Short fused solve for ncu: C3 network, B members, a few stops."""
+"""Short solve for ncu / phase timing: C3 network, B members, a few stops."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -11,7 +11,7 @@ maxit = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
 sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + int(os.environ.get('KB2_CID', '3')))
 calc = kb.PrecalculatedArrheniusCalculator(Ea, A, k_max=1e12)
 pars = kb.ODESimulationParams(tspan=(0.0, tf), u0=synthetic_u0(S), save_interval=tf / 2, low_k_cutoff="none",
-                              solve_chunks=False, abstol=1e-8, reltol=1e-6, maxiters=maxit)
+                              solve_chunks=False, abstol=float(os.environ.get('KB2_ATOL', '1e-10')), reltol=float(os.environ.get('KB2_RTOL', '1e-8')), maxiters=maxit)
 conds = [kb.ConditionSet({"T": kb.LinearDirectProfile(rate=100.0, X_start=600.0 + 600.0 * b / (B - 1), X_end=700.0 + 600.0 * b / (B - 1))},
                          ts_update=1e-2) for b in range(B)]
 for cs in conds:
@@ -22,4 +22,6 @@ for rep in range(2):
     es.prepare(conds, pars, synthetic_u0(S))
     ms = es.run()
     out_u, umax, status, stats = es.fetch()
-    print(f"rep{rep} run {ms:.1f} ms; attempts mean {stats[:,2].mean():.1f} max {stats[:,2].max()}; ok {np.sum(status==0)}/{B}")
+    ph, rounds = es.h.get_phase_times()
+    print(f"rep{rep} run {ms:.1f} ms; attempts mean {stats[:,2].mean():.1f} max {stats[:,2].max()}; ok {np.sum(status==0)}/{B}; rounds {rounds}; ms/round {ms/max(rounds,1):.3f}")
+    print("   phases:", {k: round(v["ms"], 3) for k, v in ph.items()}, "per round:", round(ph["jacobian"]["ms"] + ph["lu"]["ms"] + 6 * (ph["stage_rhs"]["ms"] + ph["stage_sweeps"]["ms"]) + ph["step_end"]["ms"], 3))

@@ -1,0 +1,139 @@
+"""Host-side check of the front plan of the window LU (kb2_front.cpp): a numpy interpreter executes
+the plan tables the way k_lu_window does (window slots, init entries, pivot block, strips, rank-nr
+update) on one random member, starting from the COMPACT Jacobian values, and must reproduce the
+result of the block plan interpreter (tests/test_block_plan.py): both schedules apply the same
+updates to every entry in the same order.  Needs no GPU."""
+import numpy as np
+import pytest
+
+from kinetica_b200 import _lib
+from kinetica_b200.synthetic import synthetic_crn, SEED_BASE
+from oracle import kinetica_oracle as ko
+from test_block_plan import run_plan
+
+
+def run_fronts(fp, plan, jv, hg_inv, padded):
+    """Window LU of one member: returns (lu storage, invd) like run_plan."""
+    Wr, Wc = fp["Wr"], fp["Wc"]
+    win = np.zeros(Wr * Wc)                        # inactive entries are zero
+    lu = np.full(padded, np.nan)
+    invd = {}
+    lists, init = fp["lists"], fp["init"]
+    dead_prev, dead_prev_r, dead_prev_c = False, set(), set()
+    for (nr, p0, nu, nl, base, nxt, loff, ioff, icnt, hot, _b, _c) in fp["f_info"]:
+        # window entries that become live at this front and have an original value
+        touches_prev = False
+        for pos, src in init[ioff: ioff + icnt]:
+            assert win[pos] == 0.0                 # nothing was there before
+            v = -jv[(src >> 1) - 1] if (src >> 1) else 0.0
+            if src & 1:
+                v += hg_inv
+            win[pos] = v
+            touches_prev |= (pos // Wc in dead_prev_r) or (pos % Wc in dead_prev_c) if dead_prev else False
+        assert hot or not touches_prev            # values land in a slot of the previous front only in flagged fronts
+        prs, pcs = lists[loff: loff + 8], lists[loff + 8: loff + 16]
+        ucs = lists[loff + 16: loff + 16 + nu]
+        ujj = lists[loff + 16 + nu: loff + 16 + 2 * nu]
+        lrs = lists[loff + 16 + 2 * nu: loff + 16 + 2 * nu + nl]
+        lgs = lists[loff + 16 + 2 * nu + nl: loff + 16 + 2 * nu + 2 * nl]
+        assert np.all(np.diff(ucs) > 0) and sorted(ujj.tolist()) == list(range(nu))
+        assert np.all(prs[:nr] >= 0) and np.all(pcs[:nr] >= 0) and np.all(prs[nr:] < 0)
+        # pivot block: Crout, pivots on L, unit diagonal on U (same operation order as tile_lu)
+        D = np.array([[win[prs[r] * Wc + pcs[j]] for j in range(nr)] for r in range(nr)])
+        for j in range(nr):
+            inv = 1.0 / D[j, j]
+            invd[p0 + j] = inv
+            D[j, j + 1:] *= inv
+            for r in range(j + 1, nr):
+                D[r, j + 1:] -= D[r, j] * D[j, j + 1:]
+        for r in range(nr):
+            for j in range(nr):
+                lu[base + (nxt + j) * nr + r] = D[r, j]
+        # U strip: U'[:, j] = inv(L') w
+        U12 = np.zeros((nr, nu))
+        for jj in range(nu):
+            w = np.array([win[prs[r] * Wc + ucs[jj]] for r in range(nr)])
+            for r in range(nr):
+                for a in range(r):
+                    w[r] -= D[r, a] * w[a]
+                w[r] *= invd[p0 + r]
+            U12[:, jj] = w
+            lu[base + (nxt + nr + ujj[jj]) * nr: base + (nxt + nr + ujj[jj] + 1) * nr] = w
+        # L strip: L'[i, :] = x inv(U'_PP)
+        L21 = np.zeros((nl, nr))
+        for ii in range(nl):
+            X = np.array([win[lrs[ii] * Wc + pcs[q]] for q in range(nr)])
+            for a in range(nr - 1):
+                for q in range(a + 1, nr):
+                    X[q] -= X[a] * D[a, q]
+            L21[ii] = X
+            slot0, stride = lgs[ii] & 0x0fffffff, (lgs[ii] >> 28) + 1
+            for q in range(nr):
+                lu[slot0 + q * stride] = X[q]
+        # rank-nr update, pivots in ascending order
+        for ii in range(nl):
+            for jj in range(nu):
+                pos = lrs[ii] * Wc + ucs[jj]
+                w = win[pos]
+                for q in range(nr):
+                    w -= L21[ii, q] * U12[q, jj]
+                win[pos] = w
+        # the pivot rows and columns are dead from here on: their slots are cleared
+        for r in range(nr):
+            win[prs[r] * Wc: (prs[r] + 1) * Wc] = 0.0
+            win[pcs[r]::Wc] = 0.0
+        dead_prev = True
+        dead_prev_r, dead_prev_c = set(prs[:nr].tolist()), set(pcs[:nr].tolist())
+    return lu, invd
+
+
+@pytest.mark.parametrize("S,R,ordering", [(96, 400, 0), (200, 1000, 3), (200, 1000, 0), (420, 2100, 3), (30, 60, 1), (64, 256, 4)])
+def test_front_plan_matches_block_plan(S, R, ordering):
+    sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + 50 + S)
+    h = _lib.Handle(-1)
+    h.set_network(S, *rd.flatten())
+    h.symbolic(ordering)
+    plan, fp, st = h.get_plan(), h.get_front_plan(), h.get_plan_stats()
+    rowptr, colidx, diagpos = h.get_lu_pattern()
+    colptr, rowval = h.get_pattern()
+    perm = h.get_ordering()
+    net = ko.Network(S, rd.id_reacs, rd.id_prods, rd.stoic_reacs, rd.stoic_prods)
+    rng = np.random.default_rng(S)
+    u = rng.uniform(0, 1, S)
+    k = 10 ** rng.uniform(-3, 3, R)
+    J = net.jac_dense(u, k)
+    hg = 50.0
+    jv = np.array([J[rowval[p], l] for l in range(S) for p in range(colptr[l], colptr[l + 1])])
+    # reference: the block plan interpreter on the assembled padded storage
+    Wp = (np.eye(S) * hg - J)[np.ix_(perm, perm)]
+    ref = np.zeros(st["padded"])
+    for i in range(S):
+        for p in range(rowptr[i], rowptr[i + 1]):
+            ref[plan["slot_of"][p]] = Wp[i, colidx[p]]
+    ref_invd = run_plan(plan, ref)
+    assert fp["NF"] == st["panels"] and fp["Wr"] > 0 and fp["Wc"] > 0
+    lu, invd = run_fronts(fp, plan, jv, hg, st["padded"])
+    assert not np.any(np.isnan(lu))                # every storage slot is written (exactly once)
+    # same updates in the same order (the interpreters differ in how they round a block product;
+    # the CUDA kernels are compared bit for bit in tests/test_gpu_kernels.py)
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(lu - ref)) <= 1e-12 * scale
+    exact = np.zeros(st["padded"], bool)
+    exact[plan["slot_of"]] = True
+    assert np.all(lu[~exact] == 0.0)              # padding stays exactly zero
+    assert np.allclose([invd[i] for i in range(S)], [ref_invd[i] for i in range(S)], rtol=1e-12)
+    h.close()
+
+
+def test_front_window_of_the_bench_network_fits_shared_memory():
+    """C3 (1k species / 5k reactions): the window of four members plus the strip buffers must fit
+    the 227 KB of shared memory a CTA can have on sm_100."""
+    sd, rd, Ea, A = synthetic_crn(1000, 5000, SEED_BASE + 3)
+    h = _lib.Handle(-1)
+    h.set_network(1000, *rd.flatten())
+    h.symbolic(4)
+    fp = h.get_front_plan()
+    MB = 4
+    need = 8 * MB * (fp["Wr"] * fp["Wc"] + 64 + 8) + 8 * (16 + 2 * fp["max_nu"] + 2 * fp["max_nl"]) + 8 * 4 * 256
+    assert need <= 227 * 1024, (fp["Wr"], fp["Wc"], fp["max_nl"], fp["max_nu"], need)
+    h.close()

@@ -117,7 +117,7 @@ def test_rhs_deterministic(small):
 
 
 @pytest.mark.parametrize("S,R,ordering,B,mb", [(96, 400, 0, 19, 0), (420, 2100, 3, 9, 1), (420, 2100, 0, 16, 4), (30, 60, 1, 3, 0),
-                                               (420, 2100, 3, 10, 2), (200, 1000, 3, 37, 4), (96, 400, 4, 8, 2), (420, 2100, 3, 19, 8), (96, 400, 0, 16, 8)])
+                                               (420, 2100, 3, 10, 2), (200, 1000, 3, 37, 4), (96, 400, 4, 8, 2), (420, 2100, 3, 19, 4), (96, 400, 0, 16, 4)])
 def test_factor_and_trisolve_panels(built, S, R, ordering, B, mb):
     """Panel LU + panel triangular solves on networks whose hub rows span several column chunks
     (S = 420: widest panel > 3 chunks), for every ordering mode and ragged member counts."""
@@ -128,7 +128,7 @@ def test_factor_and_trisolve_panels(built, S, R, ordering, B, mb):
     h = _lib.Handle(0)
     h.set_network(S, *rd.flatten())
     h.symbolic(ordering)
-    h.set_tiling(mb)        # members per warp tile: 0 auto (1 for these small ensembles), 1, 2, 4, 8
+    h.set_tiling(mb)        # members per warp tile: 0 auto (1 for these small ensembles), 1, 2, 4
     st = h.get_plan_stats()
     if S == 420:
         assert st["max_width"] > 96 and st["units"] > st["panels"]
@@ -168,6 +168,31 @@ def _factor_trisolve_check(h, net, B, seed):
                     U[i, j] = lu[p, b]
         Wp = W[np.ix_(perm, perm)]
         assert np.max(np.abs(L @ U - Wp)) <= 1e-10 * np.max(np.abs(Wp))
+
+
+@pytest.mark.parametrize("S,R,ordering,B,mb", [(96, 400, 0, 19, 0), (420, 2100, 3, 10, 2), (200, 1000, 3, 37, 4), (420, 2100, 0, 16, 4),
+                                               (1000, 5000, 4, 8, 4)])
+def test_window_lu_matches_block_plan_lu_bitwise(built, monkeypatch, S, R, ordering, B, mb):
+    """The window LU (right-looking, active submatrix in shared memory, built from the compact
+    Jacobian values) and the block-plan LU (left-looking over the assembled padded storage) apply the
+    same updates to every entry in the same order: factors and solutions must be identical bits."""
+    from kinetica_b200 import _lib
+    from kinetica_b200.synthetic import synthetic_crn, SEED_BASE
+    sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + (3 if S == 1000 else 50 + S))
+    rng = np.random.default_rng(S + B)
+    u = rng.uniform(0, 1, (S, B)); k = 10 ** rng.uniform(-3, 3, (R, B)); hg = 10 ** rng.uniform(1, 4, B)
+    rhs = rng.normal(size=(S, B))
+    res = {}
+    for mode in ("window", "panel"):
+        monkeypatch.setenv("KB2_LU", mode)
+        h = _lib.Handle(0)
+        h.set_network(S, *rd.flatten())
+        h.symbolic(ordering)
+        h.set_tiling(mb)
+        res[mode] = (h.factor(u, k, hg), h.trisolve(rhs))
+        h.close()
+    assert np.array_equal(res["window"][0], res["panel"][0])
+    assert np.array_equal(res["window"][1], res["panel"][1])
 
 
 def test_profiles_on_device(built):

@@ -113,9 +113,9 @@ def test_ensemble_vs_c_oracle(ensemble_case):
         assert np.array_equal(o.umax, np.max(np.array(o.sol.u), axis=0))
 
 
-@pytest.mark.parametrize("mb", [2, 4, 8])
+@pytest.mark.parametrize("mb", [2, 4])
 def test_tile_sizes_agree(ensemble_case, monkeypatch, mb):
-    """The ensemble solved with 2, 4 and 8 members per warp tile (the sizes large ensembles run at;
+    """The ensemble solved with 2 and 4 members per warp tile (the sizes large ensembles run at;
     this small one defaults to 1) against the 1-member-per-tile solution, ragged last tile included."""
     import kinetica_b200 as kb
     from kinetica_b200.synthetic import synthetic_u0
@@ -244,32 +244,13 @@ def test_ragged_ensemble_sizes(built):
         assert np.all(U == base[None])       # identical members: bit-identical, any tile position
 
 
-@pytest.mark.parametrize("align", ["0", "2", "3"])
-def test_phase_alignment_modes_bit_identical(ensemble_case, monkeypatch, align):
-    """The grid-wide phase-alignment barrier (kb2_solve.cuh, grid_align) only changes WHEN a warp
-    runs a step, never what it computes: every mode must reproduce the default (one barrier per
-    attempted step) bit for bit."""
-    import kinetica_b200 as kb
-    from kinetica_b200.synthetic import synthetic_u0
-    sd, rd, Ea, A, Ts, conds, outs = ensemble_case
-    monkeypatch.setenv("KB2_ALIGN", align)
-    calc = kb.PrecalculatedArrheniusCalculator(Ea, A, k_max=1e12)
-    pars = kb.ODESimulationParams(tspan=(0.0, 1.0), u0=synthetic_u0(sd.n), save_interval=0.1,
-                                  low_k_cutoff="none", solve_chunks=False, abstol=1e-12, reltol=1e-10)
-    got = kb.solve_network(kb.B200EnsembleODESolve(pars, conds, calc), sd, rd)
-    for a, b in zip(got, outs):
-        assert a.sol.retcode == "Success"
-        assert np.array_equal(np.array(a.sol.u), np.array(b.sol.u))
-        assert np.array_equal(a.sol.stats, b.sol.stats)
-
-
-def test_phase_alignment_more_tiles_than_resident_warps(built, monkeypatch):
-    """More tiles than warps fit on the GPU at once (one member per tile, 1500 tiles): warps pull
-    several tiles from the counter, warps that have run out keep the barrier complete until all have,
-    and members that need different numbers of steps (two temperatures) sit in the same launch."""
+def test_more_tiles_than_resident_warps(built, monkeypatch):
+    """More tiles than the phase kernels keep resident is fine as well (one member per tile, 6000
+    tiles: every CTA walks several tiles), with members that need different numbers of steps (two
+    temperatures) in the same launches: finished tiles are skipped, results stay bit-identical."""
     import kinetica_b200 as kb
     from kinetica_b200.synthetic import synthetic_crn, synthetic_u0, SEED_BASE
-    S, R, B = 24, 80, 1500
+    S, R, B = 24, 80, 6000
     sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + 43)
     calc = kb.PrecalculatedArrheniusCalculator(Ea, A, k_max=1e12)
     pars = kb.ODESimulationParams(tspan=(0.0, 0.2), u0=synthetic_u0(S), save_interval=0.1, low_k_cutoff="none",
@@ -283,6 +264,7 @@ def test_phase_alignment_more_tiles_than_resident_warps(built, monkeypatch):
     assert not np.array_equal(hot, cold)
     for b in range(B):
         assert np.array_equal(U[b], cold if b % 3 else hot)
-    monkeypatch.setenv("KB2_ALIGN", "0")
+    monkeypatch.setenv("KB2_MB", "4")
     ref = kb.solve_network(kb.B200EnsembleODESolve(pars, conds, calc), sd, rd)
-    assert np.array_equal(U, np.array([np.array(o.sol.u) for o in ref]))
+    # another tile size only changes the order of the per-member reductions
+    _check(np.array([np.array(o.sol.u) for o in ref]), U, rtol=1e-5)
