@@ -137,6 +137,23 @@ int32_t kb2_get_phase_times(kb2_handle h, double *ms_avg, int64_t *launches_samp
  * maxima member-major into caller-provided DEVICE buffers final_bs[b*S+i], umax_bs[b*S+i] */
 int32_t kb2_pack_results_device(kb2_handle h, double *final_bs_dev, double *umax_bs_dev);
 
+/* ---- multi-GPU: members are independent, each GPU solves a contiguous slice
+ * of the ensemble with its own handle and no communication; the one exchange is an all-gather of
+ * the final concentrations and the per-species maxima (what identify_next_seeds consumes,
+ * explore_utils.jl:344-349) over NCCL / NVLink.  NCCL is bound at run time (dlopen).
+ *   process per GPU : rank 0 calls kb2_comm_unique_id, ships the 128 bytes to the other ranks by
+ *                     any means, every rank calls kb2_comm_init_rank
+ *   single process  : kb2_comm_init_all over the handles of all devices (ncclCommInitAll)
+ * kb2_allgather_results packs the results of the last solve member-major on the device and gathers
+ * them; n = local handles (1 per process, or all of them: the calls are grouped).  Host outputs
+ * final_all[i][(r*B + b)*S + s] (r = rank) may be NULL to leave the data on the device. ---- */
+int32_t kb2_comm_unique_id(uint8_t *id128);
+int32_t kb2_comm_init_rank(kb2_handle h, int32_t nranks, int32_t rank, const uint8_t *id128);
+int32_t kb2_comm_init_all(int32_t ndev, kb2_handle *handles);
+int32_t kb2_allgather_results(kb2_handle *handles, int32_t n, double **final_all, double **umax_all);
+int32_t kb2_gathered_device(kb2_handle h, double **final_all_dev, double **umax_all_dev, float *gather_ms,
+                            int32_t *rank, int32_t *nranks);
+
 /* ---- kernel-level entry points (parity tests + per-kernel roofline) ---- */
 int32_t kb2_eval_k(kb2_handle h, int64_t B, const double *T, double *k_out);
 int32_t kb2_eval_profile(kb2_handle h, int64_t B, int64_t nt, const double *t, double *X_out);
@@ -150,6 +167,10 @@ int32_t kb2_trisolve(kb2_handle h, int64_t B, const double *rhs, double *x);
  * block-plan assembly + LU when the window does not fit), 4 trisolve, 5 block-plan W assembly,
  * 6 block-plan LU, 7 window LU alone, 8 block-plan assembly + LU */
 int32_t kb2_time_kernel(kb2_handle h, int32_t which, int64_t B, int32_t iters, float *ms_avg);
+
+/* measured FP64 FMA peak of the handle's device in TFLOP/s (dependency-free DFMA chains on every
+ * SM, CUDA-event timed): the denominator of the factorisation's FP64 fraction */
+int32_t kb2_measure_fp64_peak(kb2_handle h, double *tflops);
 
 /* tuning: members per warp tile (1, 2 or 4; 0 = auto); the second argument is reserved (pass 0) */
 int32_t kb2_set_tiling(kb2_handle h, int32_t members_per_tile, int32_t reserved);

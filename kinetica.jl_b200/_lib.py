@@ -50,6 +50,12 @@ SIGNATURES = {
     "kb2_factor": (_i32, [_H, _i64, _pf64, _pf64, _pf64, _pf64]),
     "kb2_trisolve": (_i32, [_H, _i64, _pf64, _pf64]),
     "kb2_time_kernel": (_i32, [_H, _i32, _i64, _i32, C.POINTER(C.c_float)]),
+    "kb2_comm_unique_id": (_i32, [C.POINTER(C.c_uint8)]),
+    "kb2_comm_init_rank": (_i32, [_H, _i32, _i32, C.POINTER(C.c_uint8)]),
+    "kb2_comm_init_all": (_i32, [_i32, C.POINTER(_H)]),
+    "kb2_allgather_results": (_i32, [C.POINTER(_H), _i32, C.POINTER(_pf64), C.POINTER(_pf64)]),
+    "kb2_gathered_device": (_i32, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_float), _pi32, _pi32]),
+    "kb2_measure_fp64_peak": (_i32, [_H, _pf64]),
     "kb2_set_tiling": (_i32, [_H, _i32, _i32]),
     "kb2_get_launch_info": (_i32, [_H, _pi32, _pi32]),
 }
@@ -299,6 +305,39 @@ class Handle:
     def pack_results_device(self, final_ptr, umax_ptr):
         self._ck(self._lib.kb2_pack_results_device(self._h, C.c_void_p(final_ptr), C.c_void_p(umax_ptr)))
 
+    # ---- multi-GPU ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        if load().kb2_comm_unique_id(buf) != 0:
+            raise Kb2Error("kb2_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def comm_init_rank(self, nranks: int, rank: int, uid: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(self._lib.kb2_comm_init_rank(self._h, nranks, rank, buf))
+        self._nranks = nranks
+
+    def allgather_results(self, to_host=True):
+        """All-gather of the last solve's final concentrations and per-species maxima over the
+        handle's communicator: ([nranks*B, S], [nranks*B, S]) on the host, or None, None with
+        to_host=False (results stay on the device, see gathered_device)."""
+        n = getattr(self, "_nranks", 1)
+        hs = (_H * 1)(self._h)
+        if to_host:
+            fin = np.empty((n * self._B, self.S))
+            mx = np.empty((n * self._B, self.S))
+            pf, pm = (_pf64 * 1)(_f(fin)), (_pf64 * 1)(_f(mx))
+            self._ck(self._lib.kb2_allgather_results(hs, 1, pf, pm))
+            return fin, mx
+        self._ck(self._lib.kb2_allgather_results(hs, 1, None, None))
+        return None, None
+
+    def gathered_device(self):
+        a, b, ms, r, n = C.c_void_p(), C.c_void_p(), C.c_float(), _i32(), _i32()
+        self._ck(self._lib.kb2_gathered_device(self._h, C.byref(a), C.byref(b), C.byref(ms), C.byref(r), C.byref(n)))
+        return {"final_ptr": a.value, "umax_ptr": b.value, "gather_ms": float(ms.value), "rank": r.value, "nranks": n.value}
+
     # ---- kernel-level ----
     def eval_k(self, T):
         T = _c64(np.atleast_1d(T))
@@ -335,6 +374,11 @@ class Handle:
         out = np.empty_like(rhs)
         self._ck(self._lib.kb2_trisolve(self._h, rhs.shape[1], _f(rhs), _f(out)))
         return out
+
+    def measure_fp64_peak(self) -> float:
+        v = _f64()
+        self._ck(self._lib.kb2_measure_fp64_peak(self._h, C.byref(v)))
+        return float(v.value)
 
     def time_kernel(self, which, B, iters=10) -> float:
         ms = C.c_float()

@@ -7,6 +7,9 @@
 #include "kb2_internal.h"
 #include "../../include/kinetica_b200.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -45,6 +48,9 @@ struct kb2_ctx {
     DevPlan dp{};
     DevFront df{};
     bool window_ok = false;       // the front plan's window fits the shared memory of an SM for the current tile size
+    int window_mw = 0;            // members per CTA of the window LU
+    int last_window_ctas = 0;     // resident window CTAs per SM
+    int window_stagger_ns = 0;    // start delay of the second CTA of an SM
     DevEns de{};
     int64_t ens_B = -1, ens_Ns = -1;
     size_t ens_fixed = 0;
@@ -60,6 +66,12 @@ struct kb2_ctx {
     long long phase_n[5] = {0, 0, 0, 0, 0};
     long long rounds = 0;
     int *h_flag = nullptr;        // pinned
+    // multi-GPU: one NCCL communicator per handle (kb2_comm_*), gather buffers on the device
+    ncclComm_t comm = nullptr;
+    int comm_nranks = 1, comm_rank = 0;
+    double *g_send = nullptr, *g_recv = nullptr;     // [2][B][S] packed results, [2][nranks][B][S] gathered
+    size_t g_send_cap = 0, g_recv_cap = 0;
+    float gather_ms = 0.f;
 };
 
 #define FAIL(h, msg) do { (h)->err = (msg); return 1; } while (0)
@@ -93,6 +105,8 @@ static void free_pool(std::vector<void *> &pool)
     for (void *p : pool) cudaFree(p);
     pool.clear();
 }
+
+static void kb2_comm_release(kb2_ctx *h);
 
 extern "C" int32_t kb2_create(int32_t device, kb2_handle *out)
 {
@@ -135,6 +149,9 @@ extern "C" int32_t kb2_destroy(kb2_handle h)
     free_pool(h->calc_allocs);
     free_pool(h->ens_allocs);
     cudaFree(h->stage);
+    cudaFree(h->g_send);
+    cudaFree(h->g_recv);
+    kb2_comm_release(h);
     cudaFreeHost(h->h_flag);
     for (auto &ev : h->phase_ev) cudaEventDestroy(ev);
     cudaEventDestroy(h->ev0);
@@ -544,15 +561,35 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
     }
     {
         // window LU: one CTA per tile with the active submatrix in shared memory, if it fits
+        // members per CTA (a divisor of the tile size): the largest whose window fits an SM (measured
+        // on C3: 4 members x 1 CTA per SM 8.5 ms, 2 x 2 CTAs 8.7 ms, 1 x 3 CTAs 13 ms: the update is
+        // bound by shared-memory bandwidth, which more resident warps do not add to)
         const FrontPlan &f = h->sym.fronts;
-        const size_t need = wl_smem_bytes(e.MB, f.Wr, f.Wc, f.max_nl, f.max_nu);
-        h->window_ok = f.ready && need <= h->smem_optin;
+        const size_t cap = h->smem_optin;
+        int mw = 0;
+        for (int c = e.MB; c >= 1 && !mw; c >>= 1) if (wl_smem_bytes(c, f.Wr, f.Wc, f.max_nl, f.max_nu) <= cap) mw = c;
+        if (const char *ev = getenv("KB2_MW")) {       // tuning knob
+            const int v = atoi(ev);
+            if ((v == 1 || v == 2 || v == 4) && v <= e.MB && wl_smem_bytes(v, f.Wr, f.Wc, f.max_nl, f.max_nu) <= cap) mw = v;
+        }
+        h->window_ok = f.ready && mw > 0;
+        h->window_mw = mw;
         if (const char *ev = getenv("KB2_LU")) if (!strcmp(ev, "panel")) h->window_ok = false;   // A/B switch: left-looking block plan
     }
     h->ens_B = B; h->ens_Ns = Ns; h->ens_mb = e.MB;
     h->ens_fixed = P.size();
     return 0;
 }
+
+#define DISPATCH_MW(mb, mw, ...)                                                       \
+    switch ((mb) * 8 + (mw)) {                                                         \
+    case 4 * 8 + 4: { constexpr int MB = 4, MW = 4; __VA_ARGS__; } break;              \
+    case 4 * 8 + 2: { constexpr int MB = 4, MW = 2; __VA_ARGS__; } break;              \
+    case 4 * 8 + 1: { constexpr int MB = 4, MW = 1; __VA_ARGS__; } break;              \
+    case 2 * 8 + 2: { constexpr int MB = 2, MW = 2; __VA_ARGS__; } break;              \
+    case 2 * 8 + 1: { constexpr int MB = 2, MW = 1; __VA_ARGS__; } break;              \
+    default: { constexpr int MB = 1, MW = 1; __VA_ARGS__; } break;                     \
+    }
 
 #define DISPATCH_MB(mb, ...)                                          \
     switch (mb) {                                                     \
@@ -713,19 +750,34 @@ static int launch_jac(kb2_ctx *h, int use_ctl)
 }
 
 // hg: per-member 1/(h*gamma) on the device, or null (taken from the control state of the solve)
+static int window_launch_shape(kb2_ctx *h, size_t *smem, int *grid)
+{
+    DevEns &e = h->de;
+    const int mw = h->window_mw, nwork = n_tiles(e) * (e.MB / mw);
+    *smem = wl_smem_bytes(mw, h->df.Wr, h->df.Wc, h->df.max_nl, h->df.max_nu);
+    int per_sm = 0;
+    DISPATCH_MW(e.MB, mw, {
+        int r = set_smem(h, k_lu_window<MB, MW>, *smem);
+        if (r) return r;
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lu_window<MB, MW>, WL_NT, *smem));
+    });
+    if (per_sm < 1) FAIL(h, "the window LU kernel does not fit on an SM");
+    *grid = std::min(nwork, per_sm * h->sm_count);
+    h->last_window_ctas = per_sm;
+    h->window_stagger_ns = 0;      // start delay of the second CTA of an SM: measured, no effect (KB2_WL_STAGGER to experiment)
+    if (const char *ev = getenv("KB2_WL_STAGGER")) h->window_stagger_ns = atoi(ev);
+    return 0;
+}
+
+// hg: per-member 1/(h*gamma) on the device, or null (taken from the control state of the solve)
 static int launch_window_lu(kb2_ctx *h, const double *d_hg)
 {
     DevEns &e = h->de;
-    const int ntiles = n_tiles(e);
-    const size_t smem = wl_smem_bytes(e.MB, h->df.Wr, h->df.Wc, h->df.max_nl, h->df.max_nu);
-    DISPATCH_MB(e.MB, {
-        int r = set_smem(h, k_lu_window<MB>, smem);
-        if (r) return r;
-        int per_sm = 0;
-        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lu_window<MB>, WL_NT, smem));
-        if (per_sm < 1) FAIL(h, "the window LU kernel does not fit on an SM");
-        k_lu_window<MB><<<std::min(ntiles, per_sm * h->sm_count), WL_NT, smem, h->stream>>>(h->dn, h->dp, h->df, e, d_hg, ntiles);
-    });
+    size_t smem = 0;
+    int grid = 0;
+    int rc = window_launch_shape(h, &smem, &grid);
+    if (rc) return rc;
+    DISPATCH_MW(e.MB, h->window_mw, (k_lu_window<MB, MW><<<grid, WL_NT, smem, h->stream>>>(h->dn, h->dp, h->df, e, d_hg, n_tiles(e), h->window_stagger_ns)));
     h->launches++;
     CU(h, cudaGetLastError());
     return 0;
@@ -968,18 +1020,13 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     const int data_bytes = (int)smem - 16;
     int g_init = 0, g_lu = 0, g_rhs = 0, g_sweep = 0, g_end = 0, g_jac = 0, g_wl = 0;
     const bool window = h->window_ok;
-    const size_t smem_wl = wl_smem_bytes(e.MB, h->df.Wr, h->df.Wc, h->df.max_nl, h->df.max_nu);
+    size_t smem_wl = 0;
+    if (window) { int r = window_launch_shape(h, &smem_wl, &g_wl); if (r) return r; }
     DISPATCH_MB(e.MB, {
         int r = phase_grid(h, k_solve_init<MB>, smem, ntiles, &g_init);
         if (!r) r = phase_grid(h, k_step_lu<MB>, smem, ntiles, &g_lu);
         if (!r) r = phase_grid(h, k_step_jac<MB>, smem, ntiles, &g_jac);
-        if (!r && window) {
-            r = set_smem(h, k_lu_window<MB>, smem_wl);
-            int per_sm = 0;
-            if (!r) CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lu_window<MB>, WL_NT, smem_wl));
-            if (!r && per_sm < 1) FAIL(h, "the window LU kernel does not fit on an SM");
-            g_wl = std::min(ntiles, per_sm * h->sm_count);
-        }
+
         if (!r) r = phase_grid(h, k_stage_rhs<MB>, smem, ntiles, &g_rhs);
         if (!r) r = phase_grid(h, k_stage_sweep<MB>, smem, ntiles, &g_sweep);
         if (!r) r = phase_grid(h, k_step_end<MB>, smem, ntiles, &g_end);
@@ -1022,7 +1069,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
                 if (window) {
                     k_step_jac<MB><<<g_jac, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, 1);
                     if (tm) cudaEventRecord(h->phase_ev[evi++], st);
-                    k_lu_window<MB><<<g_wl, WL_NT, smem_wl, st>>>(h->dn, h->dp, h->df, e, (const double *)nullptr, ntiles);
+                    DISPATCH_MW(MB, h->window_mw, (k_lu_window<MB, MW><<<g_wl, WL_NT, smem_wl, st>>>(h->dn, h->dp, h->df, e, (const double *)nullptr, ntiles, h->window_stagger_ns)));
                 } else {
                     if (tm) cudaEventRecord(h->phase_ev[evi++], st);
                     k_step_lu<MB><<<g_lu, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes);
@@ -1124,10 +1171,224 @@ extern "C" int32_t kb2_pack_results_device(kb2_handle h, double *final_bs_dev, d
     return 0;
 }
 
+// FP64 FMA peak of the device, measured: 16 independent DFMA chains per thread, all SMs full
+// (the denominator of the factorisation's FP64 fraction; SURVEY.md section 8d asks for a measured one)
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b)
+{
+    double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = a * (threadIdx.x + q);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = fma(v[q], b, a);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s += v[q];
+    if (s == 123.456) out[0] = s;        // never true: keeps the chains alive
+}
+
+extern "C" int32_t kb2_measure_fp64_peak(kb2_handle h, double *tflops)
+{
+    if (!h || !tflops) return 1;
+    if (h->device < 0) FAIL(h, "host-only handle: no CUDA device");
+    CU(h, cudaSetDevice(h->device));
+    double *d = nullptr;
+    CU(h, cudaMalloc((void **)&d, 8));
+    const int iters = 4096, grid = h->sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(h, cudaEventRecord(h->ev0, h->stream));
+        k_fp64_peak<<<grid, 256, 0, h->stream>>>(d, iters, 1e-3, 0.999);
+        h->launches++;
+        CU(h, cudaEventRecord(h->ev1, h->stream));
+        CU(h, cudaEventSynchronize(h->ev1));
+        float ms = 0;
+        CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (rep > 0) best = std::max(best, 2.0 * 16.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12);
+    }
+    cudaFree(d);
+    CU(h, cudaGetLastError());
+    *tflops = best;
+    return 0;
+}
+
 extern "C" int32_t kb2_get_launch_info(kb2_handle h, int32_t *members_per_tile, int32_t *ctas_per_sm)
 {
     if (!h) return 1;
     if (members_per_tile) *members_per_tile = h->ens_mb;
     if (ctas_per_sm) *ctas_per_sm = h->last_ctas_per_sm;
+    return 0;
+}
+
+// ---- multi-GPU: members are independent, so ranks never talk during the solve; the only
+// exchange is one all-gather of the packed results (final concentrations and per-species maxima,
+// member-major) over NCCL / NVLink at the end.  NCCL is bound at run time
+// (dlopen of libnccl.so.2: the copy a host process has already loaded, e.g. PyTorch's, or the
+// system one), so the library itself has no link-time dependency on it. ----
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+NcclApi g_nccl;
+
+bool nccl_load()
+{
+    if (g_nccl.lib) return true;
+    const char *names[] = {getenv("KB2_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { g_nccl.err = "libnccl.so.2 not found (set KB2_NCCL_LIB)"; return false; }
+    bool ok = true;
+    auto sym = [&](const char *n) { void *p = dlsym(g_nccl.lib, n); if (!p) ok = false; return p; };
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+    g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))sym("ncclCommInitAll");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) { g_nccl.err = "libnccl is missing a required symbol"; dlclose(g_nccl.lib); g_nccl.lib = nullptr; }
+    return ok;
+}
+}  // namespace
+
+#define NC(h, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { \
+    (h)->err = std::string(#call) + ": " + g_nccl.GetErrorString(r_); return 4; } } while (0)
+
+static void kb2_comm_release(kb2_ctx *h)
+{
+    if (h->comm && g_nccl.lib) g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr; h->comm_nranks = 1; h->comm_rank = 0;
+}
+
+extern "C" int32_t kb2_comm_unique_id(uint8_t *id128)
+{
+    if (!id128 || !nccl_load()) return 4;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return 4;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+extern "C" int32_t kb2_comm_init_rank(kb2_handle h, int32_t nranks, int32_t rank, const uint8_t *id128)
+{
+    if (!h || !id128) return 1;
+    if (h->device < 0) FAIL(h, "host-only handle: no CUDA device");
+    if (nranks < 1 || rank < 0 || rank >= nranks) FAIL(h, "bad rank / world size");
+    if (!nccl_load()) FAIL(h, g_nccl.err);
+    kb2_comm_release(h);
+    CU(h, cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NC(h, g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    h->comm_nranks = nranks; h->comm_rank = rank;
+    return 0;
+}
+
+extern "C" int32_t kb2_comm_init_all(int32_t ndev, kb2_handle *handles)
+{
+    if (ndev < 1 || !handles) return 1;
+    kb2_ctx *h0 = handles[0];
+    if (!h0) return 1;
+    if (!nccl_load()) FAIL(h0, g_nccl.err);
+    std::vector<int> devs(ndev);
+    std::vector<ncclComm_t> comms(ndev);
+    for (int i = 0; i < ndev; ++i) {
+        if (!handles[i] || handles[i]->device < 0) FAIL(h0, "every handle needs a CUDA device");
+        kb2_comm_release(handles[i]);
+        devs[i] = handles[i]->device;
+    }
+    NC(h0, g_nccl.CommInitAll(comms.data(), ndev, devs.data()));
+    for (int i = 0; i < ndev; ++i) { handles[i]->comm = comms[i]; handles[i]->comm_nranks = ndev; handles[i]->comm_rank = i; }
+    return 0;
+}
+
+// All-gather of the packed results of the last solve over the handles' communicator.  `n` local
+// handles (1 in a process-per-GPU job, all of them in a single-process job: the calls are grouped).
+// Every rank must hold the same B.  final_all[i] / umax_all[i]: host buffers of nranks*B*S doubles
+// (member-major, rank-major: [rank][b][i]) or NULL to leave the result on the device
+// (kb2_gathered_device).
+extern "C" int32_t kb2_allgather_results(kb2_handle *handles, int32_t n, double **final_all, double **umax_all)
+{
+    if (!handles || n < 1 || !handles[0]) return 1;
+    kb2_ctx *h0 = handles[0];
+    if (!nccl_load()) FAIL(h0, g_nccl.err);
+    for (int i = 0; i < n; ++i) {
+        kb2_ctx *h = handles[i];
+        if (!h || !h->comm) FAIL(h0, "kb2_comm_init_rank / kb2_comm_init_all first");
+        if (h->ens_B <= 0) FAIL(h0, "nothing to gather: run a solve first");
+        CU(h, cudaSetDevice(h->device));
+        const size_t per = (size_t)h->ens_B * h->net.S;
+        if (h->g_send_cap < 2 * per) {
+            cudaFree(h->g_send); h->g_send = nullptr; h->g_send_cap = 0;
+            CU(h, cudaMalloc((void **)&h->g_send, 2 * per * 8));
+            h->g_send_cap = 2 * per;
+        }
+        if (h->g_recv_cap < 2 * per * h->comm_nranks) {
+            cudaFree(h->g_recv); h->g_recv = nullptr; h->g_recv_cap = 0;
+            CU(h, cudaMalloc((void **)&h->g_recv, 2 * per * h->comm_nranks * 8));
+            h->g_recv_cap = 2 * per * h->comm_nranks;
+        }
+        DevEns &e = h->de;
+        const int S = (int)h->net.S, grid = conv_grid(h, per);
+        CU(h, cudaEventRecord(h->ev0, h->stream));
+        DISPATCH_MB(e.MB, (k_pack_bs<MB><<<grid, 256, 0, h->stream>>>(S, e.B, e.u, h->g_send)));
+        DISPATCH_MB(e.MB, (k_pack_bs<MB><<<grid, 256, 0, h->stream>>>(S, e.B, e.out_umax, h->g_send + per)));
+        h->launches += 2;
+        CU(h, cudaGetLastError());
+    }
+    NC(h0, g_nccl.GroupStart());
+    for (int i = 0; i < n; ++i) {
+        kb2_ctx *h = handles[i];
+        const size_t per = (size_t)h->ens_B * h->net.S;
+        cudaSetDevice(h->device);
+        NC(h, g_nccl.AllGather(h->g_send, h->g_recv, per, ncclDouble, h->comm, h->stream));
+        NC(h, g_nccl.AllGather(h->g_send + per, h->g_recv + per * h->comm_nranks, per, ncclDouble, h->comm, h->stream));
+    }
+    NC(h0, g_nccl.GroupEnd());
+    for (int i = 0; i < n; ++i) {
+        kb2_ctx *h = handles[i];
+        const size_t tot = (size_t)h->ens_B * h->net.S * h->comm_nranks;
+        CU(h, cudaSetDevice(h->device));
+        CU(h, cudaEventRecord(h->ev1, h->stream));
+        if (final_all && final_all[i]) CU(h, cudaMemcpyAsync(final_all[i], h->g_recv, tot * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (umax_all && umax_all[i]) CU(h, cudaMemcpyAsync(umax_all[i], h->g_recv + tot, tot * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    for (int i = 0; i < n; ++i) {
+        kb2_ctx *h = handles[i];
+        CU(h, cudaSetDevice(h->device));
+        CU(h, cudaStreamSynchronize(h->stream));
+        CU(h, cudaEventElapsedTime(&h->gather_ms, h->ev0, h->ev1));
+    }
+    return 0;
+}
+
+// device pointers of the gathered results ([nranks][B][S] each), device time of the last gather
+// (pack kernels + the two all-gathers), rank and world size of the handle's communicator
+extern "C" int32_t kb2_gathered_device(kb2_handle h, double **final_all_dev, double **umax_all_dev, float *gather_ms,
+                                       int32_t *rank, int32_t *nranks)
+{
+    if (!h) return 1;
+    const size_t tot = (size_t)std::max<int64_t>(h->ens_B, 0) * h->net.S * h->comm_nranks;
+    if (final_all_dev) *final_all_dev = h->g_recv;
+    if (umax_all_dev) *umax_all_dev = h->g_recv ? h->g_recv + tot : nullptr;
+    if (gather_ms) *gather_ms = h->gather_ms;
+    if (rank) *rank = h->comm_rank;
+    if (nranks) *nranks = h->comm_nranks;
     return 0;
 }

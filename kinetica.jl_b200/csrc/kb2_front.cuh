@@ -1,6 +1,7 @@
 // Window LU (sm_100a): right-looking block LU with the active submatrix in shared memory.
 //
-// One CTA of 256 threads factorises one tile of MB members at a time.  The plan (kb2_front.cpp)
+// One CTA of 256 threads factorises MW members of a tile at a time (MW = MB, or a divisor of it so
+// that two CTAs fit an SM).  The plan (kb2_front.cpp)
 // walks the panels of the block plan in order; front P consists of the pivot block of panel P, the
 // rows below it that have P as a source block (Lrows) and its U-part columns (Ucols).  Rows and
 // columns own a slot of the window  Win[row slot][column slot][member]  from the first front that
@@ -32,12 +33,13 @@ struct DevFront {
 
 constexpr int WL_NT = 256;          // threads per CTA
 constexpr int WL_CB = 4;            // columns of a register block of the update (rows: 8)
-constexpr int WL_PF = 4;            // original values of the next front a thread fetches ahead
+constexpr int WL_PF = 2;            // original values of the next front a thread fetches ahead
 
 __host__ __device__ inline int wl_list_cap(int max_nl, int max_nu) { return 16 + 2 * max_nu + 2 * max_nl; }
-__host__ __device__ inline size_t wl_smem_bytes(int mb, int Wr, int Wc, int max_nl, int max_nu)
+// mw = members per CTA
+__host__ __device__ inline size_t wl_smem_bytes(int mw, int Wr, int Wc, int max_nl, int max_nu)
 {
-    return (size_t)8 * mb * ((size_t)Wr * Wc + 64 + 8) + (size_t)8 * WL_PF * WL_NT + (size_t)2 * wl_list_cap(max_nl, max_nu) * 4;
+    return (size_t)8 * mw * ((size_t)Wr * Wc + 64 + 8) + (size_t)8 * WL_PF * WL_NT + (size_t)2 * wl_list_cap(max_nl, max_nu) * 4;
 }
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
@@ -52,11 +54,11 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 #define KB2_WL_KU 2
 #endif
 constexpr int WL_KU = KB2_WL_KU;
-template <int MB>
+template <int MW>
 __device__ __forceinline__ void wl_update_block(double *WinM, const int *prs, const int *pcs, const int (&ro)[8], const int (&co)[WL_CB],
                                                 const bool (&rok)[8], const bool (&cok)[WL_CB], int nr, int Wc)
 {
-    // WinM = Win + m; ro[i] = row slot * Wc * MB, co[c] = column slot * MB
+    // WinM = Win + member; ro[i] = row slot * Wc * MW, co[c] = column slot * MW
     double acc[8][WL_CB];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -64,7 +66,7 @@ __device__ __forceinline__ void wl_update_block(double *WinM, const int *prs, co
         for (int c = 0; c < WL_CB; ++c) acc[i][c] = WinM[ro[i] + co[c]];
 #pragma unroll WL_KU
     for (int k = 0; k < nr; ++k) {
-        const int pc = pcs[k] * MB, pr = prs[k] * Wc * MB;
+        const int pc = pcs[k] * MW, pr = prs[k] * Wc * MW;
         double l[8], u[WL_CB];
 #pragma unroll
         for (int i = 0; i < 8; ++i) l[i] = WinM[ro[i] + pc];
@@ -82,24 +84,32 @@ __device__ __forceinline__ void wl_update_block(double *WinM, const int *prs, co
             if (rok[i] && cok[c]) WinM[ro[i] + co[c]] = acc[i][c];
 }
 
+// One CTA factorises MW members of a tile (MW divides MB: a tile may be shared by MB/MW CTAs, so
+// that two CTAs fit an SM and one's pivot-block / barrier latencies hide behind the other's update).
+// Window layout [row slot][column slot][MW]; HBM arrays keep the tile layout [index][MB].
 // hg: per-member 1/(h*gamma) (kernel-level entry point), or null: taken from the control state,
-// tiles without a running member are skipped
-template <int MB>
-__global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, DevFront fr, DevEns en, const double *hg, int ntiles)
+// work items without a running member are skipped.
+template <int MB, int MW>
+__global__ void __launch_bounds__(WL_NT, (MW < 4) ? 2 : 1) k_lu_window(DevNet net, DevPlan pl, DevFront fr, DevEns en, const double *hg, int ntiles, int stagger_ns)
 {
     extern __shared__ double smem[];
-    constexpr int NX = WL_NT / MB, FREC = 12;
-    constexpr int NXL = (WL_NT - 32) / MB;                // x-threads outside warp 0: they fetch the next front's values
+    constexpr int NX = WL_NT / MW, FREC = 12, NPART = MB / MW;
+    constexpr int NXL = (WL_NT - 32) / MW;                // x-threads outside warp 0: they fetch the next front's values
     const int Wc = fr.Wc, Wr = fr.Wr;
-    double *Win = smem;                                   // [Wr*Wc][MB]
-    double *Dl = Win + (size_t)Wr * Wc * MB;              // [8][8][MB]: L'_PP (lower + pivots) and U'_PP (strict upper) of the front
-    double *dinv = Dl + 64 * MB;                          // [8][MB]
+    double *Win = smem;                                   // [Wr*Wc][MW]
+    double *Dl = Win + (size_t)Wr * Wc * MW;              // [8][8][MW]: L'_PP (lower + pivots) and U'_PP (strict upper) of the front
+    double *dinv = Dl + 64 * MW;                          // [8][MW]
+    double *stage = dinv + 8 * MW;                        // [WL_PF][WL_NT]: Jacobian values of the next front's new entries
     const int LCAP = wl_list_cap(fr.max_nl, fr.max_nu);
-    double *stage = dinv + 8 * MB;                        // [WL_PF][WL_NT]: Jacobian values of the next front's new entries
     int *lst = reinterpret_cast<int *>(stage + WL_PF * WL_NT);   // [2][LCAP]: lists of this front and the next
-    const int tid = threadIdx.x, m = tid % MB, x = tid / MB, lane = tid & 31, warp = tid >> 5;
-    const int xl = x - 32 / MB;                           // index among the x-threads outside warp 0 (negative in warp 0)
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tid = threadIdx.x, mw = tid % MW, x = tid / MW, lane = tid & 31, warp = tid >> 5;
+    const int xl = x - 32 / MW;                           // index among the x-threads outside warp 0 (negative in warp 0)
+    // Two CTAs share an SM (MW < 4) and would run the same phases at the same time, single-warp
+    // pivot block included; the second one starts half a front late, so that one's pivot block and
+    // barrier waits overlap the other's update
+    if (stagger_ns > 0 && blockIdx.x >= gridDim.x / 2) __nanosleep(stagger_ns);
+    for (int work = blockIdx.x; work < ntiles * NPART; work += gridDim.x) {
+        const int tile = work / NPART, m = (work % NPART) * MW + mw;
         const int b = tile * MB + m;
         double hgi;
         if (hg) hgi = hg[b];
@@ -108,32 +118,27 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
             if (!__syncthreads_or(c->active)) continue;
             hgi = 1.0 / (c->hs * kGamma);
         }
-        const double *jv = en.jv + (size_t)tile * net.nnzJ * MB;
-        double *lu = en.lu + (size_t)tile * pl.padded * MB;
-        double *invd = en.invd + (size_t)tile * net.S * MB;
+        const double *jv = en.jv + (size_t)tile * net.nnzJ * MB + m;
+        double *lu = en.lu + (size_t)tile * pl.padded * MB + m;
+        double *invd = en.invd + (size_t)tile * net.S * MB + m;
+        double *WinM = Win + mw;
         auto init_value = [&](int src) {
-            double v = (src >> 1) ? -jv[(size_t)((src >> 1) - 1) * MB + m] : 0.0;
+            double v = (src >> 1) ? -jv[(size_t)((src >> 1) - 1) * MB] : 0.0;
             if (src & 1) v += hgi;
             return v;
         };
         // ---- prologue: clear the window (inactive entries are zero from here on), lists and
         // original values of front 0 ----
         {
-            const int n = Wr * Wc * MB;
-            if (MB >= 2) {
-                double2 *z = reinterpret_cast<double2 *>(Win);
-                for (int i = tid; i < n / 2; i += WL_NT) z[i] = make_double2(0.0, 0.0);
-                if (tid == 0 && (n & 1)) Win[n - 1] = 0.0;
-            } else {
-                for (int i = tid; i < n; i += WL_NT) Win[i] = 0.0;
-            }
+            const int n = Wr * Wc * MW;
+            for (int i = tid; i < n; i += WL_NT) Win[i] = 0.0;
             const int *f = fr.f_info;
             const int len = 16 + 2 * f[2] + 2 * f[3];
             for (int i = tid; i < len; i += WL_NT) lst[i] = fr.lists[f[6] + i];
             __syncthreads();
             for (int e = x; e < f[8]; e += NX) {
                 const int2 ent = fr.init[f[7] + e];
-                Win[ent.x * MB + m] = init_value(ent.y);
+                WinM[ent.x * MW] = init_value(ent.y);
             }
         }
         __syncthreads();
@@ -157,21 +162,21 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
             for (int q = 0; q < WL_PF; ++q) { ppos[q] = -1; psrc[q] = 0; }
             if (warp == 0) {
                 cp_async_commit();
-                // ---- B: pivot block (lane = row * MB + member) ----
-                const int ln = lane / MB;
+                // ---- B: pivot block (lane = row * MW + member) ----
+                const int ln = lane / MW;
                 const bool own = ln < nr;
                 double D[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) D[j] = (own && j < nr) ? Win[(prs[ln] * Wc + pcs[j]) * MB + m] : 0.0;
+                for (int j = 0; j < 8; ++j) D[j] = (own && j < nr) ? WinM[(prs[ln] * Wc + pcs[j]) * MW] : 0.0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (j < nr) {
-                        const double piv = __shfl_sync(FULL, D[j], j * MB + m);
+                        const double piv = __shfl_sync(FULL, D[j], j * MW + mw);
                         const double inv = 1.0 / piv;
-                        if (ln == j) { invd[(p0 + j) * MB + m] = inv; dinv[j * MB + m] = inv; }
+                        if (ln == j) { invd[(size_t)(p0 + j) * MB] = inv; dinv[j * MW + mw] = inv; }
 #pragma unroll
                         for (int i = j + 1; i < 8; ++i) {
-                            const double uji = __shfl_sync(FULL, D[i], j * MB + m) * inv;
+                            const double uji = __shfl_sync(FULL, D[i], j * MW + mw) * inv;
                             if (ln == j) D[i] = uji;
                             else if (ln > j && ln < 8) D[i] -= D[j] * uji;
                         }
@@ -181,8 +186,8 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         if (j < nr) {
-                            Dl[(ln * 8 + j) * MB + m] = D[j];
-                            lu[((size_t)base + (size_t)(next + j) * nr + ln) * MB + m] = D[j];
+                            Dl[(ln * 8 + j) * MW + mw] = D[j];
+                            lu[((size_t)base + (size_t)(next + j) * nr + ln) * MB] = D[j];
                         }
                 }
             } else {
@@ -197,44 +202,45 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
                 }
 #pragma unroll
                 for (int q = 0; q < WL_PF; ++q)
-                    if (ppos[q] >= 0 && (psrc[q] >> 1)) cp_async8(stage + q * WL_NT + tid, jv + (size_t)((psrc[q] >> 1) - 1) * MB + m);
+                    if (ppos[q] >= 0 && (psrc[q] >> 1)) cp_async8(stage + q * WL_NT + tid, jv + (size_t)((psrc[q] >> 1) - 1) * MB);
                 cp_async_commit();
             }
             __syncthreads();
             // ---- C: strips, in place ----
             for (int t = x; t < nu + nl; t += NX) {
                 if (t < nu) {
-                    const int col = ucs[t];
+                    double *cp = WinM + ucs[t] * MW;
                     double w[8];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) w[r] = r < nr ? Win[(prs[r] * Wc + col) * MB + m] : 0.0;
+                    for (int r = 0; r < 8; ++r) w[r] = r < nr ? cp[prs[r] * Wc * MW] : 0.0;
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
                         if (r < nr) {
 #pragma unroll
-                            for (int a = 0; a < r; ++a) w[r] -= Dl[(r * 8 + a) * MB + m] * w[a];
-                            w[r] *= dinv[r * MB + m];
+                            for (int a = 0; a < r; ++a) w[r] -= Dl[(r * 8 + a) * MW + mw] * w[a];
+                            w[r] *= dinv[r * MW + mw];
                         }
                     }
-                    double *g = lu + ((size_t)base + (size_t)(next + nr + ujj[t]) * nr) * MB + m;
+                    double *g = lu + ((size_t)base + (size_t)(next + nr + ujj[t]) * nr) * MB;
 #pragma unroll
                     for (int r = 0; r < 8; ++r)
-                        if (r < nr) { Win[(prs[r] * Wc + col) * MB + m] = w[r]; g[r * MB] = w[r]; }
+                        if (r < nr) { cp[prs[r] * Wc * MW] = w[r]; g[r * MB] = w[r]; }
                 } else {
-                    const int ii = t - nu, row = lrs[ii] * Wc, gs = lgs[ii];
+                    const int ii = t - nu, gs = lgs[ii];
+                    double *rp = WinM + lrs[ii] * Wc * MW;
                     double X[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) X[q] = q < nr ? Win[(row + pcs[q]) * MB + m] : 0.0;
+                    for (int q = 0; q < 8; ++q) X[q] = q < nr ? rp[pcs[q] * MW] : 0.0;
 #pragma unroll
                     for (int a = 0; a < 7; ++a)
 #pragma unroll
                         for (int q = a + 1; q < 8; ++q)
-                            if (q < nr) X[q] -= X[a] * Dl[(a * 8 + q) * MB + m];
-                    double *g = lu + (size_t)(gs & 0x0fffffff) * MB + m;
+                            if (q < nr) X[q] -= X[a] * Dl[(a * 8 + q) * MW + mw];
+                    double *g = lu + (size_t)(gs & 0x0fffffff) * MB;
                     const int stride = ((gs >> 28) + 1) * MB;
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
-                        if (q < nr) { Win[(row + pcs[q]) * MB + m] = X[q]; g[q * stride] = X[q]; }
+                        if (q < nr) { rp[pcs[q] * MW] = X[q]; g[q * stride] = X[q]; }
                 }
             }
             __syncthreads();
@@ -246,19 +252,22 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
                     int ro[8], co[WL_CB];
                     bool rok[8], cok[WL_CB];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { rok[i] = rb * 8 + i < nl; ro[i] = lrs[min(rb * 8 + i, nl - 1)] * Wc * MB; }
+                    for (int i = 0; i < 8; ++i) { rok[i] = rb * 8 + i < nl; ro[i] = lrs[min(rb * 8 + i, nl - 1)] * Wc * MW; }
 #pragma unroll
-                    for (int c = 0; c < WL_CB; ++c) { cok[c] = cb + c * ncb < nu; co[c] = ucs[min(cb + c * ncb, nu - 1)] * MB; }
-                    wl_update_block<MB>(Win + m, prs, pcs, ro, co, rok, cok, nr, Wc);
+                    for (int c = 0; c < WL_CB; ++c) { cok[c] = cb + c * ncb < nu; co[c] = ucs[min(cb + c * ncb, nu - 1)] * MW; }
+                    wl_update_block<MW>(WinM, prs, pcs, ro, co, rok, cok, nr, Wc);
                 }
             }
             __syncthreads();
             // ---- the pivot rows and columns of P are dead: clear their slots (inactive entries stay
             // zero), then the next front's original values (which may land in those slots) ----
-            for (int r = 0; r < nr; ++r) {
-                double *row = Win + (size_t)prs[r] * Wc * MB + m, *col = Win + (size_t)pcs[r] * MB + m;
-                for (int z = x; z < Wc; z += NX) row[z * MB] = 0.0;
-                for (int z = x; z < Wr; z += NX) col[(size_t)z * Wc * MB] = 0.0;
+            // (warp r clears pivot r: its row slot is contiguous, its column slot strided)
+            if (warp < nr) {
+                const int r = warp;
+                double *row = Win + prs[r] * Wc * MW;
+                for (int i = lane; i < Wc * MW; i += 32) row[i] = 0.0;
+                double *col = Win + pcs[r] * MW + lane % MW;
+                for (int z = lane / MW; z < Wr; z += 32 / MW) col[z * Wc * MW] = 0.0;
             }
             cp_async_wait_all();
             if (hot) __syncthreads();
@@ -267,12 +276,18 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
                 if (ppos[q] >= 0) {
                     double v = (psrc[q] >> 1) ? -stage[q * WL_NT + tid] : 0.0;
                     if (psrc[q] & 1) v += hgi;
-                    Win[ppos[q] * MB + m] = v;
+                    WinM[ppos[q] * MW] = v;
                 }
-            if (xl >= 0)
-                for (int e = xl + WL_PF * NXL; e < ni; e += NXL) {
-                    const int2 ent = fr.init[ioff + e];
-                    Win[ent.x * MB + m] = init_value(ent.y);
+            if (xl >= 0)       // fronts with more new values than the staged ones (the first front of a block): four at a time
+                for (int e0 = xl + WL_PF * NXL; e0 < ni; e0 += 4 * NXL) {
+                    int2 ent[4];
+                    double v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ent[q] = e0 + q * NXL < ni ? fr.init[ioff + e0 + q * NXL] : make_int2(-1, 0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = ent[q].x >= 0 ? init_value(ent[q].y) : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (ent[q].x >= 0) WinM[ent[q].x * MW] = v[q];
                 }
             __syncthreads();
         }

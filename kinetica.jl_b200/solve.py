@@ -336,7 +336,7 @@ def _solve_with_retry(solver: EnsembleSolver, conds, pars, u0):
 
 
 def solve_network(method: AbstractODESolveMethod, sd: SpeciesData, rd: RxData, copy_network=True,
-                  device=0, solver: Optional[EnsembleSolver] = None):
+                  device=0, solver: Optional[EnsembleSolver] = None, _keep_solver: Optional[dict] = None):
     """methods.jl:105-130 (static) / :330-360 (variable) + the new ensemble method.
     Returns an `ODESolveOutput` (a list of them for `B200EnsembleODESolve`)."""
     if copy_network:
@@ -374,9 +374,14 @@ def solve_network(method: AbstractODESolveMethod, sd: SpeciesData, rd: RxData, c
     try:
         out_u, umax, status, stats, sol_k = _solve_with_retry(solver, conds, pars, u0)
         save_t = solver.save_t
-    finally:
+    except BaseException:
         if own:
             solver.close()
+        raise
+    if own and _keep_solver is None:
+        solver.close()
+    if _keep_solver is not None:
+        _keep_solver["solver"] = solver          # the caller closes it (multi-GPU gather of its results)
     outs = []
     for b, cs in enumerate(conds):
         sol = Solution(t=save_t.copy(), u=[out_u[s, :, b].copy() for s in range(out_u.shape[0])],
