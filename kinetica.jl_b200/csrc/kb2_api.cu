@@ -705,15 +705,31 @@ static int upload_uk(kb2_ctx *h, int64_t B, const double *u, const double *k)
     return rc;
 }
 
+// shared memory of a streaming-phase CTA: the tile's state vector when it is staged
+static size_t stream_smem(kb2_ctx *h) { return h->de.u_smem ? (size_t)h->net.S * h->de.MB * 8 : 0; }
+
+template <class K>
+static int stream_grid(kb2_ctx *h, K kern, int threads, size_t smem, int ntiles, int *grid)
+{
+    int r = set_smem(h, kern, smem);
+    if (r) return r;
+    int per_sm = 0;
+    CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) FAIL(h, "a phase kernel does not fit on an SM");
+    *grid = std::min(ntiles, per_sm * h->sm_count);
+    return 0;
+}
+
 static int launch_rhs(kb2_ctx *h)
 {
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
-    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr) + 16;
+    const size_t smem = stream_smem(h);
     DISPATCH_MB(e.MB, {
-        int r = set_smem(h, k_rhs<MB>, smem);
+        int grid = 0;
+        int r = stream_grid(h, k_rhs<MB, RHS_NW>, RHS_NW * 32, smem, ntiles, &grid);
         if (r) return r;
-        k_rhs<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles, (int)smem - 16);
+        k_rhs<MB, RHS_NW><<<grid, RHS_NW * 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles);
     });
     h->launches++;
     CU(h, cudaGetLastError());
@@ -738,11 +754,12 @@ static int launch_jac(kb2_ctx *h, int use_ctl)
 {
     DevEns &e = h->de;
     const int ntiles = n_tiles(e);
-    const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr) + 16;
+    const size_t smem = stream_smem(h);
     DISPATCH_MB(e.MB, {
-        int r = set_smem(h, k_step_jac<MB>, smem);
+        int grid = 0;
+        int r = stream_grid(h, k_step_jac<MB, RHS_NW>, RHS_NW * 32, smem, ntiles, &grid);
         if (r) return r;
-        k_step_jac<MB><<<std::min(ntiles, 32 * h->sm_count), 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles, (int)smem - 16, use_ctl);
+        k_step_jac<MB, RHS_NW><<<grid, RHS_NW * 32, smem, h->stream>>>(h->dn, h->dp, e, ntiles, use_ctl);
     });
     h->launches++;
     CU(h, cudaGetLastError());
@@ -1019,15 +1036,16 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     const size_t smem = warp_smem_bytes(e.MB, h->net.S, nullptr) + 16;
     const int data_bytes = (int)smem - 16;
     int g_init = 0, g_lu = 0, g_rhs = 0, g_sweep = 0, g_end = 0, g_jac = 0, g_wl = 0;
+    const size_t smem_st = stream_smem(h);
     const bool window = h->window_ok;
     size_t smem_wl = 0;
     if (window) { int r = window_launch_shape(h, &smem_wl, &g_wl); if (r) return r; }
     DISPATCH_MB(e.MB, {
         int r = phase_grid(h, k_solve_init<MB>, smem, ntiles, &g_init);
         if (!r) r = phase_grid(h, k_step_lu<MB>, smem, ntiles, &g_lu);
-        if (!r) r = phase_grid(h, k_step_jac<MB>, smem, ntiles, &g_jac);
+        if (!r) r = stream_grid(h, k_step_jac<MB, RHS_NW>, RHS_NW * 32, smem_st, ntiles, &g_jac);
 
-        if (!r) r = phase_grid(h, k_stage_rhs<MB>, smem, ntiles, &g_rhs);
+        if (!r) r = stream_grid(h, k_stage_rhs<MB, RHS_NW>, RHS_NW * 32, smem_st, ntiles, &g_rhs);
         if (!r) r = phase_grid(h, k_stage_sweep<MB>, smem, ntiles, &g_sweep);
         if (!r) r = phase_grid(h, k_step_end<MB>, smem, ntiles, &g_end);
         if (r) return r;
@@ -1067,7 +1085,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
             if (tm) { sampled = true; CU(h, cudaEventRecord(h->phase_ev[evi++], st)); }
             DISPATCH_MB(e.MB, {
                 if (window) {
-                    k_step_jac<MB><<<g_jac, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, 1);
+                    k_step_jac<MB, RHS_NW><<<g_jac, RHS_NW * 32, smem_st, st>>>(h->dn, h->dp, e, ntiles, 1);
                     if (tm) cudaEventRecord(h->phase_ev[evi++], st);
                     DISPATCH_MW(MB, h->window_mw, (k_lu_window<MB, MW><<<g_wl, WL_NT, smem_wl, st>>>(h->dn, h->dp, h->df, e, (const double *)nullptr, ntiles, h->window_stagger_ns)));
                 } else {
@@ -1076,7 +1094,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
                 }
                 if (tm) cudaEventRecord(h->phase_ev[evi++], st);
                 for (int s = 0; s < 6; ++s) {
-                    k_stage_rhs<MB><<<g_rhs, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, s);
+                    k_stage_rhs<MB, RHS_NW><<<g_rhs, RHS_NW * 32, smem_st, st>>>(h->dn, h->dp, e, ntiles, s);
                     if (tm) cudaEventRecord(h->phase_ev[evi++], st);
                     k_stage_sweep<MB><<<g_sweep, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, s);
                     if (tm) cudaEventRecord(h->phase_ev[evi++], st);

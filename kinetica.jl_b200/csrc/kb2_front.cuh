@@ -90,7 +90,7 @@ __device__ __forceinline__ void wl_update_block(double *WinM, const int *prs, co
 // hg: per-member 1/(h*gamma) (kernel-level entry point), or null: taken from the control state,
 // work items without a running member are skipped.
 template <int MB, int MW>
-__global__ void __launch_bounds__(WL_NT, (MW < 4) ? 2 : 1) k_lu_window(DevNet net, DevPlan pl, DevFront fr, DevEns en, const double *hg, int ntiles, int stagger_ns)
+__global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, DevFront fr, DevEns en, const double *hg, int ntiles, int stagger_ns)
 {
     extern __shared__ double smem[];
     constexpr int NX = WL_NT / MW, FREC = 12, NPART = MB / MW;
@@ -162,7 +162,9 @@ __global__ void __launch_bounds__(WL_NT, (MW < 4) ? 2 : 1) k_lu_window(DevNet ne
             for (int q = 0; q < WL_PF; ++q) { ppos[q] = -1; psrc[q] = 0; }
             if (warp == 0) {
                 cp_async_commit();
-                // ---- B: pivot block (lane = row * MW + member) ----
+                // ---- B: pivot block (lane = row * MW + member; pivot rows are broadcast with shuffles).
+                // Measured alternative: the whole block in the registers of every lane (no shuffles,
+                // 64 broadcast loads) is slower, 8.9 vs 8.5 ms on C3. ----
                 const int ln = lane / MW;
                 const bool own = ln < nr;
                 double D[8];
@@ -294,27 +296,23 @@ __global__ void __launch_bounds__(WL_NT, (MW < 4) ? 2 : 1) k_lu_window(DevNet ne
     }
 }
 
-// compact Jacobian values of every tile, CSC order, tile-major [tile][nnzJ][MB] (input of the window LU)
-template <int MB>
-__global__ void __launch_bounds__(32) k_step_jac(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes, int use_ctl)
+// compact Jacobian values of every tile, CSC order, tile-major [tile][nnzJ][MB] (input of the window
+// LU); NW warps of one CTA share a tile like in the right-hand side
+template <int MB, int NW>
+__global__ void __launch_bounds__(NW * 32, KB2_RHS_MINB) k_step_jac(DevNet net, DevPlan pl, DevEns en, int ntiles, int use_ctl)
 {
     extern __shared__ double smem[];
-    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    BulkChan ch; ch.bar = 0; ch.par = nullptr;
+    const int w = threadIdx.x >> 5;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en, ch);
-        if (use_ctl && !__any_sync(FULL, en.ctl[tl.b].active)) continue;
+        if (use_ctl && !__syncthreads_or(en.ctl[tl.b].active)) continue;
         const double *u = tl.u;
         if (en.u_smem) {
-            if (tl.ch.bar) {
-                bulk_issue(tl.ch, smem, u, (unsigned)(net.S * MB * 8), tl.lane, true);
-                bulk_wait(tl.ch, tl.lane);
-            } else {
-                for (int i = tl.lane; i < net.S * MB; i += 32) smem[i] = u[i];
-                __syncwarp();
-            }
+            stage_vector<MB, NW>(tl, smem, u, net.S * MB);
             u = smem;
         }
-        tile_jac_csc(tl, net, u, en.jv + (size_t)tile * net.nnzJ * MB);
+        tile_jac_csc<MB, NW>(tl, net, u, en.jv + (size_t)tile * net.nnzJ * MB, w);
     }
 }
 

@@ -212,6 +212,9 @@ __device__ inline double profile_eval(int kind, const double *p, double t)
 #ifndef KB2_K_STREAM
 #define KB2_K_STREAM 0         // k is loaded with an L2 evict_first policy in the per-reaction passes
 #endif
+#ifndef KB2_RHS_MINB
+#define KB2_RHS_MINB 4           // resident CTAs per SM requested for the multi-warp streaming kernels (register cap)
+#endif
 constexpr int PR = 8;          // rows per panel (PanelPlan::PR)
 constexpr int CWMAX = 96;      // columns per chunk (PanelPlan::CW)
 constexpr unsigned FULL = 0xffffffffu;
@@ -482,47 +485,87 @@ __device__ __forceinline__ void ell_gather(const WTile<MB> &tl, const int *order
     }
 }
 
-template <int MB>
-__device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u, double *out, bool accumulate, double *su)
+// A tile may be worked on by NW warps of one CTA (the streaming phases: right-hand side, Jacobian
+// values); phase boundaries inside the tile primitives are then block barriers.
+template <int NW>
+__device__ __forceinline__ void tile_sync()
+{
+    if (NW > 1) __syncthreads(); else __syncwarp();
+}
+
+// Contiguous share [g0, g1) of the ELL groups for warp w of NW, balanced by ELL length (the groups
+// are sorted by decreasing length, so equal counts would not be equal work).
+template <int NW>
+__device__ __forceinline__ void ell_share(const int *ell_ptr, int ngroups, int w, int &g0, int &g1)
+{
+    if (NW == 1) { g0 = 0; g1 = ngroups; return; }
+    const int total = ell_ptr[ngroups] - ell_ptr[0];
+    auto cut = [&](int k) {        // first group whose start is at or beyond k/NW of the total (plus one group per warp as a floor)
+        if (k <= 0) return 0;
+        if (k >= NW) return ngroups;
+        const long long target = (long long)total * k / NW + ell_ptr[0];
+        int lo = 0, hi = ngroups;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ell_ptr[mid] < target) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    g0 = cut(w); g1 = cut(w + 1);
+}
+
+// state vector of the tile -> shared memory (all NW warps copy, 16 bytes per thread and step)
+template <int MB, int NW>
+__device__ __forceinline__ void stage_vector(const WTile<MB> &tl, double *su, const double *u, int n)
+{
+    if (NW == 1 && tl.ch.bar) {
+        bulk_issue(tl.ch, su, u, (unsigned)(n * 8), tl.lane, true);
+        bulk_wait(tl.ch, tl.lane);
+        return;
+    }
+    const int tid = NW == 1 ? tl.lane : (int)threadIdx.x;
+    if (MB >= 2) {
+        const double2 *s2 = reinterpret_cast<const double2 *>(u);
+        double2 *d2 = reinterpret_cast<double2 *>(su);
+        for (int i = tid; i < n / 2; i += NW * 32) d2[i] = s2[i];
+    } else {
+        for (int i = tid; i < n; i += NW * 32) su[i] = u[i];
+    }
+    tile_sync<NW>();
+}
+
+template <int MB, int NW = 1>
+__device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u, double *out, bool accumulate, double *su, int w = 0)
 {
     constexpr int LN = 32 / MB;
     const int m = tl.m;
     if (su) {       // stage the state vector in shared memory: the reactant gathers never leave the SM
-        if (tl.ch.bar) {
-            bulk_issue(tl.ch, su, u, (unsigned)(net.S * MB * 8), tl.lane, true);
-            bulk_wait(tl.ch, tl.lane);
-        } else {
-            for (int i = tl.lane; i < net.S * MB; i += 32) su[i] = u[i];
-            __syncwarp();
-        }
+        stage_vector<MB, NW>(tl, su, u, net.S * MB);
         u = su;
     }
     {
-        constexpr int UR = 4;
+        constexpr int UR = 4, VL = LN * NW;       // virtual lanes of a member over the NW warps
         const unsigned long long pol_k = l2_policy_first();
-        for (int j0 = tl.ln; j0 < net.R; j0 += UR * LN) {
+        for (int j0 = w * LN + tl.ln; j0 < net.R; j0 += UR * VL) {
             int4 d[UR];
             double kj[UR];
 #pragma unroll
             for (int v = 0; v < UR; ++v) {
-                const int j = min(j0 + v * LN, net.R - 1);
+                const int j = min(j0 + v * VL, net.R - 1);
                 d[v] = net.rdesc[j];
                 kj[v] = ld_stream(tl.k + j * MB + m, pol_k);
             }
             double rt[UR];
             int ps[UR];
 #pragma unroll
-            for (int v = 0; v < UR; ++v) ps[v] = net.rate_pos[min(j0 + v * LN, net.R - 1)];
+            for (int v = 0; v < UR; ++v) ps[v] = net.rate_pos[min(j0 + v * VL, net.R - 1)];
 #pragma unroll
             for (int v = 0; v < UR; ++v) rt[v] = rate_of(d[v], u, MB, m, kj[v]);
 #pragma unroll
             for (int v = 0; v < UR; ++v)
-                if (j0 + v * LN < net.R) tl.rate[ps[v] * MB + m] = rt[v];
+                if (j0 + v * VL < net.R) tl.rate[ps[v] * MB + m] = rt[v];
         }
     }
-    __syncwarp();
+    tile_sync<NW>();
     // rows of hub species (hundreds of terms): the LN lanes of the member stride over the terms
-    for (int z = 0; z < net.rhs_nlong; ++z) {
+    for (int z = w; z < net.rhs_nlong; z += NW) {
         const int i = net.rhs_order[z];
         const int e1 = net.rhs_ptr[i + 1];
         const double b0 = (accumulate && tl.ln == 0) ? out[i * MB + m] : 0.0;
@@ -539,10 +582,12 @@ __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u
         if (tl.ln == 0) out[i * MB + m] = a + b0;
     }
     // the other rows one per lane slot as a sliced ELL (groups of 64 rows of about equal length)
-    ell_gather<MB>(tl, net.rhs_order, net.S, net.rhs_nlong, net.ell_ptr, net.ell, net.ell_ngroups, tl.rate,
+    int g0, g1;
+    ell_share<NW>(net.ell_ptr, net.ell_ngroups, w, g0, g1);
+    ell_gather<MB>(tl, net.rhs_order, net.S, net.rhs_nlong + g0 * ELL_G, net.ell_ptr + g0, net.ell, g1 - g0, tl.rate,
                    [&](int i) { return accumulate ? out[i * MB + m] : 0.0; },
                    [&](int i, double b0, double a) { out[i * MB + m] = a + b0; });
-    __syncwarp();
+    tile_sync<NW>();
 }
 
 // K3: analytic Jacobian entries  J_p = sum_t coef_t * k_j * d(prod)/du_l  for every entry p of
@@ -551,26 +596,26 @@ __device__ void tile_rhs(const WTile<MB> &tl, const DevNet &net, const double *u
 //                                                      the table itself are coalesced streams)
 //   J_p     = sum_t coef_t * d[index_t]               (gather-sum: entries with many terms (hub
 //             columns) are split across the lanes of the member, the others go through the ELL)
-template <int MB, class Pre, class Put>
-__device__ __forceinline__ void tile_jac_entries(const WTile<MB> &tl, const DevNet &net, const double *u, Pre pre, Put put)
+template <int MB, class Pre, class Put, int NW = 1>
+__device__ __forceinline__ void tile_jac_entries(const WTile<MB> &tl, const DevNet &net, const double *u, Pre pre, Put put, int w = 0)
 {
     constexpr int LN = 32 / MB;
     const int m = tl.m, ns = net.jslots;
     {
-        constexpr int UR = 4;
+        constexpr int UR = 4, VL = LN * NW;
         const unsigned long long pol_k = l2_policy_first();
-        for (int j0 = tl.ln; j0 < net.R; j0 += UR * LN) {
+        for (int j0 = w * LN + tl.ln; j0 < net.R; j0 += UR * VL) {
             int4 d[UR];
             double kj[UR];
 #pragma unroll
             for (int v = 0; v < UR; ++v) {
-                const int j = min(j0 + v * LN, net.R - 1);
+                const int j = min(j0 + v * VL, net.R - 1);
                 d[v] = net.rdesc[j];
                 kj[v] = ld_stream(tl.k + j * MB + m, pol_k);
             }
 #pragma unroll
             for (int v = 0; v < UR; ++v) {
-                const int j = j0 + v * LN;
+                const int j = j0 + v * VL;
                 const double x0 = u[max(d[v].x, 0) * MB + m], x1 = u[max(d[v].y, 0) * MB + m], x2 = u[max(d[v].z, 0) * MB + m];
                 const int e0 = d[v].w & 255, e1 = (d[v].w >> 8) & 255, e2 = (d[v].w >> 16) & 255;
                 double g0, g1, g2;
@@ -595,8 +640,8 @@ __device__ __forceinline__ void tile_jac_entries(const WTile<MB> &tl, const DevN
             }
         }
     }
-    __syncwarp();
-    for (int z = 0; z < net.j_nlong; ++z) {
+    tile_sync<NW>();
+    for (int z = w; z < net.j_nlong; z += NW) {
         const int p = net.j_order[z];
         const int t1 = net.jt_ptr[p + 1];
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -615,15 +660,19 @@ __device__ __forceinline__ void tile_jac_entries(const WTile<MB> &tl, const DevN
         const double a = member_sum<MB>((a0 + a1) + (a2 + a3));
         if (tl.ln == 0) put(p, pre(p), a);
     }
-    ell_gather<MB>(tl, net.j_order, net.nnzJ, net.j_nlong, net.jell_ptr, net.jell, net.jell_ngroups, tl.drate, pre, put);
+    int g0, g1;
+    ell_share<NW>(net.jell_ptr, net.jell_ngroups, w, g0, g1);
+    ell_gather<MB>(tl, net.j_order, net.nnzJ, net.j_nlong + g0 * ELL_G, net.jell_ptr + g0, net.jell, g1 - g0, tl.drate, pre, put);
 }
 
-template <int MB>
-__device__ void tile_jac_csc(const WTile<MB> &tl, const DevNet &net, const double *u, double *Jval)
+template <int MB, int NW = 1>
+__device__ void tile_jac_csc(const WTile<MB> &tl, const DevNet &net, const double *u, double *Jval, int w = 0)
 {
     const int m = tl.m;
-    tile_jac_entries<MB>(tl, net, u, [](int p) { return p; }, [&](int, int p, double v) { Jval[p * MB + m] = v; });
-    __syncwarp();
+    auto pre = [](int p) { return p; };
+    auto put = [&](int, int p, double v) { Jval[p * MB + m] = v; };
+    tile_jac_entries<MB, decltype(pre), decltype(put), NW>(tl, net, u, pre, put, w);
+    tile_sync<NW>();
 }
 
 // W = I/(h*gamma) - J assembled straight into the padded block storage: zero fill (coalesced
@@ -635,13 +684,7 @@ __device__ void tile_assemble_w(const WTile<MB> &tl, const DevNet &net, const De
     constexpr int LN = 32 / MB;
     const int m = tl.m;
     if (su) {
-        if (tl.ch.bar) {
-            bulk_issue(tl.ch, su, u, (unsigned)(net.S * MB * 8), tl.lane, true);
-            bulk_wait(tl.ch, tl.lane);
-        } else {
-            for (int i = tl.lane; i < net.S * MB; i += 32) su[i] = u[i];
-            __syncwarp();
-        }
+        stage_vector<MB, 1>(tl, su, u, net.S * MB);
         u = su;
     }
     if (MB == 1) {

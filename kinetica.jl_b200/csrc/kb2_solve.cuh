@@ -67,14 +67,15 @@ __global__ void __launch_bounds__(32) k_rates(DevNet net, DevPlan pl, DevEns en,
     }
 }
 
-template <int MB>
-__global__ void __launch_bounds__(32) k_rhs(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes)
+template <int MB, int NW>
+__global__ void __launch_bounds__(NW * 32, KB2_RHS_MINB) k_rhs(DevNet net, DevPlan pl, DevEns en, int ntiles)
 {
     extern __shared__ double smem[];
-    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    BulkChan ch; ch.bar = 0; ch.par = nullptr;
+    const int w = threadIdx.x >> 5;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en, ch);
-        tile_rhs(tl, net, tl.u, tl.rv, false, en.u_smem ? smem : nullptr);
+        tile_rhs<MB, NW>(tl, net, tl.u, tl.rv, false, en.u_smem ? smem : nullptr, w);
     }
 }
 
@@ -288,25 +289,29 @@ __global__ void __launch_bounds__(32) k_step_lu(DevNet net, DevPlan pl, DevEns e
 }
 
 // stage s: argument ua = u + sum_{q<s} a_sq K_q (stage 6 shares stage 5's coefficients plus K5) and,
-// from the same loads, the stage combination rv = sum_{q<s} (C_sq/h) K_q; then rv += f(ua)
-template <int MB>
-__global__ void __launch_bounds__(32) k_stage_rhs(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes, int s)
+// from the same loads, the stage combination rv = sum_{q<s} (C_sq/h) K_q; then rv += f(ua).
+// NW warps of one CTA share a tile: the passes are streams with short dependent chains, so what
+// they need is many warps in flight per SM (NW = 4: 28 resident warps instead of 7 on C3).
+constexpr int RHS_NW = 4;
+template <int MB, int NW>
+__global__ void __launch_bounds__(NW * 32, KB2_RHS_MINB) k_stage_rhs(DevNet net, DevPlan pl, DevEns en, int ntiles, int s)
 {
     extern __shared__ double smem[];
-    constexpr int LN = 32 / MB;
-    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    constexpr int LN = 32 / MB, VL = LN * NW;
+    BulkChan ch; ch.bar = 0; ch.par = nullptr;
+    const int w = threadIdx.x >> 5;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en, ch);
         const Ctl *c = en.ctl + tl.b;
-        if (!__any_sync(FULL, c->active)) continue;
-        const int m = tl.m, ln = tl.ln;
+        if (!__syncthreads_or(c->active)) continue;
+        const int m = tl.m, vl = w * LN + tl.ln;
         const double *Us = tl.u;
         if (s > 0) {
             const double ih = 1.0 / c->hs;
             const double a0 = cA[s][0], a1 = cA[s][1], a2 = cA[s][2], a3 = cA[s][3], a4 = cA[s][4];
             const double c0 = cC[s][0] * ih, c1 = cC[s][1] * ih, c2 = cC[s][2] * ih, c3 = cC[s][3] * ih, c4 = cC[s][4] * ih;
 #pragma unroll 4
-            for (int i = ln; i < net.S; i += LN) {
+            for (int i = vl; i < net.S; i += VL) {
                 const int o = i * MB + m;
                 const double k0 = tl.K[0][o];
                 double a = tl.u[o] + a0 * k0, r = c0 * k0;
@@ -317,10 +322,10 @@ __global__ void __launch_bounds__(32) k_stage_rhs(DevNet net, DevPlan pl, DevEns
                 tl.ua[o] = a;
                 tl.rv[o] = r;
             }
-            __syncwarp();
+            __syncthreads();
             Us = tl.ua;
         }
-        tile_rhs(tl, net, Us, tl.rv, s > 0, en.u_smem ? smem : nullptr);
+        tile_rhs<MB, NW>(tl, net, Us, tl.rv, s > 0, en.u_smem ? smem : nullptr, w);
     }
 }
 
