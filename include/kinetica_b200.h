@@ -119,7 +119,16 @@ int32_t kb2_solve(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, 
                   double abstol, double reltol, double dtmin, int64_t maxiters,
                   int32_t ban_negatives, int64_t Ns, double *out_u, double *out_umax,
                   int32_t *status, int64_t *stats);
-/* the same in three phases (bench.py times `run` alone with inputs resident in HBM) */
+/* Batch tiling: kb2_solve walks an ensemble that does not fit the device memory in chunks of
+ * b_tile members (members are independent; network tables, plans and calculator stay resident).
+ * kb2_memory_plan reports the device bytes one member needs for Ns save points, the chunk size the
+ * free memory allows (or the kb2_set_batch_tile override; 0 = automatic) and the free bytes;
+ * kb2_last_batch_tiles = chunks the last kb2_solve used. */
+int32_t kb2_memory_plan(kb2_handle h, int64_t Ns, int64_t *bytes_per_member, int64_t *b_tile, int64_t *free_bytes);
+int32_t kb2_set_batch_tile(kb2_handle h, int64_t b_tile);
+int64_t kb2_last_batch_tiles(kb2_handle h);
+/* the same in three phases (bench.py times `run` alone with inputs resident in HBM); the whole
+ * ensemble must fit the device memory */
 int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, double t0,
                           double abstol, double reltol, double dtmin, int64_t maxiters,
                           int32_t ban_negatives, int64_t Ns);

@@ -38,6 +38,9 @@ SIGNATURES = {
     "kb2_set_stops": (_i32, [_H, _i64, _pf64, _pi32]),
     "kb2_set_member_stops": (_i32, [_H, _i64, _i64, _pi32, _pf64, _pi32]),
     "kb2_solve": (_i32, [_H, _i64, _pf64, _i64, _f64, _f64, _f64, _f64, _i64, _i32, _i64, _pf64, _pf64, _pi32, _pi64]),
+    "kb2_memory_plan": (_i32, [_H, _i64, _pi64, _pi64, _pi64]),
+    "kb2_set_batch_tile": (_i32, [_H, _i64]),
+    "kb2_last_batch_tiles": (_i64, [_H]),
     "kb2_solve_prepare": (_i32, [_H, _i64, _pf64, _i64, _f64, _f64, _f64, _f64, _i64, _i32, _i64]),
     "kb2_solve_run": (_i32, [_H, C.POINTER(C.c_float)]),
     "kb2_solve_fetch": (_i32, [_H, _pf64, _pf64, _pi32, _pi64]),
@@ -274,6 +277,31 @@ class Handle:
         self._B, self._Ns = int(B), int(Ns)
         self._ck(self._lib.kb2_solve_prepare(self._h, B, _f(u0), stride, t0, abstol, reltol, dtmin,
                                              int(maxiters), int(bool(ban_negatives)), Ns))
+
+    def solve(self, B, u0, t0, abstol, reltol, dtmin, maxiters, ban_negatives, Ns):
+        """One-shot solve with batch tiling (kb2_solve): returns (out_u[Ns,S,B], umax[S,B], status, stats)."""
+        u0 = _c64(u0)
+        stride = 0 if u0.ndim == 1 else self.S
+        self._B, self._Ns = int(B), int(Ns)
+        out_u = np.empty((Ns, self.S, B))
+        umax = np.empty((self.S, B))
+        status = np.zeros(B, dtype=np.int32)
+        stats = np.zeros((B, 8), dtype=np.int64)
+        self._ck(self._lib.kb2_solve(self._h, B, _f(u0), stride, t0, abstol, reltol, dtmin, int(maxiters),
+                                     int(bool(ban_negatives)), Ns, _f(out_u), _f(umax), status.ctypes.data_as(_pi32), _i(stats)))
+        return out_u, umax, status, stats
+
+    def memory_plan(self, Ns):
+        a, b, c = _i64(), _i64(), _i64()
+        self._ck(self._lib.kb2_memory_plan(self._h, Ns, C.byref(a), C.byref(b), C.byref(c)))
+        return {"bytes_per_member": a.value, "b_tile": b.value, "free_bytes": c.value}
+
+    def set_batch_tile(self, b_tile=0):
+        self._ck(self._lib.kb2_set_batch_tile(self._h, int(b_tile)))
+
+    @property
+    def last_batch_tiles(self) -> int:
+        return int(self._lib.kb2_last_batch_tiles(self._h))
 
     def solve_run(self) -> float:
         ms = C.c_float()

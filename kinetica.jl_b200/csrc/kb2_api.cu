@@ -48,6 +48,8 @@ struct kb2_ctx {
     DevPlan dp{};
     DevFront df{};
     bool window_ok = false;       // the front plan's window fits the shared memory of an SM for the current tile size
+    int64_t b_tile_user = 0;      // batch tile override (0: sized from the free device memory)
+    int64_t last_tiles = 0;       // batch tiles of the last kb2_solve
     int window_mw = 0;            // members per CTA of the window LU
     int last_window_ctas = 0;     // resident window CTAs per SM
     int window_stagger_ns = 0;    // start delay of the second CTA of an SM
@@ -921,19 +923,20 @@ extern "C" int32_t kb2_time_kernel(kb2_handle h, int32_t which, int64_t B, int32
 }
 
 // ---- the solve ------------------------------------------------------------------------------
-extern "C" int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, double t0,
-                                     double abstol, double reltol, double dtmin, int64_t maxiters,
-                                     int32_t ban_negatives, int64_t Ns)
+// Prepare members [b0, b0 + B) of an ensemble of Btot members whose per-member tables (profiles,
+// stops, T table) were set for all Btot (batch tiling: kb2_solve walks the ensemble in chunks that
+// fit the device memory; the three-phase API prepares everything at once, b0 = 0, B = Btot).
+static int prepare_range(kb2_ctx *h, int64_t b0, int64_t B, int64_t Btot, const double *u0, int64_t u0_stride, double t0,
+                         double abstol, double reltol, double dtmin, int64_t maxiters, int32_t ban_negatives, int64_t Ns)
 {
-    if (!h) return 1;
     h->prepared = false;
     if (h->calc_mode < 0) FAIL(h, "no calculator set");
     if (h->stop_t.empty()) FAIL(h, "no stops set");
-    if (h->calc_mode == 0 && h->Bprof != B) FAIL(h, "kb2_set_profiles must be called with the same B");
+    if (h->calc_mode == 0 && h->Bprof != Btot) FAIL(h, "kb2_set_profiles must be called with the same B");
     const int64_t nstops = h->ns_row;
     const bool shared = h->stop_cnt.empty();
-    if (!shared && h->Bstops != B) FAIL(h, "kb2_set_member_stops was called with a different B");
-    if (!h->Ttab.empty() && (h->Btab != B || (int64_t)h->Ttab.size() != B * nstops))
+    if (!shared && h->Bstops != Btot) FAIL(h, "kb2_set_member_stops was called with a different B");
+    if (!h->Ttab.empty() && (h->Btab != Btot || (int64_t)h->Ttab.size() != Btot * nstops))
         FAIL(h, "T table does not match B x nstops");
     if (!(abstol > 0) || !(reltol > 0)) FAIL(h, "tolerances must be positive");
     const int64_t Bp64 = (B + 31) / 32 * 32;
@@ -941,9 +944,9 @@ extern "C" int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, 
     std::vector<double> st((size_t)(Bp64 * nstops), 0.0);
     std::vector<int32_t> sf((size_t)(Bp64 * nstops), 0), ridx((size_t)(Bp64 * nstops), -1), cnt((size_t)Bp64, 0);
     for (int64_t b = 0; b < B; ++b) {
-        const double *ts = shared ? h->stop_t.data() : h->stop_t.data() + b * nstops;
-        const int32_t *fl = shared ? h->stop_flags.data() : h->stop_flags.data() + b * nstops;
-        const int64_t n = shared ? nstops : h->stop_cnt[b];
+        const double *ts = shared ? h->stop_t.data() : h->stop_t.data() + (b0 + b) * nstops;
+        const int32_t *fl = shared ? h->stop_flags.data() : h->stop_flags.data() + (b0 + b) * nstops;
+        const int64_t n = shared ? nstops : h->stop_cnt[b0 + b];
         int64_t nsave = 0, nrate = 0;
         for (int64_t s = 0; s < n; ++s) {
             if (ts[s] < t0) FAIL(h, "stops must not precede t0");
@@ -974,7 +977,7 @@ extern "C" int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, 
         const size_t MB = e.MB, Bt = (size_t)(B + e.MB - 1) / e.MB * e.MB;
         std::vector<double> up(S * Bt, 0.0);
         for (int64_t b = 0; b < B; ++b) {
-            const double *src = u0 + (size_t)(u0_stride ? b * u0_stride : 0);
+            const double *src = u0 + (size_t)(u0_stride ? (b0 + b) * u0_stride : 0);
             double *dst = up.data() + (size_t)(b / MB) * S * MB + b % MB;
             for (size_t i = 0; i < S; ++i) dst[i * MB] = src[i];
         }
@@ -987,8 +990,8 @@ extern "C" int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, 
     std::vector<int32_t> kind(Bp, 0);
     std::vector<double> par(Bp * 16, 0.0);
     if (h->calc_mode == 0) {
-        std::copy(h->pkind.begin(), h->pkind.end(), kind.begin());
-        std::copy(h->pparams.begin(), h->pparams.end(), par.begin());
+        std::copy(h->pkind.begin() + b0, h->pkind.begin() + b0 + B, kind.begin());
+        std::copy(h->pparams.begin() + b0 * 16, h->pparams.begin() + (b0 + B) * 16, par.begin());
     }
     rc |= dev_upload(h, P, kind.data(), kind.size(), &e.pkind);
     rc |= dev_upload(h, P, par.data(), par.size(), &e.pparams);
@@ -999,7 +1002,7 @@ extern "C" int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, 
     e.Ttab = nullptr;
     if (!h->Ttab.empty()) {
         std::vector<double> tp(Bp * nstops, NAN);
-        std::copy(h->Ttab.begin(), h->Ttab.end(), tp.begin());
+        std::copy(h->Ttab.begin() + b0 * nstops, h->Ttab.begin() + (b0 + B) * nstops, tp.begin());
         rc |= dev_upload(h, P, tp.data(), tp.size(), &e.Ttab);
     }
     if (rc) return rc;
@@ -1008,6 +1011,47 @@ extern "C" int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, 
     e.t0 = t0; e.abstol = abstol; e.reltol = reltol; e.dtmin = dtmin; e.maxiters = maxiters;
     e.ban_neg = ban_negatives;
     h->prepared = true;
+    return 0;
+}
+
+extern "C" int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, double t0,
+                                     double abstol, double reltol, double dtmin, int64_t maxiters,
+                                     int32_t ban_negatives, int64_t Ns)
+{
+    if (!h) return 1;
+    return prepare_range(h, 0, B, B, u0, u0_stride, t0, abstol, reltol, dtmin, maxiters, ban_negatives, Ns);
+}
+
+// Device bytes one member of the current network needs during a solve with Ns save points, and how
+// many members fit the free device memory at once (batch tile; 0 = kb2_set_batch_tile override unset).
+extern "C" int32_t kb2_memory_plan(kb2_handle h, int64_t Ns, int64_t *bytes_per_member, int64_t *b_tile, int64_t *free_bytes)
+{
+    if (!h) return 1;
+    if (h->device < 0) FAIL(h, "host-only handle: no CUDA device");
+    if (!h->net_on_device) FAIL(h, "run kb2_symbolic first");
+    const int64_t S = h->net.S, R = h->net.R;
+    // LU values, Jacobian values, derivative table, k + rate, 11 state-sized vectors + maxima, saves
+    // (twice: the layout conversion of the fetch stages them), control state and tables
+    const int64_t per = 8 * (h->sym.panels.padded + std::max<int64_t>(h->sym.nnzJ, 1) + (int64_t)h->sym.jslots * R + 2 * R + 12 * S +
+                             2 * std::max<int64_t>(Ns, 1) * S) + (int64_t)sizeof(Ctl) + 2048;
+    CU(h, cudaSetDevice(h->device));
+    size_t fr = 0, tot = 0;
+    CU(h, cudaMemGetInfo(&fr, &tot));
+    // memory this handle already holds for an ensemble is reusable
+    int64_t tile = (int64_t)((double)fr * 0.9 / (double)per);
+    tile = tile / 128 * 128;
+    if (h->b_tile_user > 0) tile = h->b_tile_user;
+    if (bytes_per_member) *bytes_per_member = per;
+    if (b_tile) *b_tile = tile;
+    if (free_bytes) *free_bytes = (int64_t)fr;
+    return 0;
+}
+
+extern "C" int32_t kb2_set_batch_tile(kb2_handle h, int64_t b_tile)
+{
+    if (!h) return 1;
+    if (b_tile < 0) FAIL(h, "batch tile must be >= 0 (0 = sized from the free device memory)");
+    h->b_tile_user = b_tile;
     return 0;
 }
 
@@ -1169,11 +1213,46 @@ extern "C" int32_t kb2_solve(kb2_handle h, int64_t B, const double *u0, int64_t 
                              double abstol, double reltol, double dtmin, int64_t maxiters, int32_t ban_negatives,
                              int64_t Ns, double *out_u, double *out_umax, int32_t *status, int64_t *stats)
 {
-    int rc = kb2_solve_prepare(h, B, u0, u0_stride, t0, abstol, reltol, dtmin, maxiters, ban_negatives, Ns);
+    if (!h) return 1;
+    // batch tiling: an ensemble larger than the device memory is solved in chunks of b_tile members
+    // (members are independent; the network tables, plan and calculator stay resident)
+    int64_t per = 0, tile = 0;
+    if (h->ens_B != B) {          // an allocation of the right size is kept as it is
+        CU(h, cudaSetDevice(h->device < 0 ? 0 : h->device));
+        if (h->device >= 0) { CU(h, cudaStreamSynchronize(h->stream)); free_pool(h->ens_allocs); h->ens_B = -1; h->prepared = false; }
+    }
+    int rc = kb2_memory_plan(h, Ns, &per, &tile, nullptr);
     if (rc) return rc;
-    if ((rc = kb2_solve_run(h, nullptr))) return rc;
-    return kb2_solve_fetch(h, out_u, out_umax, status, stats);
+    if (h->ens_B == B) tile = std::max(tile, B);
+    if (tile <= 0) FAIL(h, "not enough device memory for a single member of this network");
+    h->last_tiles = (B + tile - 1) / tile;
+    if (B <= tile) {
+        rc = prepare_range(h, 0, B, B, u0, u0_stride, t0, abstol, reltol, dtmin, maxiters, ban_negatives, Ns);
+        if (rc) return rc;
+        if ((rc = kb2_solve_run(h, nullptr))) return rc;
+        return kb2_solve_fetch(h, out_u, out_umax, status, stats);
+    }
+    const size_t S = h->net.S;
+    std::vector<double> cu, cm;
+    for (int64_t b0 = 0; b0 < B; b0 += tile) {
+        const int64_t Bc = std::min(tile, B - b0);
+        rc = prepare_range(h, b0, Bc, B, u0, u0_stride, t0, abstol, reltol, dtmin, maxiters, ban_negatives, Ns);
+        if (rc) return rc;
+        if ((rc = kb2_solve_run(h, nullptr))) return rc;
+        if (out_u) cu.resize((size_t)Ns * S * Bc);
+        if (out_umax) cm.resize(S * Bc);
+        rc = kb2_solve_fetch(h, out_u ? cu.data() : nullptr, out_umax ? cm.data() : nullptr, status ? status + b0 : nullptr,
+                             stats ? stats + b0 * 8 : nullptr);
+        if (rc) return rc;
+        if (out_u)
+            for (size_t r = 0; r < (size_t)Ns * S; ++r) std::copy(cu.begin() + r * Bc, cu.begin() + (r + 1) * Bc, out_u + r * B + b0);
+        if (out_umax)
+            for (size_t r = 0; r < S; ++r) std::copy(cm.begin() + r * Bc, cm.begin() + (r + 1) * Bc, out_umax + r * B + b0);
+    }
+    return 0;
 }
+
+extern "C" int64_t kb2_last_batch_tiles(kb2_handle h) { return h ? h->last_tiles : 0; }
 
 extern "C" int32_t kb2_pack_results_device(kb2_handle h, double *final_bs_dev, double *umax_bs_dev)
 {

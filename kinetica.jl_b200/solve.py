@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import copy
 import itertools
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, List, Optional, Sequence
 
 import numpy as np
@@ -23,7 +23,7 @@ from .network import RxData, SpeciesData
 from .params import ODESimulationParams
 
 STOP_RATE, STOP_SAVE = 1, 2
-RETCODES = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 5: "Unfinished"}
+RETCODES = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable", 5: "Unfinished"}
 
 
 # ---------------------------------------------------------------- filters (filters.jl:1-52)
@@ -160,16 +160,39 @@ class Solution:
         return np.array([np.interp(tq, self.t, U[:, i]) for i in range(U.shape[1])])
 
 
-@dataclass
+class RateSolution:
+    """`res.sol_k` of a discrete-update solve: the precalculated rate constants at the tstops
+    (`DiffEqArray(k_precalc, tstops)` in the reference, solve_utils.jl:91-109, analysis/io.jl:36-38):
+    `.t` = tstops, `.u[n]` = k(T(tstop_n)) for all reactions."""
+
+    def __init__(self, t, u):
+        self.t = np.asarray(t, dtype=np.float64)
+        self.u = np.asarray(u, dtype=np.float64)
+
+    def __call__(self, tq):
+        """zero-order hold, like the rate update callback (solve_utils.jl:445-450)"""
+        i = np.clip(np.searchsorted(self.t, tq, side="right") - 1, 0, len(self.t) - 1)
+        return self.u[i]
+
+
 class ODESolveOutput:
-    sd: SpeciesData
-    rd: RxData
-    sol: Solution
-    sol_k: Any = None                # (tstops, k table) when rate constants were tabulated / requested
-    sol_vcs: Any = None
-    pars: Any = None
-    conditions: Any = None
-    umax: Optional[np.ndarray] = None   # per-species max over saved points (identify_next_seeds input)
+    """analysis/io.jl:3-11: sd, rd, sol, sol_k, sol_vcs, pars, conditions.  `sol_k` is the table of
+    precalculated rate constants for discrete-update solves (None for static conditions), `sol_vcs`
+    the variable-condition trajectories when they are integrated along with the species (continuous
+    mode) and None otherwise — the reference's rule (io.jl:36-38).  For ensembles `sol_k` is
+    evaluated on first access (Nt x R doubles per member)."""
+
+    def __init__(self, sd, rd, sol, sol_k=None, sol_vcs=None, pars=None, conditions=None, umax=None):
+        self.sd, self.rd, self.sol = sd, rd, sol
+        self._sol_k = sol_k
+        self.sol_vcs, self.pars, self.conditions = sol_vcs, pars, conditions
+        self.umax = umax               # per-species max over saved points (identify_next_seeds input)
+
+    @property
+    def sol_k(self):
+        if callable(self._sol_k):
+            self._sol_k = self._sol_k()
+        return self._sol_k
 
 
 # ---------------------------------------------------------------- the device-backed solver
@@ -244,13 +267,13 @@ class EnsembleSolver:
             sol_k = (ts, k_all)
         return dict(k_table=k_table, k_init=k_init, sol_k=sol_k)
 
-    def prepare(self, conds: Sequence[ConditionSet], pars: ODESimulationParams, u0):
-        """Host-side assembly of the stop / profile tables (cached per (conds, pars) identity: the
-        tables are rebuilt only when a different ensemble is bound), then the H2D upload."""
-        key = (id(conds), id(pars), len(conds), pars.abstol, pars.reltol)
-        if getattr(self, "_bound_key", None) != key:
-            self._bind(conds, pars)
-            self._bound_key = key
+    def bind(self, conds: Sequence[ConditionSet], pars: ODESimulationParams):
+        """Host-side assembly of the stop / profile / rate tables of an ensemble and their hand-over to
+        the library.  Explicit: the tables of the last `bind` stay in force until the next one (bench.py
+        binds once and re-runs `prepare`; `solve_network` binds on every call)."""
+        if self.calculator is not None and hasattr(self.calculator, "Ea") and len(self.calculator.Ea) != self.rd.nr:
+            raise ValueError("calculator and reaction data disagree on the number of reactions")
+        self._bind(conds, pars)
         b = self._bound
         if b["shared"]:
             self.h.set_stops(b["stop_t"], b["flags"])
@@ -262,10 +285,28 @@ class EnsembleSolver:
         else:
             self.h.set_rate_table(b["k_table"], b["k_init"])
             self.h.set_T_table(None)
-        t0, tf = pars.tspan
-        self.h.solve_prepare(len(conds), u0, t0, pars.abstol, pars.reltol, float(np.spacing(tf)), pars.maxiters,
-                             pars.ban_negatives, len(self.save_t))
+        self._bound_B, self._bound_pars = len(conds), pars
         return b["sol_k"]
+
+    def _solve_args(self, pars, u0):
+        t0, tf = pars.tspan
+        return (self._bound_B, u0, t0, pars.abstol, pars.reltol, float(np.spacing(tf)), pars.maxiters,
+                pars.ban_negatives, len(self.save_t))
+
+    def prepare(self, conds: Sequence[ConditionSet], pars: ODESimulationParams, u0):
+        """Upload of the bound ensemble (H2D of u0, profiles, stop tables).  `conds` must be the
+        ensemble of the last `bind` (bound here on first use)."""
+        if getattr(self, "_bound", None) is None or self._bound_B != len(conds):
+            self.bind(conds, pars)
+        self.h.solve_prepare(*self._solve_args(pars, u0))
+        return self._bound["sol_k"]
+
+    def solve(self, conds: Sequence[ConditionSet], pars: ODESimulationParams, u0):
+        """bind + one-shot kb2_solve (batch-tiled when the ensemble does not fit the device memory)
+        -> (out_u[Ns,S,B], umax[S,B], status[B], stats[B,8], sol_k)"""
+        sol_k = self.bind(conds, pars)
+        out_u, umax, status, stats = self.h.solve(*self._solve_args(pars, u0))
+        return out_u, umax, status, stats, sol_k
 
     def _bind(self, conds: Sequence[ConditionSet], pars: ODESimulationParams):
         t0, tf = pars.tspan
@@ -315,22 +356,32 @@ class EnsembleSolver:
 
 
 def _solve_with_retry(solver: EnsembleSolver, conds, pars, u0):
-    """adaptive_solve! (solve_utils.jl:376-424): on failure tighten abstol/reltol x0.1 and restart
-    the whole solve, at most 5 attempts, never below eps."""
+    """adaptive_solve! (solve_utils.jl:376-424) per member: members whose solve failed are solved
+    again, as a smaller ensemble, with abstol/reltol tightened x0.1 — at most 5 attempts, never
+    below eps; members that succeeded keep their result (each member is its own `solve!`)."""
     p = copy.copy(pars)
     mintol = np.finfo(np.float64).eps
+    B = len(conds)
+    todo = np.arange(B)
+    out_u = umax = status = stats = None
+    sol_k = None
     iters = 0
     while True:
         iters += 1
-        sol_k = solver.prepare(conds, p, u0)
-        solver.run()
-        out_u, umax, status, stats = solver.fetch()
-        if np.all(status == 0):
+        sub = [conds[b] for b in todo]
+        ou, um, st, sx, sk = solver.solve(sub, p, u0)
+        if out_u is None:
+            out_u, umax, status, stats, sol_k = ou, um, st.copy(), sx, sk
+        else:
+            out_u[:, :, todo], umax[:, todo], status[todo], stats[todo] = ou, um, st, sx
+        bad = st != 0
+        if not np.any(bad):
             if pars.update_tols and p.abstol != pars.abstol:
                 pars.abstol, pars.reltol = p.abstol, p.reltol
             return out_u, umax, status, stats, sol_k
         if not pars.adaptive_tols or iters >= 5 or p.abstol / 10 <= mintol or p.reltol / 10 <= mintol:
             raise RuntimeError("ODE solution failed.")       # ErrorException, solve_utils.jl:405-411
+        todo = todo[bad]
         p.abstol /= 10
         p.reltol /= 10
 
@@ -382,10 +433,21 @@ def solve_network(method: AbstractODESolveMethod, sd: SpeciesData, rd: RxData, c
         solver.close()
     if _keep_solver is not None:
         _keep_solver["solver"] = solver          # the caller closes it (multi-GPU gather of its results)
+    def rate_table(cs):
+        """res.sol_k: k at the tstops (calculate_discrete_rates); None for static conditions"""
+        if cs.isstatic() or not cs.discrete_updates:
+            return None
+        ts, k_all = calculate_discrete_rates(cs, calc, rd.nr)
+        return RateSolution(ts, k_all)
+
     outs = []
     for b, cs in enumerate(conds):
         sol = Solution(t=save_t.copy(), u=[out_u[s, :, b].copy() for s in range(out_u.shape[0])],
                        retcode=RETCODES.get(int(status[b]), "Failure"), stats=stats[b].copy())
-        outs.append(ODESolveOutput(sd=sd, rd=rd, sol=sol, sol_k=sol_k, pars=pars, conditions=cs,
+        if sol_k is not None:
+            sk = RateSolution(*sol_k)
+        else:
+            sk = (lambda cs=cs: rate_table(cs)) if ensemble else rate_table(cs)
+        outs.append(ODESolveOutput(sd=sd, rd=rd, sol=sol, sol_k=sk, sol_vcs=None, pars=pars, conditions=cs,
                                    umax=umax[:, b].copy()))
     return outs if ensemble else outs[0]
