@@ -154,7 +154,11 @@ std::string build_fronts(Symbolic &sym, int64_t S)
         }
         fp.max_nl = std::max(fp.max_nl, nl);
         fp.max_nu = std::max(fp.max_nu, nu);
-        const int32_t rec[FrontPlan::FREC] = {nr, p0, nu, nl, pp.p_base[P], next, loff, 0, (int32_t)init_of[P].size(), hot[P], 0, 0};
+        // look-ahead: the pivot block of P can be factorised while front P-1 is still updating the
+        // window if all of its rows and columns were active before P (none of its entries is new)
+        int32_t la = P >= 1 && act_rowpanel[P] < P;
+        for (int r = 0; r < nr && la; ++r) la = act_col[p0 + r] < P;
+        const int32_t rec[FrontPlan::FREC] = {nr, p0, nu, nl, pp.p_base[P], next, loff, 0, (int32_t)init_of[P].size(), hot[P], la, 0};
         fp.f_info.insert(fp.f_info.end(), rec, rec + FrontPlan::FREC);
         // ---- eliminate: the pivot rows and columns leave the window ----
         for (int r = 0; r < nr; ++r) {

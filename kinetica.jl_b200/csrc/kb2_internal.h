@@ -60,7 +60,8 @@ struct FrontPlan {
     static constexpr int FREC = 12;
     // per front: {nr, first pivot row, nu, nl, base slot of the panel, position of the diagonal block,
     //             offset into `lists`, offset into `init` (entries), init entries,
-    //             1 if a row/column of this front takes a slot that the previous front gave up, 0, 0}
+    //             1 if a row/column of this front takes a slot that the previous front gave up,
+    //             1 if the pivot block may be factorised ahead (no entry of it is new at this front), 0}
     std::vector<int32_t> f_info;
     // per front, at its offset: prs[8] pcs[8] (window slots of the pivot rows / columns, -1 beyond nr),
     // ucs[nu] (column slots of Ucols, ascending), ujj[nu] (position of that column in the panel's U

@@ -20,7 +20,7 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
     invd = {}
     lists, init = fp["lists"], fp["init"]
     dead_prev, dead_prev_r, dead_prev_c = False, set(), set()
-    for (nr, p0, nu, nl, base, nxt, loff, ioff, icnt, hot, _b, _c) in fp["f_info"]:
+    for (nr, p0, nu, nl, base, nxt, loff, ioff, icnt, hot, la, _c) in fp["f_info"]:
         # window entries that become live at this front and have an original value
         touches_prev = False
         for pos, src in init[ioff: ioff + icnt]:
@@ -32,6 +32,9 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
             touches_prev |= (pos // Wc in dead_prev_r) or (pos % Wc in dead_prev_c) if dead_prev else False
         assert hot or not touches_prev            # values land in a slot of the previous front only in flagged fronts
         prs, pcs = lists[loff: loff + 8], lists[loff + 8: loff + 16]
+        if la:      # look-ahead fronts: no entry of the pivot block is new at this front
+            blk = {int(r) * Wc + int(c) for r in prs[:nr] for c in pcs[:nr]}
+            assert not any(int(pos) in blk for pos, _ in init[ioff: ioff + icnt])
         ucs = lists[loff + 16: loff + 16 + nu]
         ujj = lists[loff + 16 + nu: loff + 16 + 2 * nu]
         lrs = lists[loff + 16 + 2 * nu: loff + 16 + 2 * nu + nl]
