@@ -86,7 +86,9 @@ def build_problem(name, B, rank=0, world=1, tol="default", members=None):
     pars = kb.ODESimulationParams(tspan=(0.0, 1.0), u0=synthetic_u0(S), save_interval=0.1,
                                   low_k_cutoff="none", solve_chunks=False, abstol=TOLS[tol][0], reltol=TOLS[tol][1])
     Btot = B * world
-    idx = list(members) if members is not None else list(range(rank * B, (rank + 1) * B))
+    # a rank's members are strided over the global sweep (b = rank, rank + world, ...): every rank gets
+    # the same mix of temperatures, hence about the same number of steps (load balance, parallel.py)
+    idx = list(members) if members is not None else list(range(rank, Btot, world))
     # member b of the whole job: ramp from 600 + 600*b/(Btot-1) K, +100 K at 100 K/s, ts_update 1e-2
     conds = []
     for b in idx:
@@ -280,6 +282,7 @@ def main():
         _, _, status, stats = es.h.solve_fetch(out_u, out_umax)   # D2H: saves, maxima, status, stats
         g_ms = 0.0
         if dist is not None:
+            barrier()                            # ranks finish their solves at different times: keep that wait out of the gather's own time
             es.h.allgather_results(to_host=False)
             g_ms = es.h.gathered_device()["gather_ms"]
         barrier()

@@ -32,6 +32,7 @@ enum {
     KB2_OK = 0,
     KB2_MAXITERS = 1,      /* reference maxiters, src/solving/methods.jl:165 */
     KB2_DTMIN = 2,         /* reference dtmin = eps(tspan[end]), src/solving/methods.jl:164 */
+    KB2_UNSTABLE = 3,      /* step size below dtmin with a non-finite error norm (singular pivot, overflow) */
     KB2_UNFINISHED = 5
 };
 
@@ -49,6 +50,9 @@ enum {
 /* stop flags */
 #define KB2_STOP_RATE 1   /* discrete rate update: CompleteRateUpdateAffect, solve_utils.jl:445-450 */
 #define KB2_STOP_SAVE 2   /* saveat point, methods.jl:166 */
+#define KB2_STOP_CHUNK 4  /* start of a new chunk of a chunkwise solve (methods.jl:185-303, 717-865): the integrator is
+                             re-initialised there — maxiters counts per chunk, the step size restarts, tolerances
+                             tightened by a retry are reset */
 
 /* ---- lifetime ---- */
 int32_t kb2_create(int32_t device, kb2_handle *out);
@@ -114,7 +118,7 @@ int32_t kb2_set_member_stops(kb2_handle h, int64_t B, int64_t nstops_max, const 
  * solve_utils.jl:376-424) for B members at once.
  *   u0[u0_stride*b + i]  (u0_stride = 0 broadcasts one vector; else u0_stride = S)
  *   out_u[(s*S + i)*B + b]  s = save index;  out_umax[i*B + b] = max over saves (NULL to skip)
- *   status[b];  stats[b*8] = {accepted, rejected, lu, rhs, saves, stops passed, attempts, 0} ---- */
+ *   status[b];  stats[b*8] = {accepted, rejected, lu, rhs, saves, stops passed, attempts in the last chunk, chunk retries} ---- */
 int32_t kb2_solve(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, double t0,
                   double abstol, double reltol, double dtmin, int64_t maxiters,
                   int32_t ban_negatives, int64_t Ns, double *out_u, double *out_umax,
@@ -127,6 +131,11 @@ int32_t kb2_solve(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, 
 int32_t kb2_memory_plan(kb2_handle h, int64_t Ns, int64_t *bytes_per_member, int64_t *b_tile, int64_t *free_bytes);
 int32_t kb2_set_batch_tile(kb2_handle h, int64_t b_tile);
 int64_t kb2_last_batch_tiles(kb2_handle h);
+/* chunkwise solves: adaptive_solve! per chunk (solve_utils.jl:376-424 inside the chunk loops) on the
+ * device — a member whose chunk fails (maxiters, dtmin) repeats it from the chunk's start state with
+ * abstol / reltol x0.1, at most five attempts; update_tols keeps the tightened tolerances for the
+ * following chunks (params.jl update_tols).  Without chunk stops the whole solve is one chunk. */
+int32_t kb2_set_chunking(kb2_handle h, int32_t retry_failed_chunks, int32_t update_tols);
 /* the same in three phases (bench.py times `run` alone with inputs resident in HBM); the whole
  * ensemble must fit the device memory */
 int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, double t0,

@@ -48,6 +48,8 @@ struct kb2_ctx {
     DevPlan dp{};
     DevFront df{};
     bool window_ok = false;       // the front plan's window fits the shared memory of an SM for the current tile size
+    int chunk_retry = 0, chunk_update_tols = 0;     // kb2_set_chunking
+    bool has_chunk_stops = false;
     int64_t b_tile_user = 0;      // batch tile override (0: sized from the free device memory)
     int64_t last_tiles = 0;       // batch tiles of the last kb2_solve
     int window_mw = 0;            // members per CTA of the window LU
@@ -543,6 +545,7 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
     rc |= dev_alloc(h, P, R * Bt * (size_t)h->sym.jslots, &e.drate);
     rc |= dev_alloc(h, P, (size_t)h->sym.panels.padded * Bt, &e.lu);
     rc |= dev_alloc(h, P, (size_t)std::max<int64_t>(h->sym.nnzJ, 1) * Bt, &e.jv);
+    rc |= dev_alloc(h, P, S * Bt, &e.uc);
     rc |= dev_alloc(h, P, S * Bt, &e.invd);
     rc |= dev_alloc(h, P, (size_t)std::max<int64_t>(Ns, 1) * S * Bt, &e.out_u);
     rc |= dev_alloc(h, P, S * Bt, &e.out_umax);
@@ -943,6 +946,7 @@ static int prepare_range(kb2_ctx *h, int64_t b0, int64_t B, int64_t Btot, const 
     // expand to per-member tables [b][nstops]
     std::vector<double> st((size_t)(Bp64 * nstops), 0.0);
     std::vector<int32_t> sf((size_t)(Bp64 * nstops), 0), ridx((size_t)(Bp64 * nstops), -1), cnt((size_t)Bp64, 0);
+    bool chunked = false;
     for (int64_t b = 0; b < B; ++b) {
         const double *ts = shared ? h->stop_t.data() : h->stop_t.data() + (b0 + b) * nstops;
         const int32_t *fl = shared ? h->stop_flags.data() : h->stop_flags.data() + (b0 + b) * nstops;
@@ -953,6 +957,7 @@ static int prepare_range(kb2_ctx *h, int64_t b0, int64_t B, int64_t Btot, const 
             st[b * nstops + s] = ts[s];
             sf[b * nstops + s] = fl[s];
             if (fl[s] & KB2_STOP_SAVE) ++nsave;
+            if (fl[s] & KB2_STOP_CHUNK) chunked = true;
             if (fl[s] & KB2_STOP_RATE) ridx[b * nstops + s] = (int32_t)nrate++;
         }
         cnt[b] = (int32_t)n;
@@ -1010,7 +1015,18 @@ static int prepare_range(kb2_ctx *h, int64_t b0, int64_t B, int64_t Btot, const 
     e.nstops = (int)nstops; e.Ns = (int)Ns;
     e.t0 = t0; e.abstol = abstol; e.reltol = reltol; e.dtmin = dtmin; e.maxiters = maxiters;
     e.ban_neg = ban_negatives;
+    e.chunk_retry = h->chunk_retry; e.update_tols = h->chunk_update_tols;
+    h->has_chunk_stops = chunked;
     h->prepared = true;
+    return 0;
+}
+
+extern "C" int32_t kb2_set_chunking(kb2_handle h, int32_t retry_failed_chunks, int32_t update_tols)
+{
+    if (!h) return 1;
+    h->chunk_retry = retry_failed_chunks ? 1 : 0;
+    h->chunk_update_tols = update_tols ? 1 : 0;
+    h->prepared = false;
     return 0;
 }
 
@@ -1032,7 +1048,7 @@ extern "C" int32_t kb2_memory_plan(kb2_handle h, int64_t Ns, int64_t *bytes_per_
     const int64_t S = h->net.S, R = h->net.R;
     // LU values, Jacobian values, derivative table, k + rate, 11 state-sized vectors + maxima, saves
     // (twice: the layout conversion of the fetch stages them), control state and tables
-    const int64_t per = 8 * (h->sym.panels.padded + std::max<int64_t>(h->sym.nnzJ, 1) + (int64_t)h->sym.jslots * R + 2 * R + 12 * S +
+    const int64_t per = 8 * (h->sym.panels.padded + std::max<int64_t>(h->sym.nnzJ, 1) + (int64_t)h->sym.jslots * R + 2 * R + 13 * S +
                              2 * std::max<int64_t>(Ns, 1) * S) + (int64_t)sizeof(Ctl) + 2048;
     CU(h, cudaSetDevice(h->device));
     size_t fr = 0, tot = 0;
@@ -1112,7 +1128,9 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     // rounds are launched in batches; flags[j] of a batch = some member is still running after
     // round j of it.  A round on a finished ensemble is thirteen empty kernels.
     const int NB = 16;
-    const long long max_rounds = e.maxiters + 2;       // every running member counts each round against maxiters
+    // every running member counts each round against maxiters; chunkwise solves count per chunk
+    // (and per repeat of a chunk), so the loop's own limit is per stop
+    const long long max_rounds = (e.maxiters + 2) * (h->has_chunk_stops ? (long long)e.nstops * 5 : 1);
     int *hflag = h->h_flag;
     bool running = true;
     {
@@ -1168,6 +1186,11 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     }
     if (running) {
         k_mark_unfinished<<<(e.B + 255) / 256, 256, 0, st>>>(e);
+        h->launches++;
+    }
+    {
+        const size_t n = (size_t)ntiles * h->net.S * e.MB;
+        DISPATCH_MB(e.MB, (k_umax<MB><<<conv_grid(h, n), 256, 0, st>>>(e, (int)h->net.S, n)));
         h->launches++;
     }
     CU(h, cudaEventRecord(h->ev1, st));

@@ -73,9 +73,12 @@ struct DevPlan {
 // Control state of one member between the phase kernels of a step (kb2_solve.cuh).
 struct Ctl {
     double t, h, hs, hold, errold, T, hfirst;
+    double atol, rtol;                 // tolerances in force (tightened by the chunk retry)
+    double tchunk, Tchunk;             // start of the current chunk: time, condition value of its rate constants
     long long iters;
     int ns, si, isave, status, hit, active, rejlast, firstacc, accept, upd, ridx, sav, fresh;
     int nacc, nrej, nlu, nrhs;
+    int si_chunk, isave_chunk, ridx_chunk, retries, chunk, nretry;   // chunk = a chunk boundary was just passed
 };
 
 // Ensemble state.  Every per-member array is TILE-MAJOR: [tile][index][MB] with MB members per
@@ -86,6 +89,7 @@ struct DevEns {
     int u_smem;               // 1: a tile's state vector (S*MB doubles) fits the warp's shared memory and is staged there for the gathers
     double *u, *ua, *rv, *y, *K[6], *k, *rate, *drate, *lu, *invd;
     double *jv;               // compact Jacobian values, CSC order: [tile][nnzJ][MB]
+    double *uc;               // state at the start of the current chunk (chunk retry), like u
     // conditions
     int nstops;               // row length of the per-member stop tables
     const double *stop_t;     // [b*nstops + s]
@@ -104,6 +108,8 @@ struct DevEns {
     double t0, abstol, reltol, dtmin;
     long long maxiters;
     int ban_neg;
+    int chunk_retry;          // a failed chunk is repeated from its start with tolerances x0.1 (adaptive_solve! per chunk)
+    int update_tols;          // tightened tolerances stay in force for the following chunks
 };
 
 // x^e for the small non-negative integer stoichiometries of mass action; exponents 0, 1 and 2
@@ -285,7 +291,7 @@ template <int MB>
 struct WTile {
     static constexpr int LN = 32 / MB;
     int lane, m, ln, b;
-    double *u, *ua, *rv, *y, *K[6], *k, *rate, *drate, *lu, *invd, *out_u, *out_umax;
+    double *u, *ua, *rv, *y, *K[6], *k, *rate, *drate, *lu, *invd, *out_u, *out_umax, *uc;
     BulkChan ch;
     __device__ WTile(int tile, const DevNet &net, const DevPlan &pl, const DevEns &en, const BulkChan &chan)
     {
@@ -295,7 +301,7 @@ struct WTile {
         ln = lane / MB;
         b = tile * MB + m;
         const size_t vs = (size_t)tile * net.S * MB;
-        u = en.u + vs; ua = en.ua + vs; rv = en.rv + vs; y = en.y + vs; invd = en.invd + vs;
+        u = en.u + vs; ua = en.ua + vs; rv = en.rv + vs; y = en.y + vs; invd = en.invd + vs; uc = en.uc + vs;
 #pragma unroll
         for (int q = 0; q < 6; ++q) K[q] = en.K[q] + vs;
         k = en.k + (size_t)tile * net.R * MB;

@@ -131,7 +131,7 @@ template <int MB>
 __device__ void tile_process_stop(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, bool at_start)
 {
     constexpr int LN = 32 / MB;
-    c.upd = 0; c.sav = -1;
+    c.upd = 0; c.sav = -1; c.chunk = 0;
     const size_t sb = (size_t)tl.b * en.nstops;
     const bool due = at_start ? (c.status == ST_RUNNING && c.si < c.ns && en.stop_t[sb + c.si] <= en.t0)
                               : (c.accept && c.hit);
@@ -143,6 +143,7 @@ __device__ void tile_process_stop(const WTile<MB> &tl, const DevNet &net, const 
             c.T = T; c.upd = 1; c.ridx = en.stop_ridx[sb + s];
         }
         if (fl & 2) c.sav = c.isave++;
+        if (fl & 4) c.chunk = 1;
         c.si = s + 1;
         if (c.si >= c.ns) c.status = 0;   // reached the end of tspan
     }
@@ -150,12 +151,21 @@ __device__ void tile_process_stop(const WTile<MB> &tl, const DevNet &net, const 
     const int sv = c.sav;
     if (__any_sync(FULL, sv >= 0)) {
         if (sv >= 0)
-            for (int i = tl.ln; i < net.S; i += LN) {
-                const double v = tl.u[i * MB + tl.m];
-                tl.out_u[((size_t)sv * net.S + i) * MB + tl.m] = v;
-                double *mx = tl.out_umax + i * MB + tl.m;
-                *mx = (sv == 0) ? v : fmax(*mx, v);
-            }
+            for (int i = tl.ln; i < net.S; i += LN) tl.out_u[((size_t)sv * net.S + i) * MB + tl.m] = tl.u[i * MB + tl.m];
+        __syncwarp();
+    }
+    // a chunk starts here (reference chunkwise solves, methods.jl:185-303, 717-865: the integrator is
+    // re-initialised at every multiple of solve_chunkstep): iteration count and tolerances start
+    // afresh, and the state is kept for a repeat of the chunk (adaptive_solve! per chunk)
+    const bool cstart = (at_start || c.chunk) && c.status == ST_RUNNING;
+    if (cstart) {
+        c.iters = 0; c.retries = 0;
+        c.tchunk = c.t; c.Tchunk = c.T; c.ridx_chunk = c.ridx; c.si_chunk = c.si; c.isave_chunk = c.isave;
+        if (!en.update_tols) { c.atol = en.abstol; c.rtol = en.reltol; }
+    }
+    if (en.chunk_retry && __any_sync(FULL, cstart)) {
+        if (cstart)
+            for (int i = tl.ln; i < net.S; i += LN) tl.uc[i * MB + tl.m] = tl.u[i * MB + tl.m];
         __syncwarp();
     }
 }
@@ -172,7 +182,7 @@ __device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns 
     double d0 = 0, d1 = 0;
     for (int i = tl.ln; i < net.S; i += LN) {
         const double ui = tl.u[i * MB + m], fi = tl.rv[i * MB + m];
-        const double sc = en.abstol + en.reltol * fabs(ui);
+        const double sc = c.atol + c.rtol * fabs(ui);
         d0 += (ui / sc) * (ui / sc); d1 += (fi / sc) * (fi / sc);
     }
     d0 = sqrt(member_sum<MB>(d0) / net.S);
@@ -183,7 +193,7 @@ __device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns 
     tile_rhs(tl, net, tl.ua, tl.y, false, su);
     double d2 = 0;
     for (int i = tl.ln; i < net.S; i += LN) {
-        const double sc = en.abstol + en.reltol * fabs(tl.u[i * MB + m]);
+        const double sc = c.atol + c.rtol * fabs(tl.u[i * MB + m]);
         const double q = (tl.y[i * MB + m] - tl.rv[i * MB + m]) / sc;
         d2 += q * q;
     }
@@ -192,7 +202,7 @@ __device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns 
     const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
     const double hn = fmin(100.0 * h0, h1);
     if (initial) { c.h = hn; c.hold = hn; c.nrhs += 2; }
-    else if (c.upd && c.status == ST_RUNNING && !(c.hfirst > 0.0)) { c.h = fmin(c.h, 0.1 * hn); c.nrhs += 2; }
+    else if ((c.upd || c.chunk) && c.status == ST_RUNNING && !(c.hfirst > 0.0)) { c.h = fmin(c.h, 0.1 * hn); c.nrhs += 2; }
     __syncwarp();
 }
 
@@ -204,7 +214,7 @@ __device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns 
 template <int MB>
 __device__ void tile_restart_h(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, double *su)
 {
-    const bool upd = c.upd && c.status == ST_RUNNING;
+    const bool upd = (c.upd || c.chunk) && c.status == ST_RUNNING;      // a chunk boundary re-initialises the integrator as well
     if (upd) { c.fresh = 1; c.firstacc = 1; }
     if (__any_sync(FULL, upd && !(c.hfirst > 0.0))) tile_hinit(tl, net, en, c, false, su);
     if (upd && c.hfirst > 0.0) c.h = fmin(c.h, c.hfirst);
@@ -229,6 +239,34 @@ __device__ __forceinline__ void plan_attempt(const DevEns &en, Ctl &c, int b)
     c.active = act; c.hs = hs; c.hit = hit; c.accept = 0;
 }
 
+// adaptive_solve! per chunk (solve_utils.jl:376-424 inside the chunk loops of methods.jl): a member
+// whose chunk failed (maxiters, dtmin) goes back to the start of the chunk with abstol / reltol x0.1,
+// at most five attempts and never below eps; then the failure stands.
+template <int MB>
+__device__ void tile_chunk_retry(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, double *su)
+{
+    constexpr int LN = 32 / MB;
+    const double mintol = 2.220446049250313e-16;
+    const bool redo = (c.status == 1 || c.status == 2 || c.status == 3) && c.retries < 4 && c.atol / 10 > mintol && c.rtol / 10 > mintol;
+    if (!__any_sync(FULL, redo)) return;
+    if (redo) {
+        for (int i = tl.ln; i < net.S; i += LN) tl.u[i * MB + tl.m] = tl.uc[i * MB + tl.m];
+        c.t = c.tchunk; c.si = c.si_chunk; c.isave = c.isave_chunk; c.T = c.Tchunk; c.ridx = c.ridx_chunk;
+        c.atol /= 10; c.rtol /= 10; c.retries++; c.nretry++;
+        c.iters = 0; c.status = ST_RUNNING;
+        c.rejlast = 0; c.firstacc = 1; c.fresh = 0; c.errold = 1.0; c.hfirst = 0.0;
+    }
+    __syncwarp();
+    tile_rates(tl, net, c.T, redo, c.ridx);          // the rate constants the chunk started with
+    {
+        // fresh starting step for the repeated members only
+        Ctl tmp = c;
+        tile_hinit(tl, net, en, tmp, true, su);
+        if (redo) { c.h = tmp.h; c.hold = tmp.hold; c.nrhs += 2; }
+    }
+    if (redo) plan_attempt(en, c, tl.b);
+}
+
 // end of a kernel that changes the control state: one lane per member writes it back, results of
 // finished members are published, and the tile reports whether it still has work
 template <int MB>
@@ -240,7 +278,7 @@ __device__ __forceinline__ void store_ctl(const WTile<MB> &tl, const DevEns &en,
             en.status[tl.b] = c.status;
             long long *st = en.stats + (size_t)tl.b * 8;
             st[0] = c.nacc; st[1] = c.nrej; st[2] = c.nlu; st[3] = c.nrhs;
-            st[4] = c.isave; st[5] = c.si; st[6] = c.iters; st[7] = 0;
+            st[4] = c.isave; st[5] = c.si; st[6] = c.iters; st[7] = c.nretry;
         }
     }
     if (__any_sync(FULL, c.active) && tl.lane == 0) en.flags[slot] = 1;
@@ -262,6 +300,8 @@ __global__ void __launch_bounds__(32) k_solve_init(DevNet net, DevPlan pl, DevEn
         c.nacc = c.nrej = c.nlu = c.nrhs = 0;
         c.rejlast = 0; c.firstacc = 1; c.accept = 0; c.hit = 0; c.active = 0; c.upd = 0; c.ridx = -1; c.sav = -1;
         c.errold = 1.0; c.h = 0.0; c.hs = 1.0; c.hold = 0.0; c.hfirst = 0.0; c.fresh = 0;
+        c.atol = en.abstol; c.rtol = en.reltol; c.tchunk = en.t0; c.Tchunk = 0.0;
+        c.si_chunk = 0; c.isave_chunk = 0; c.ridx_chunk = -1; c.retries = 0; c.chunk = 0; c.nretry = 0;
         // initial conditions: static -> value, variable -> X_start (condition_set.jl:111-121); both sit
         // in the profile's X(0) for every supported kind
         c.T = (net.calc_mode == 0) ? profile_eval(en.pkind[b], en.pparams + (size_t)b * 16, -1.0) : 0.0;
@@ -363,7 +403,7 @@ __global__ void __launch_bounds__(32) k_step_end(DevNet net, DevPlan pl, DevEns 
         for (int i = ln; i < net.S; i += LN) {
             const int o = i * MB + m;
             const double k6 = tl.K[5][o], un = tl.ua[o] + k6;
-            const double sc = en.abstol + en.reltol * fmax(fabs(tl.u[o]), fabs(un));
+            const double sc = c.atol + c.rtol * fmax(fabs(tl.u[o]), fabs(un));
             e2 += (k6 / sc) * (k6 / sc);
             neg |= (un < 0.0);
         }
@@ -393,7 +433,7 @@ __global__ void __launch_bounds__(32) k_step_end(DevNet net, DevPlan pl, DevEns 
                 else { c.t += hs; c.h = hnew; }
             } else {
                 c.nrej++; c.rejlast = 1; c.h = hnew;
-                if (hnew < en.dtmin) c.status = 2;
+                if (hnew < en.dtmin) c.status = (err < INFINITY) ? 2 : 3;      // 3: the last error norm was not finite (singular pivot, overflow)
             }
         }
         if (c.accept)
@@ -403,9 +443,24 @@ __global__ void __launch_bounds__(32) k_step_end(DevNet net, DevPlan pl, DevEns 
             }
         __syncwarp();
         tile_process_stop(tl, net, en, c, false);
-        if (__any_sync(FULL, c.upd)) tile_restart_h(tl, net, en, c, su);
+        if (__any_sync(FULL, c.upd || c.chunk)) tile_restart_h(tl, net, en, c, su);
         plan_attempt(en, c, tl.b);
+        if (en.chunk_retry) tile_chunk_retry(tl, net, en, c, su);
         store_ctl(tl, en, c, slot);
+    }
+}
+
+// per-species maxima over the save points (what identify_next_seeds consumes, explore_utils.jl:344-349)
+template <int MB>
+__global__ void k_umax(DevEns en, int S, size_t n)
+{
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        // idx = (tile * S + i) * MB + m
+        const size_t tile = idx / ((size_t)S * MB), rem = idx % ((size_t)S * MB);
+        const double *src = en.out_u + tile * en.Ns * S * MB + rem;
+        double mx = src[0];
+        for (int s = 1; s < en.Ns; ++s) mx = fmax(mx, src[(size_t)s * S * MB]);
+        en.out_umax[idx] = mx;
     }
 }
 

@@ -12,36 +12,31 @@ from typing import Sequence
 import numpy as np
 
 
-def member_slice(B_total: int, rank: int, world: int):
-    """Contiguous slice [lo, hi) of the (temperature-sorted) member axis owned by `rank`;
-    the first B_total % world ranks take one extra member."""
-    base, rem = divmod(B_total, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+def member_indices(B_total: int, rank: int, world: int) -> np.ndarray:
+    """Members owned by `rank`: b = rank, rank + world, rank + 2*world, ...  Strided, not contiguous:
+    the step count of a member depends on its condition (C3: 2204-2804 accepted steps across the
+    temperature sweep), and every rank waits for the slowest one at the gather, so each rank takes an
+    even sample of the (sorted) member axis."""
+    return np.arange(rank, B_total, world)
 
 
 def shard_members(items: Sequence, rank: int, world: int):
-    """This rank's slice of a per-member list, padded with copies of its last entry to the largest
+    """This rank's members of a per-member list, padded with copies of its last entry to the largest
     shard (the all-gather needs the same member count on every rank) -> (padded list, valid count)."""
     B = len(items)
-    lo, hi = member_slice(B, rank, world)
+    idx = member_indices(B, rank, world)
     per = -(-B // world)
-    loc = list(items[lo:hi])
+    loc = [items[int(b)] for b in idx]
     if not loc:
         raise ValueError("more ranks than ensemble members")
-    return loc + [loc[-1]] * (per - len(loc)), hi - lo
+    return loc + [loc[-1]] * (per - len(loc)), len(idx)
 
 
 def unpad_gathered(arr: np.ndarray, B_total: int, world: int):
-    """[world * per, ...] rank-major gathered array -> [B_total, ...] with the padding dropped."""
+    """[world * per, ...] rank-major gathered array -> [B_total, ...] in member order, padding dropped."""
     per = -(-B_total // world)
-    if per * world == B_total:
-        return arr
-    parts = []
-    for r in range(world):
-        lo, hi = member_slice(B_total, r, world)
-        parts.append(arr[r * per: r * per + (hi - lo)])
-    return np.concatenate(parts, axis=0)
+    b = np.arange(B_total)
+    return arr[(b % world) * per + b // world]
 
 
 def exchange_unique_id(make_id, rank: int, group=None) -> bytes:
@@ -60,7 +55,7 @@ def init_comm(handle, rank: int, world: int, group=None):
 
 def solve_network_sharded(method, sd, rd, rank: int, world: int, device: int = 0, group=None, solver=None):
     """`solve_network(B200EnsembleODESolve(...))` over `world` GPUs: every rank integrates its
-    contiguous slice of `method.conditions` and all ranks receive the gathered summaries.
+    strided share of `method.conditions` and all ranks receive the gathered summaries.
 
     Returns (outs, final_all, umax_all): this rank's `ODESolveOutput`s, and `[B_total, S]` arrays of
     final concentrations and per-species maxima of the whole ensemble (rank-major = member order).

@@ -22,7 +22,7 @@ from .conditions import (ConditionSet, StaticConditionProfile, create_savepoints
 from .network import RxData, SpeciesData
 from .params import ODESimulationParams
 
-STOP_RATE, STOP_SAVE = 1, 2
+STOP_RATE, STOP_SAVE, STOP_CHUNK = 1, 2, 4
 RETCODES = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable", 5: "Unfinished"}
 
 
@@ -175,6 +175,13 @@ class RateSolution:
         return self.u[i]
 
 
+class _Lazy:
+    """a value computed on first access"""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+
 class ODESolveOutput:
     """analysis/io.jl:3-11: sd, rd, sol, sol_k, sol_vcs, pars, conditions.  `sol_k` is the table of
     precalculated rate constants for discrete-update solves (None for static conditions), `sol_vcs`
@@ -190,22 +197,56 @@ class ODESolveOutput:
 
     @property
     def sol_k(self):
-        if callable(self._sol_k):
-            self._sol_k = self._sol_k()
+        if isinstance(self._sol_k, _Lazy):
+            self._sol_k = self._sol_k.fn()
         return self._sol_k
 
 
 # ---------------------------------------------------------------- the device-backed solver
-def merge_stops(tstops, saveat, t0, tf):
+def merge_stops(tstops, saveat, t0, tf, chunks=None):
+    """Merged, sorted stop list of one member with flags.  Times from different sources that differ
+    only in the last bits (a chunk boundary `nc * chunkstep` against a tstop of the profile's range
+    arithmetic) are one stop; the tstop's value is kept (it is where the profile is evaluated)."""
     ts = np.asarray(tstops, dtype=np.float64) if tstops is not None else np.zeros(0)
     sv = np.asarray(saveat, dtype=np.float64)
+    ck = np.asarray(chunks, dtype=np.float64) if chunks is not None else np.zeros(0)
     ts = ts[(ts >= t0) & (ts <= tf)]
     sv = sv[(sv >= t0) & (sv <= tf)]
-    allt = np.unique(np.concatenate([ts, sv, [tf]]))
-    flags = np.zeros(len(allt), dtype=np.int32)
-    flags[np.isin(allt, ts)] |= STOP_RATE
-    flags[np.isin(allt, sv)] |= STOP_SAVE
+    ck = ck[(ck > t0) & (ck < tf)]
+    t_all = np.concatenate([ts, sv, ck, [tf]])
+    f_all = np.concatenate([np.full(len(ts), STOP_RATE), np.full(len(sv), STOP_SAVE), np.full(len(ck), STOP_CHUNK), [0]]).astype(np.int32)
+    pri = np.concatenate([np.zeros(len(ts)), np.ones(len(sv)), np.ones(len(ck)), [1]])      # tstops first inside a cluster
+    order = np.lexsort((pri, t_all))
+    t_all, f_all = t_all[order], f_all[order]
+    tol = 1e-12 * max(1.0, abs(tf))
+    new = np.concatenate([[True], np.diff(t_all) > tol])
+    grp = np.cumsum(new) - 1
+    allt = np.zeros(grp[-1] + 1)
+    flags = np.zeros(grp[-1] + 1, dtype=np.int32)
+    # value of a cluster: its tstop if it has one (sorted first among equal times is not guaranteed, so pick explicitly)
+    allt[grp[::-1]] = t_all[::-1]                       # first element of every cluster ...
+    is_ts = f_all == STOP_RATE
+    allt[grp[is_ts]] = t_all[is_ts]                     # ... overridden by the cluster's tstop
+    np.bitwise_or.at(flags, grp, f_all)
+    allt[-1] = tf if abs(allt[-1] - tf) <= tol else allt[-1]
     return allt, flags
+
+
+def chunk_grid(pars: ODESimulationParams):
+    """Chunk boundaries and save times of a chunkwise solve (methods.jl:214-222, 757-765): chunks of
+    `solve_chunkstep`, local save points 0:save_interval:chunkstep (save_interval defaults to the
+    chunk step), global time = local time + nc * chunkstep, `(len(saveat_local) - 1) * n_chunks + 1`
+    points in all."""
+    t0, tf = pars.tspan
+    step = pars.solve_chunkstep
+    n_chunks = int(tf / step)
+    si = step if pars.save_interval is None else pars.save_interval
+    nloc = int(np.floor(step / si + 1e-9)) + 1                       # length of 0.0:si:step
+    local = np.arange(nloc) * si
+    save = [local[i] + nc * step for nc in range(n_chunks) for i in range(nloc - 1)]
+    save.append(local[-1] + (n_chunks - 1) * step)
+    bounds = np.arange(1, n_chunks) * step
+    return np.array(bounds), np.array(save)
 
 
 class EnsembleSolver:
@@ -285,13 +326,16 @@ class EnsembleSolver:
         else:
             self.h.set_rate_table(b["k_table"], b["k_init"])
             self.h.set_T_table(None)
+        # chunkwise: a failed chunk is repeated on the device (adaptive_solve! per chunk)
+        self.h.set_chunking(bool(pars.solve_chunks and pars.adaptive_tols), bool(pars.update_tols))
         self._bound_B, self._bound_pars = len(conds), pars
         return b["sol_k"]
 
     def _solve_args(self, pars, u0):
         t0, tf = pars.tspan
-        return (self._bound_B, u0, t0, pars.abstol, pars.reltol, float(np.spacing(tf)), pars.maxiters,
-                pars.ban_negatives, len(self.save_t))
+        # dtmin = eps(tspan[end]) (methods.jl:164), eps(solve_chunkstep) in chunkwise solves (:231)
+        dtmin = float(np.spacing(pars.solve_chunkstep if pars.solve_chunks else tf))
+        return (self._bound_B, u0, t0, pars.abstol, pars.reltol, dtmin, pars.maxiters, pars.ban_negatives, len(self.save_t))
 
     def prepare(self, conds: Sequence[ConditionSet], pars: ODESimulationParams, u0):
         """Upload of the bound ensemble (H2D of u0, profiles, stop tables).  `conds` must be the
@@ -310,8 +354,15 @@ class EnsembleSolver:
 
     def _bind(self, conds: Sequence[ConditionSet], pars: ODESimulationParams):
         t0, tf = pars.tspan
-        si = pars.save_interval if pars.save_interval is not None else tf / 1000
-        saveat = create_savepoints(t0, tf, si)
+        if pars.solve_chunks:
+            # the reference default (params.jl:65): the integrator is re-initialised every solve_chunkstep
+            chunks, saveat = chunk_grid(pars)
+        else:
+            # complete solve; save_interval = nothing means "every step" in the reference (saveat = []):
+            # here a fixed grid of tf/1000 (the device saves at stops only) — documented deviation
+            chunks = None
+            si = pars.save_interval if pars.save_interval is not None else tf / 1000
+            saveat = create_savepoints(t0, tf, si)
         B = len(conds)
         if conds[0].isstatic():
             tstops0, same = None, all(cs.isstatic() for cs in conds)
@@ -327,11 +378,11 @@ class EnsembleSolver:
                     break
         bound = {"shared": same, "counts": None}
         if same:
-            stop_t, flags = merge_stops(tstops0, saveat, t0, tf)
+            stop_t, flags = merge_stops(tstops0, saveat, t0, tf, chunks)
             self.save_t = stop_t[(flags & STOP_SAVE) != 0]
         else:
             # members with their own tstops grids (e.g. t_end differing in the last bit)
-            lists = [merge_stops(cs.get_tstops(), saveat, t0, tf) for cs in conds]
+            lists = [merge_stops(cs.get_tstops(), saveat, t0, tf, chunks) for cs in conds]
             nmax = max(len(t) for t, _ in lists)
             stop_t = np.zeros((B, nmax))
             flags = np.zeros((B, nmax), dtype=np.int32)
@@ -379,7 +430,8 @@ def _solve_with_retry(solver: EnsembleSolver, conds, pars, u0):
             if pars.update_tols and p.abstol != pars.abstol:
                 pars.abstol, pars.reltol = p.abstol, p.reltol
             return out_u, umax, status, stats, sol_k
-        if not pars.adaptive_tols or iters >= 5 or p.abstol / 10 <= mintol or p.reltol / 10 <= mintol:
+        # chunkwise solves have already repeated the failed chunk on the device (five attempts)
+        if pars.solve_chunks or not pars.adaptive_tols or iters >= 5 or p.abstol / 10 <= mintol or p.reltol / 10 <= mintol:
             raise RuntimeError("ODE solution failed.")       # ErrorException, solve_utils.jl:405-411
         todo = todo[bad]
         p.abstol /= 10
@@ -447,7 +499,7 @@ def solve_network(method: AbstractODESolveMethod, sd: SpeciesData, rd: RxData, c
         if sol_k is not None:
             sk = RateSolution(*sol_k)
         else:
-            sk = (lambda cs=cs: rate_table(cs)) if ensemble else rate_table(cs)
+            sk = _Lazy(lambda cs=cs: rate_table(cs)) if ensemble else rate_table(cs)
         outs.append(ODESolveOutput(sd=sd, rd=rd, sol=sol, sol_k=sk, sol_vcs=None, pars=pars, conditions=cs,
                                    umax=umax[:, b].copy()))
     return outs if ensemble else outs[0]

@@ -159,3 +159,19 @@ def test_stop_merging():
     assert list(t) == [0.0, 0.4, 0.8, 1.0] and list(f) == [2, 2, 2, 0]
     t, f = merge_stops(np.array([0.5, 2.0]), np.array([0.0, 1.0]), 0.0, 1.0)  # stops beyond tf dropped
     assert list(t) == [0.0, 0.5, 1.0] and list(f) == [2, 1, 2]
+
+
+def test_chunk_grid_follows_the_reference_formula():
+    """methods.jl:214-222: n_chunks = Int(tspan[2] / chunkstep), saveat_local = 0:save_interval:chunkstep,
+    (len(saveat_local) - 1) * n_chunks + 1 points, global time = local + nc * chunkstep."""
+    import kinetica_b200 as kb
+    from kinetica_b200.solve import chunk_grid, merge_stops, STOP_CHUNK, STOP_SAVE, STOP_RATE
+    p = kb.ODESimulationParams(tspan=(0.0, 14.0), u0=[1.0])
+    bounds, save = chunk_grid(p)
+    assert len(save) == 14001 and len(bounds) == 13999 and save[0] == 0.0 and save[-1] == 0.001 + 13999 * 0.001
+    p = kb.ODESimulationParams(tspan=(0.0, 1.0), u0=[1.0], solve_chunkstep=0.25, save_interval=0.05)
+    bounds, save = chunk_grid(p)
+    assert len(save) == (6 - 1) * 4 + 1 and np.allclose(save, np.arange(21) * 0.05) and bounds.tolist() == [0.25, 0.5, 0.75]
+    st, fl = merge_stops([0.0, 0.5, 1.0], save, 0.0, 1.0, bounds)
+    assert fl[list(st).index(0.5)] == (STOP_RATE | STOP_SAVE | STOP_CHUNK) and fl[list(st).index(0.25)] == (STOP_SAVE | STOP_CHUNK)
+    assert fl[-1] & STOP_CHUNK == 0                      # tf is not the start of a chunk

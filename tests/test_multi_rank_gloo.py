@@ -1,6 +1,6 @@
 """N > 1 path on CPU: world_size-2 gloo.  The ensemble shards over ranks with no exchange during
 the solve (kinetica_b200.parallel); the NCCL unique id travels from rank 0 through
-torch.distributed, every rank integrates its (padded) member slice — here with the plain-C oracle
+torch.distributed, every rank integrates its (padded) member share (strided over the member axis) — here with the plain-C oracle
 standing in for the GPU — and the rank-major gathered array is un-padded into member order."""
 import socket
 
@@ -28,7 +28,7 @@ class _FakeHandle:
 def _worker(rank, world, port, B_total, q):
     import torch
     import torch.distributed as dist
-    from kinetica_b200.parallel import init_comm, member_slice, shard_members
+    from kinetica_b200.parallel import init_comm, member_indices, shard_members
     from oracle import c_oracle as co, kinetica_oracle as ko
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     h = _FakeHandle(rank)
@@ -37,8 +37,8 @@ def _worker(rank, world, port, B_total, q):
     net = ko.Network(3, [[0], [1], [1, 2]], [[1], [1, 2], [0, 2]], [[1], [2], [1, 1]], [[1], [1, 1], [1, 1]])
     Ts_all = [300.0 + 10.0 * b for b in range(B_total)]
     Ts, nvalid = shard_members(Ts_all, rank, world)
-    lo, hi = member_slice(B_total, rank, world)
-    assert nvalid == hi - lo and len(Ts) == -(-B_total // world) and Ts[:nvalid] == Ts_all[lo:hi]
+    idx = member_indices(B_total, rank, world)
+    assert nvalid == len(idx) and len(Ts) == -(-B_total // world) and Ts[:nvalid] == [Ts_all[b] for b in idx]
     A = np.array([0.04, 3e7, 1e4]) / ko.N_A
     Ea = np.array([0.0, 2e3, 1e3])
     out, st, _, _ = co.solve_rodas4(net, A, Ea, None, 1.0, Ts, None, None, [1.0, 0, 0], (0.0, 1.0), np.array([0.0, 1.0]),
@@ -55,9 +55,9 @@ def _worker(rank, world, port, B_total, q):
 @pytest.mark.parametrize("B_total", [6, 7])
 def test_sharded_ensemble_allgather(built, B_total):
     import torch.multiprocessing as mp
-    from kinetica_b200.parallel import member_slice, unpad_gathered
+    from kinetica_b200.parallel import member_indices, unpad_gathered
     from oracle import c_oracle as co, kinetica_oracle as ko
-    assert member_slice(7, 0, 2) == (0, 4) and member_slice(7, 1, 2) == (4, 7)
+    assert member_indices(7, 0, 2).tolist() == [0, 2, 4, 6] and member_indices(7, 1, 2).tolist() == [1, 3, 5]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -77,17 +77,17 @@ def test_sharded_ensemble_allgather(built, B_total):
 
 
 def test_shard_helpers():
-    from kinetica_b200.parallel import member_slice, shard_members, unpad_gathered
+    from kinetica_b200.parallel import member_indices, shard_members, unpad_gathered
     for B, world in ((10, 4), (8, 8), (65536, 8), (5, 2)):
         per = -(-B // world)
         cover = []
         blocks = []
         for r in range(world):
             loc, nv = shard_members(list(range(B)), r, world)
-            assert len(loc) == per and loc[:nv] == list(range(*member_slice(B, r, world)))
+            assert len(loc) == per and loc[:nv] == member_indices(B, r, world).tolist()
             cover += loc[:nv]
             blocks.append(np.array(loc)[:, None])
-        assert cover == list(range(B))
+        assert sorted(cover) == list(range(B))
         assert np.array_equal(unpad_gathered(np.concatenate(blocks), B, world)[:, 0], np.arange(B))
     with pytest.raises(ValueError):
         shard_members([1], 1, 2)
