@@ -131,6 +131,12 @@ int32_t kb2_solve(kb2_handle h, int64_t B, const double *u0, int64_t u0_stride, 
 int32_t kb2_memory_plan(kb2_handle h, int64_t Ns, int64_t *bytes_per_member, int64_t *b_tile, int64_t *free_bytes);
 int32_t kb2_set_batch_tile(kb2_handle h, int64_t b_tile);
 int64_t kb2_last_batch_tiles(kb2_handle h);
+/* continuous rate updates (methods.jl:363-458: k follows the condition profile inside the step instead
+ * of being held between tstops): every Rodas4 stage evaluates k(T_b(t + c_s h)) from the member's
+ * profile on the device, and the non-autonomous term h d_s df/dt (df/dt = f(u; dk/dT dT/dt)) enters
+ * the stages.  Needs kb2_set_arrhenius + kb2_set_profiles; stops flagged KB2_STOP_RATE are then only
+ * forced step ends (the kinks of the profiles). */
+int32_t kb2_set_continuous(kb2_handle h, int32_t continuous);
 /* chunkwise solves: adaptive_solve! per chunk (solve_utils.jl:376-424 inside the chunk loops) on the
  * device — a member whose chunk fails (maxiters, dtmin) repeats it from the chunk's start state with
  * abstol / reltol x0.1, at most five attempts; update_tols keeps the tightened tolerances for the

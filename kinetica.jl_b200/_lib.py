@@ -42,6 +42,7 @@ SIGNATURES = {
     "kb2_set_batch_tile": (_i32, [_H, _i64]),
     "kb2_last_batch_tiles": (_i64, [_H]),
     "kb2_set_chunking": (_i32, [_H, _i32, _i32]),
+    "kb2_set_continuous": (_i32, [_H, _i32]),
     "kb2_solve_prepare": (_i32, [_H, _i64, _pf64, _i64, _f64, _f64, _f64, _f64, _i64, _i32, _i64]),
     "kb2_solve_run": (_i32, [_H, C.POINTER(C.c_float)]),
     "kb2_solve_fetch": (_i32, [_H, _pf64, _pf64, _pi32, _pi64]),
@@ -269,6 +270,9 @@ class Handle:
 
     def set_chunking(self, retry_failed_chunks=False, update_tols=False):
         self._ck(self._lib.kb2_set_chunking(self._h, int(bool(retry_failed_chunks)), int(bool(update_tols))))
+
+    def set_continuous(self, continuous=False):
+        self._ck(self._lib.kb2_set_continuous(self._h, int(bool(continuous))))
 
     def set_tiling(self, members_per_tile=0, reserved=0):
         self._ck(self._lib.kb2_set_tiling(self._h, members_per_tile, reserved))

@@ -49,6 +49,7 @@ struct kb2_ctx {
     DevFront df{};
     bool window_ok = false;       // the front plan's window fits the shared memory of an SM for the current tile size
     int chunk_retry = 0, chunk_update_tols = 0;     // kb2_set_chunking
+    int continuous = 0;                             // kb2_set_continuous
     bool has_chunk_stops = false;
     int64_t b_tile_user = 0;      // batch tile override (0: sized from the free device memory)
     int64_t last_tiles = 0;       // batch tiles of the last kb2_solve
@@ -546,6 +547,10 @@ static int ensure_ensemble(kb2_ctx *h, int64_t B, int64_t Ns)
     rc |= dev_alloc(h, P, (size_t)h->sym.panels.padded * Bt, &e.lu);
     rc |= dev_alloc(h, P, (size_t)std::max<int64_t>(h->sym.nnzJ, 1) * Bt, &e.jv);
     rc |= dev_alloc(h, P, S * Bt, &e.uc);
+    if (h->continuous) {
+        rc |= dev_alloc(h, P, R * Bt, &e.kdot);
+        rc |= dev_alloc(h, P, S * Bt, &e.ft);
+    }
     rc |= dev_alloc(h, P, S * Bt, &e.invd);
     rc |= dev_alloc(h, P, (size_t)std::max<int64_t>(Ns, 1) * S * Bt, &e.out_u);
     rc |= dev_alloc(h, P, S * Bt, &e.out_umax);
@@ -1016,8 +1021,19 @@ static int prepare_range(kb2_ctx *h, int64_t b0, int64_t B, int64_t Btot, const 
     e.t0 = t0; e.abstol = abstol; e.reltol = reltol; e.dtmin = dtmin; e.maxiters = maxiters;
     e.ban_neg = ban_negatives;
     e.chunk_retry = h->chunk_retry; e.update_tols = h->chunk_update_tols;
+    e.continuous = h->continuous;
+    if (h->continuous && h->calc_mode != 0) FAIL(h, "continuous rate updates need a calculator with a device form (kb2_set_arrhenius)");
     h->has_chunk_stops = chunked;
     h->prepared = true;
+    return 0;
+}
+
+extern "C" int32_t kb2_set_continuous(kb2_handle h, int32_t continuous)
+{
+    if (!h) return 1;
+    const int v = continuous ? 1 : 0;
+    if (v != h->continuous) { h->continuous = v; h->ens_B = -1; }      // the ensemble carries two more arrays in continuous mode
+    h->prepared = false;
     return 0;
 }
 

@@ -374,6 +374,12 @@ __global__ void __launch_bounds__(NW * 32, KB2_RHS_MINB) k_step_jac(DevNet net, 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en, ch);
         if (use_ctl && !__syncthreads_or(en.ctl[tl.b].active)) continue;
+        if (use_ctl && en.continuous) {
+            // continuous rate updates: the Jacobian belongs to k(T(t)) at the start of the step (the
+            // stages of the previous attempt left k at their own times)
+            const Ctl *c = en.ctl + tl.b;
+            tile_rates<MB, NW>(tl, net, profile_eval(en.pkind[tl.b], en.pparams + (size_t)tl.b * 16, c->t), c->active != 0, -1, w);
+        }
         const double *u = tl.u;
         if (en.u_smem) {
             stage_vector<MB, NW>(tl, smem, u, net.S * MB);

@@ -40,6 +40,11 @@ __constant__ double cC[6][6] = {
     {0.8083246795921522e+01, -0.7981132988064893e+01, -0.3152159432874371e+02, 0.1631930543123136e+02,
      -0.6058818238834054e+01, 0}};
 
+// non-autonomous form (continuous rate updates): stage times t + cT[i]*h and the time-derivative
+// weights h*cD[i]*df/dt;  c = A d (row sums), checked in tests/test_oracle_golden.py
+__constant__ double cT[6] = {0.0, 0.386, 0.21, 0.63, 1.0, 1.0};
+__constant__ double cD[6] = {0.25, -0.1043, 0.1035, -0.3620000000000023e-01, 0.0, 0.0};
+
 struct DevNet {
     int S, R, nnzJ;
     const int *rhs_ptr, *rhs_rxn, *rhs_coef;   // gather CSR by species; rhs_rxn holds positions in the rate table
@@ -90,6 +95,8 @@ struct DevEns {
     double *u, *ua, *rv, *y, *K[6], *k, *rate, *drate, *lu, *invd;
     double *jv;               // compact Jacobian values, CSC order: [tile][nnzJ][MB]
     double *uc;               // state at the start of the current chunk (chunk retry), like u
+    int continuous;           // continuous rate updates (methods.jl:363-458): k(T(t)) at every stage time, df/dt term
+    double *kdot, *ft;        // dk/dt [tile][R][MB] and df/dt [tile][S][MB] of the current step (continuous mode)
     // conditions
     int nstops;               // row length of the per-member stop tables
     const double *stop_t;     // [b*nstops + s]
@@ -150,6 +157,41 @@ __device__ __forceinline__ double arrhenius(const DevNet &net, int r, double T)
     kr = kr * kNA * net.t_mult;
     if (isnan(net.k_max)) return kr;
     return 1.0 / ((1.0 / net.k_max) + (1.0 / kr));
+}
+
+// dk/dT of the same expression (continuous rate updates: the df/dt term of the Rosenbrock stages)
+__device__ __forceinline__ double arrhenius_dT(const DevNet &net, int r, double T)
+{
+    double kr = net.A[r] * exp(-net.Ea[r] / (kR * T));
+    double dln = net.Ea[r] / (kR * T * T);                 // d ln k_r / dT
+    if (net.n) { kr *= pow(T, net.n[r]); dln += net.n[r] / T; }
+    kr = kr * kNA * net.t_mult;
+    const double dkr = kr * dln;
+    if (isnan(net.k_max)) return dkr;
+    const double k = 1.0 / ((1.0 / net.k_max) + (1.0 / kr));
+    return (kr > 0.0) ? dkr * (k / kr) * (k / kr) : 0.0;    // k = 1/(1/kmax + 1/kr)  =>  dk = (k/kr)^2 dkr
+}
+
+// dX/dt of a member's condition profile (right-continuous at the kinks, which are forced step ends)
+__device__ inline double profile_grad(int kind, const double *p, double t)
+{
+    switch (kind) {
+    case 2: case 3: return (t >= 0.0 && t < p[3]) ? p[0] : 0.0;
+    case 4: {
+        const double r1 = p[1], r2 = p[2], tb = p[7];
+        const double ts[2] = {p[3], p[5]}, te[2] = {p[4], p[6]}, rr[2] = {r1, r2};
+        double g = 0.0;
+        for (int q = 0; q < 2; ++q) {
+            if (tb > 0.0) {
+                if (t >= ts[q] - tb && t < ts[q] + tb) g += rr[q] * (t - ts[q] + tb) / (2 * tb);
+                else if (t >= ts[q] + tb && t < te[q] - tb) g += rr[q];
+                else if (t >= te[q] - tb && t < te[q] + tb) g += rr[q] * (1.0 - (t - te[q] + tb) / (2 * tb));
+            } else if (t >= ts[q] && t < te[q]) g += rr[q];
+        }
+        return g;
+    }
+    default: return 0.0;
+    }
 }
 
 // Condition value X(t) of one member (reference src/conditions/*.jl; closed forms of the
@@ -373,20 +415,33 @@ __device__ __forceinline__ double ld_stream(const double *a, unsigned long long 
 #endif
 }
 
-// K1: k[r][m] for the member's current condition value T (masked by `upd`)
-template <int MB>
-__device__ void tile_rates(const WTile<MB> &tl, const DevNet &net, double T, bool upd, int ridx)
+// A tile may be worked on by NW warps of one CTA (the streaming phases: right-hand side, Jacobian
+// values); phase boundaries inside the tile primitives are then block barriers.
+template <int NW>
+__device__ __forceinline__ void tile_sync()
 {
-    constexpr int LN = 32 / MB;
+    if (NW > 1) __syncthreads(); else __syncwarp();
+}
+
+// K1: k[r][m] for the member's current condition value T (masked by `upd`); with `kdot` also
+// dk/dt = dk/dT * Tdot (continuous rate updates).  NW warps of a CTA may share the tile.
+template <int MB, int NW = 1>
+__device__ void tile_rates(const WTile<MB> &tl, const DevNet &net, double T, bool upd, int ridx, int w = 0,
+                           double *kdot = nullptr, double Tdot = 0.0)
+{
+    constexpr int LN = 32 / MB, VL = LN * NW;
     if (upd) {
         if (net.calc_mode == 0) {
-            for (int r = tl.ln; r < net.R; r += LN) tl.k[r * MB + tl.m] = arrhenius(net, r, T);
+            for (int r = w * LN + tl.ln; r < net.R; r += VL) {
+                tl.k[r * MB + tl.m] = arrhenius(net, r, T);
+                if (kdot) kdot[r * MB + tl.m] = Tdot != 0.0 ? arrhenius_dT(net, r, T) * Tdot : 0.0;
+            }
         } else {
             const double *src = ridx < 0 ? net.kinit : net.ktab + (size_t)ridx * net.R;
-            for (int r = tl.ln; r < net.R; r += LN) tl.k[r * MB + tl.m] = src[r];
+            for (int r = w * LN + tl.ln; r < net.R; r += VL) tl.k[r * MB + tl.m] = src[r];
         }
     }
-    __syncwarp();
+    tile_sync<NW>();
 }
 
 // K2: mass-action right-hand side in two gather passes (no atomics, fixed summation order):
@@ -489,14 +544,6 @@ __device__ __forceinline__ void ell_gather(const WTile<MB> &tl, const int *order
         for (int v = 0; v < U; ++v) { sp[v] = spn[v]; hh[v] = hn[v]; ia[v] = ja[v]; ib[v] = jb[v]; ra[v] = rn[v]; }
         q0 = q1; q1 = q2; q2 = q3;
     }
-}
-
-// A tile may be worked on by NW warps of one CTA (the streaming phases: right-hand side, Jacobian
-// values); phase boundaries inside the tile primitives are then block barriers.
-template <int NW>
-__device__ __forceinline__ void tile_sync()
-{
-    if (NW > 1) __syncthreads(); else __syncwarp();
 }
 
 // Contiguous share [g0, g1) of the ELL groups for warp w of NW, balanced by ELL length (the groups

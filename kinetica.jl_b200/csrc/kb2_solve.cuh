@@ -323,6 +323,8 @@ __global__ void __launch_bounds__(32) k_step_lu(DevNet net, DevPlan pl, DevEns e
         WTile<MB> tl(tile, net, pl, en, ch);
         const Ctl *c = en.ctl + tl.b;
         if (!__any_sync(FULL, c->active)) continue;
+        if (en.continuous)      // k(T(t)) at the start of the step (see k_step_jac)
+            tile_rates(tl, net, profile_eval(en.pkind[tl.b], en.pparams + (size_t)tl.b * 16, c->t), c->active != 0, -1);
         tile_assemble_w(tl, net, pl, tl.u, 1.0 / (c->hs * kGamma), en.u_smem ? smem : nullptr);
         tile_lu(tl, pl, smem);
     }
@@ -346,6 +348,24 @@ __global__ void __launch_bounds__(NW * 32, KB2_RHS_MINB) k_stage_rhs(DevNet net,
         if (!__syncthreads_or(c->active)) continue;
         const int m = tl.m, vl = w * LN + tl.ln;
         const double *Us = tl.u;
+        if (en.continuous) {
+            // k at the stage time t + c_s h from the member's own profile; at the first stage also
+            // dk/dt and from it df/dt = f(u; dk/dt) (mass action is linear in k), which enters the
+            // first four stages with the weights h*d_s
+            const double ts = c->t + cT[s] * c->hs;
+            const int kind = en.pkind[tl.b];
+            const double *pp = en.pparams + (size_t)tl.b * 16;
+            const double Ts = profile_eval(kind, pp, ts);
+            double *kd = en.kdot + (size_t)tile * net.R * MB, *ft = en.ft + (size_t)tile * net.S * MB;
+            if (s == 0) {
+                tile_rates<MB, NW>(tl, net, Ts, c->active != 0, -1, w, kd, profile_grad(kind, pp, ts));
+                WTile<MB> tk = tl;
+                tk.k = kd;
+                tile_rhs<MB, NW>(tk, net, tl.u, ft, false, en.u_smem ? smem : nullptr, w);
+            } else if (s < 5) {
+                tile_rates<MB, NW>(tl, net, Ts, c->active != 0, -1, w);
+            }
+        }
         if (s > 0) {
             const double ih = 1.0 / c->hs;
             const double a0 = cA[s][0], a1 = cA[s][1], a2 = cA[s][2], a3 = cA[s][3], a4 = cA[s][4];
@@ -366,6 +386,12 @@ __global__ void __launch_bounds__(NW * 32, KB2_RHS_MINB) k_stage_rhs(DevNet net,
             Us = tl.ua;
         }
         tile_rhs<MB, NW>(tl, net, Us, tl.rv, s > 0, en.u_smem ? smem : nullptr, w);
+        if (en.continuous && s < 4) {
+            const double hd = c->hs * cD[s];
+            const double *ft = en.ft + (size_t)tile * net.S * MB;
+            for (int i = vl; i < net.S; i += VL) tl.rv[i * MB + m] += hd * ft[i * MB + m];
+            __syncthreads();
+        }
     }
 }
 

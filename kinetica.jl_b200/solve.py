@@ -78,8 +78,8 @@ class B200EnsembleODESolve(AbstractODESolveMethod):
         for cs in conditions:
             if not calculator.has_conditions(cs.symbols):
                 raise ValueError("Calculator does not support all of the provided conditions.")
-            if not cs.isstatic() and not cs.discrete_updates:
-                raise ValueError("The B200 ensemble path needs discrete rate updates (ts_update) for variable conditions.")
+            if not cs.isstatic() and not cs.discrete_updates and not calculator.allows_continuous():
+                raise ValueError("Calculator does not support continuous rate updates in simulations.")
         self.pars, self.conditions, self.calculator = pars, list(conditions), calculator
         self.filter = filter if filter is not None else RxFilter()
 
@@ -203,19 +203,22 @@ class ODESolveOutput:
 
 
 # ---------------------------------------------------------------- the device-backed solver
-def merge_stops(tstops, saveat, t0, tf, chunks=None):
+def merge_stops(tstops, saveat, t0, tf, chunks=None, plain=None):
     """Merged, sorted stop list of one member with flags.  Times from different sources that differ
     only in the last bits (a chunk boundary `nc * chunkstep` against a tstop of the profile's range
     arithmetic) are one stop; the tstop's value is kept (it is where the profile is evaluated)."""
     ts = np.asarray(tstops, dtype=np.float64) if tstops is not None else np.zeros(0)
     sv = np.asarray(saveat, dtype=np.float64)
     ck = np.asarray(chunks, dtype=np.float64) if chunks is not None else np.zeros(0)
+    pl = np.asarray(plain, dtype=np.float64) if plain is not None else np.zeros(0)    # forced step ends without an action
     ts = ts[(ts >= t0) & (ts <= tf)]
     sv = sv[(sv >= t0) & (sv <= tf)]
     ck = ck[(ck > t0) & (ck < tf)]
-    t_all = np.concatenate([ts, sv, ck, [tf]])
-    f_all = np.concatenate([np.full(len(ts), STOP_RATE), np.full(len(sv), STOP_SAVE), np.full(len(ck), STOP_CHUNK), [0]]).astype(np.int32)
-    pri = np.concatenate([np.zeros(len(ts)), np.ones(len(sv)), np.ones(len(ck)), [1]])      # tstops first inside a cluster
+    pl = pl[(pl > t0) & (pl < tf)]
+    t_all = np.concatenate([ts, sv, ck, pl, [tf]])
+    f_all = np.concatenate([np.full(len(ts), STOP_RATE), np.full(len(sv), STOP_SAVE), np.full(len(ck), STOP_CHUNK),
+                            np.zeros(len(pl)), [0]]).astype(np.int32)
+    pri = np.concatenate([np.zeros(len(ts)), np.ones(len(sv)), np.ones(len(ck)), np.ones(len(pl)), [1]])   # tstops first inside a cluster
     order = np.lexsort((pri, t_all))
     t_all, f_all = t_all[order], f_all[order]
     tol = 1e-12 * max(1.0, abs(tf))
@@ -326,6 +329,7 @@ class EnsembleSolver:
         else:
             self.h.set_rate_table(b["k_table"], b["k_init"])
             self.h.set_T_table(None)
+        self.h.set_continuous(self.continuous)
         # chunkwise: a failed chunk is repeated on the device (adaptive_solve! per chunk)
         self.h.set_chunking(bool(pars.solve_chunks and pars.adaptive_tols), bool(pars.update_tols))
         self._bound_B, self._bound_pars = len(conds), pars
@@ -364,6 +368,19 @@ class EnsembleSolver:
             si = pars.save_interval if pars.save_interval is not None else tf / 1000
             saveat = create_savepoints(t0, tf, si)
         B = len(conds)
+        # continuous rate updates (methods.jl:363-458): the profile's tstops (its kinks) are only forced
+        # step ends, k follows the profile inside the step on the device
+        cont = (not conds[0].isstatic()) and (not conds[0].discrete_updates)
+        if any(((not cs.isstatic()) and (not cs.discrete_updates)) != cont for cs in conds):
+            raise ValueError("discrete and continuous rate updates cannot be mixed in one ensemble")
+        if cont and self.dev is None:
+            raise ValueError("Calculator does not support continuous rate updates on the device.")
+        self.continuous = cont
+
+        def stops_of(cs):
+            ts = None if cs.isstatic() else cs.get_tstops()
+            return merge_stops(None, saveat, t0, tf, chunks, plain=ts) if cont else merge_stops(ts, saveat, t0, tf, chunks)
+
         if conds[0].isstatic():
             tstops0, same = None, all(cs.isstatic() for cs in conds)
             if not same:
@@ -378,11 +395,11 @@ class EnsembleSolver:
                     break
         bound = {"shared": same, "counts": None}
         if same:
-            stop_t, flags = merge_stops(tstops0, saveat, t0, tf, chunks)
+            stop_t, flags = stops_of(conds[0])
             self.save_t = stop_t[(flags & STOP_SAVE) != 0]
         else:
             # members with their own tstops grids (e.g. t_end differing in the last bit)
-            lists = [merge_stops(cs.get_tstops(), saveat, t0, tf, chunks) for cs in conds]
+            lists = [stops_of(cs) for cs in conds]
             nmax = max(len(t) for t, _ in lists)
             stop_t = np.zeros((B, nmax))
             flags = np.zeros((B, nmax), dtype=np.int32)
@@ -449,9 +466,6 @@ def solve_network(method: AbstractODESolveMethod, sd: SpeciesData, rd: RxData, c
     conds = method.conditions if ensemble else [method.conditions]
     if copy_network:
         calc = copy.deepcopy(calc)
-    if isinstance(method, VariableODESolve) and not method.conditions.discrete_updates:
-        raise NotImplementedError("continuous rate updates (methods.jl:363-653) are not on the B200 path yet; "
-                                  "pass ts_update to ConditionSet for discrete updates")
     for cs in conds:
         cs.solve_variable_conditions(pars)
     mask = get_filter_mask(method.filter, sd, rd)
@@ -485,6 +499,15 @@ def solve_network(method: AbstractODESolveMethod, sd: SpeciesData, rd: RxData, c
         solver.close()
     if _keep_solver is not None:
         _keep_solver["solver"] = solver          # the caller closes it (multi-GPU gather of its results)
+    continuous = getattr(solver, "continuous", False)
+
+    def vc_solution(cs):
+        """res.sol_vcs (analysis/io.jl:36-37): the variable conditions at the save times, as the
+        continuous solve carries them along with the species"""
+        from .conditions import _Sol
+        return {s: _Sol(save_t.copy(), np.asarray(p.values_at(save_t), dtype=np.float64))
+                for s, p in zip(cs.symbols, cs.profiles) if isvariable(p)}
+
     def rate_table(cs):
         """res.sol_k: k at the tstops (calculate_discrete_rates); None for static conditions"""
         if cs.isstatic() or not cs.discrete_updates:
@@ -500,6 +523,7 @@ def solve_network(method: AbstractODESolveMethod, sd: SpeciesData, rd: RxData, c
             sk = RateSolution(*sol_k)
         else:
             sk = _Lazy(lambda cs=cs: rate_table(cs)) if ensemble else rate_table(cs)
-        outs.append(ODESolveOutput(sd=sd, rd=rd, sol=sol, sol_k=sk, sol_vcs=None, pars=pars, conditions=cs,
+        outs.append(ODESolveOutput(sd=sd, rd=rd, sol=sol, sol_k=None if continuous else sk,
+                                   sol_vcs=vc_solution(cs) if continuous else None, pars=pars, conditions=cs,
                                    umax=umax[:, b].copy()))
     return outs if ensemble else outs[0]

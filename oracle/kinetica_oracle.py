@@ -724,3 +724,37 @@ def solve_trajectory(net: Network, u0, k_table, tstops, tspan, saveat, k_init=No
             out[sel] = sol.y.T[np.searchsorted(te, saveat[sel])]
         u = sol.y[:, -1]
     return out
+
+
+def solve_trajectory_continuous(net: Network, u0, k_of_t, breaks, tspan, saveat, method="Radau", rtol=1e-10, atol=1e-14):
+    """Integrate du/dt = rhs(u, k(t)) with CONTINUOUS rate constants k(t) = calculator(X(t)) — the
+    reference's continuous rate update mode (src/solving/methods.jl:363-458: k is an algebraic
+    variable bound to the condition profile).  `breaks`: the profile's tstops (its kinks), where the
+    integration is restarted like the reference's `tstops` keyword (:446).  Returns u[Ns, S]."""
+    from scipy.integrate import solve_ivp
+
+    t0, tf = float(tspan[0]), float(tspan[1])
+    saveat = np.asarray(saveat, dtype=np.float64)
+    colptr, rowval = net.pattern_csc()
+    have_pat = len(rowval) > 0
+    brk = [t0] + [float(t) for t in np.asarray(breaks, dtype=np.float64) if t0 < t < tf] + [tf]
+    u = np.array(u0, dtype=np.float64).copy()
+    out = np.zeros((len(saveat), net.S))
+
+    def f(t, y):
+        return net.rhs(y, k_of_t(t))
+
+    def jac(t, y):
+        kk = k_of_t(t)
+        return net.jac_sparse(y, kk) if (have_pat and net.S > 64) else net.jac_dense(y, kk)
+
+    for a, b in zip(brk[:-1], brk[1:]):
+        sel = np.nonzero((saveat >= a) & ((saveat < b) | ((b == tf) & (saveat <= b))))[0]
+        te = np.unique(np.append(saveat[sel], b))
+        sol = solve_ivp(f, (a, b), u, method=method, jac=jac, rtol=rtol, atol=atol, t_eval=te)
+        if not sol.success:
+            raise RuntimeError("oracle integration failed: " + sol.message)
+        if sel.size:
+            out[sel] = sol.y.T[np.searchsorted(te, saveat[sel])]
+        u = sol.y[:, -1]
+    return out

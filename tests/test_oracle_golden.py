@@ -183,6 +183,12 @@ def test_rodas4_tableau_order_conditions():
     assert np.max(np.abs(conds(b))) < 1e-13
     assert np.max(np.abs(conds(bh)[:4])) < 1e-13 and abs(conds(bh)[4]) > 1e-3
     assert np.allclose(ai, [0, 0.386, 0.21, 0.63, 1, 1], atol=1e-14)
+    # non-autonomous form (continuous rate updates, kb2_kernels.cuh cT / cD): stage times c_i = row sums
+    # of alpha, time-derivative weights d_i = gamma_i = row sums of Gamma = G's inverse relation
+    # (beta - alpha = G), and c = A d in the transformed tableau
+    d = G.sum(1)
+    assert np.allclose(d, [0.25, -0.1043, 0.1035, -0.3620000000000023e-01, 0.0, 0.0], atol=1e-13)
+    assert np.allclose(A @ d, ai, atol=1e-13)
 
 
 def test_c_oracle_known_answers(built):
