@@ -511,9 +511,10 @@ static int pick_mb(kb2_ctx *h, int64_t B)
         if (v == 1 || v == 2 || v == 4) return v;
     }
     // four members per warp tile (32-byte sectors fully used) unless the ensemble is too small to
-    // give every SM a few warps
+    // give every SM two tiles (the sweeps run one warp per tile).  Measured on C4 (1024 members):
+    // 91 / 76 / 77 ms per attempted step with 1 / 2 / 4 members per tile.
     int mb = 4;
-    while (mb > 1 && (B + mb - 1) / mb < (int64_t)4 * h->sm_count) mb >>= 1;
+    while (mb > 1 && (B + mb - 1) / mb < (int64_t)2 * h->sm_count) mb >>= 1;
     return mb;
 }
 
@@ -1113,6 +1114,10 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     const int data_bytes = (int)smem - 16;
     int g_init = 0, g_lu = 0, g_rhs = 0, g_sweep = 0, g_end = 0, g_jac = 0, g_wl = 0;
     const size_t smem_st = stream_smem(h);
+    // right-hand side with the tile's rate table in shared memory, when state vector + table fit an SM
+    const size_t smem_rs = (size_t)(h->net.S + h->net.R) * e.MB * 8;
+    bool rhs_rs = e.u_smem && smem_rs + 1024 <= h->smem_optin;
+    if (const char *ev = getenv("KB2_RHS_RS")) rhs_rs = rhs_rs && atoi(ev) != 0;      // A/B switch
     const bool window = h->window_ok;
     size_t smem_wl = 0;
     if (window) { int r = window_launch_shape(h, &smem_wl, &g_wl); if (r) return r; }
@@ -1121,7 +1126,8 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
         if (!r) r = phase_grid(h, k_step_lu<MB>, smem, ntiles, &g_lu);
         if (!r) r = stream_grid(h, k_step_jac<MB, RHS_NW>, RHS_NW * 32, smem_st, ntiles, &g_jac);
 
-        if (!r) r = stream_grid(h, k_stage_rhs<MB, RHS_NW>, RHS_NW * 32, smem_st, ntiles, &g_rhs);
+        if (!r && rhs_rs) r = stream_grid(h, k_stage_rhs<MB, RHS_NW_RS, true>, RHS_NW_RS * 32, smem_rs, ntiles, &g_rhs);
+        if (!r && !rhs_rs) r = stream_grid(h, k_stage_rhs<MB, RHS_NW, false>, RHS_NW * 32, smem_st, ntiles, &g_rhs);
         if (!r) r = phase_grid(h, k_stage_sweep<MB>, smem, ntiles, &g_sweep);
         if (!r) r = phase_grid(h, k_step_end<MB>, smem, ntiles, &g_end);
         if (r) return r;
@@ -1172,7 +1178,8 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
                 }
                 if (tm) cudaEventRecord(h->phase_ev[evi++], st);
                 for (int s = 0; s < 6; ++s) {
-                    k_stage_rhs<MB, RHS_NW><<<g_rhs, RHS_NW * 32, smem_st, st>>>(h->dn, h->dp, e, ntiles, s);
+                    if (rhs_rs) k_stage_rhs<MB, RHS_NW_RS, true><<<g_rhs, RHS_NW_RS * 32, smem_rs, st>>>(h->dn, h->dp, e, ntiles, s);
+                    else k_stage_rhs<MB, RHS_NW, false><<<g_rhs, RHS_NW * 32, smem_st, st>>>(h->dn, h->dp, e, ntiles, s);
                     if (tm) cudaEventRecord(h->phase_ev[evi++], st);
                     k_stage_sweep<MB><<<g_sweep, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, s);
                     if (tm) cudaEventRecord(h->phase_ev[evi++], st);

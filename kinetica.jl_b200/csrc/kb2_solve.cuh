@@ -334,9 +334,12 @@ __global__ void __launch_bounds__(32) k_step_lu(DevNet net, DevPlan pl, DevEns e
 // from the same loads, the stage combination rv = sum_{q<s} (C_sq/h) K_q; then rv += f(ua).
 // NW warps of one CTA share a tile: the passes are streams with short dependent chains, so what
 // they need is many warps in flight per SM (NW = 4: 28 resident warps instead of 7 on C3).
-constexpr int RHS_NW = 4;
-template <int MB, int NW>
-__global__ void __launch_bounds__(NW * 32, KB2_RHS_MINB) k_stage_rhs(DevNet net, DevPlan pl, DevEns en, int ntiles, int s)
+// RS: the tile's rate table (R*MB doubles) lives in shared memory next to the state vector, so the
+// rates never travel to HBM and back between the per-reaction pass and the gather (networks whose
+// table fits: one 16-warp CTA per SM).
+constexpr int RHS_NW = 4, RHS_NW_RS = 16;
+template <int MB, int NW, bool RS>
+__global__ void __launch_bounds__(NW * 32, RS ? 1 : KB2_RHS_MINB) k_stage_rhs(DevNet net, DevPlan pl, DevEns en, int ntiles, int s)
 {
     extern __shared__ double smem[];
     constexpr int LN = 32 / MB, VL = LN * NW;
@@ -344,6 +347,7 @@ __global__ void __launch_bounds__(NW * 32, KB2_RHS_MINB) k_stage_rhs(DevNet net,
     const int w = threadIdx.x >> 5;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en, ch);
+        if (RS) tl.rate = smem + (size_t)net.S * MB;
         const Ctl *c = en.ctl + tl.b;
         if (!__syncthreads_or(c->active)) continue;
         const int m = tl.m, vl = w * LN + tl.ln;
