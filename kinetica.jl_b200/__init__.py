@@ -7,6 +7,7 @@ from .conditions import (ConditionSet, DoubleRampGradientProfile, LinearDirectPr
                          LinearGradientProfile, NullDirectProfile, NullGradientProfile,
                          StaticConditionProfile, create_savepoints, tconvert)
 from .network import RxData, SpeciesData
+from .parallel import solve_network_sharded
 from .params import B200Rodas4, ODESimulationParams
 from .seeds import identify_next_seeds, identify_next_seeds_ensemble
 from .solve import (B200EnsembleODESolve, EnsembleSolver, ODESolveOutput, RxFilter, StaticODESolve,
