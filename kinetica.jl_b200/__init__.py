@@ -6,6 +6,7 @@ from .calculator import (AbstractKineticCalculator, DummyKineticCalculator,
 from .conditions import (ConditionSet, DoubleRampGradientProfile, LinearDirectProfile,
                          LinearGradientProfile, NullDirectProfile, NullGradientProfile,
                          StaticConditionProfile, create_savepoints, tconvert)
+from .io import load_output, save_output
 from .network import RxData, SpeciesData
 from .parallel import solve_network_sharded
 from .params import B200Rodas4, ODESimulationParams

@@ -36,7 +36,10 @@ struct DevFront {
 };
 
 constexpr int WL_NT = 256;          // threads per CTA
-constexpr int WL_CB = 4;            // columns of a register block of the update (rows: 8)
+#ifndef KB2_WL_CB
+#define KB2_WL_CB 4
+#endif
+constexpr int WL_CB = KB2_WL_CB;    // columns of a register block of the update (rows: 8)
 constexpr int WL_PF = 4;            // original values of the next front a thread fetches ahead
 
 __host__ __device__ inline int wl_list_cap(int max_nl, int max_nu) { return 16 + 2 * max_nu + 2 * max_nl; }
