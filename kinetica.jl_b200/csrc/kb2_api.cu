@@ -1114,6 +1114,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     const int data_bytes = (int)smem - 16;
     int g_init = 0, g_lu = 0, g_rhs = 0, g_sweep = 0, g_end = 0, g_jac = 0, g_wl = 0;
     const size_t smem_st = stream_smem(h);
+    const size_t smem_end = smem_st + (size_t)END_NW * e.MB * 8;      // + the cross-warp reduction buffer
     // right-hand side with the tile's rate table in shared memory, when state vector + table fit an SM
     const size_t smem_rs = (size_t)(h->net.S + h->net.R) * e.MB * 8;
     bool rhs_rs = e.u_smem && smem_rs + 1024 <= h->smem_optin;
@@ -1122,14 +1123,14 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     size_t smem_wl = 0;
     if (window) { int r = window_launch_shape(h, &smem_wl, &g_wl); if (r) return r; }
     DISPATCH_MB(e.MB, {
-        int r = phase_grid(h, k_solve_init<MB>, smem, ntiles, &g_init);
+        int r = stream_grid(h, k_solve_init<MB, END_NW>, END_NW * 32, smem_end, ntiles, &g_init);
         if (!r) r = phase_grid(h, k_step_lu<MB>, smem, ntiles, &g_lu);
         if (!r) r = stream_grid(h, k_step_jac<MB, RHS_NW>, RHS_NW * 32, smem_st, ntiles, &g_jac);
 
         if (!r && rhs_rs) r = stream_grid(h, k_stage_rhs<MB, RHS_NW_RS, true>, RHS_NW_RS * 32, smem_rs, ntiles, &g_rhs);
         if (!r && !rhs_rs) r = stream_grid(h, k_stage_rhs<MB, RHS_NW, false>, RHS_NW * 32, smem_st, ntiles, &g_rhs);
         if (!r) r = phase_grid(h, k_stage_sweep<MB>, smem, ntiles, &g_sweep);
-        if (!r) r = phase_grid(h, k_step_end<MB>, smem, ntiles, &g_end);
+        if (!r) r = stream_grid(h, k_step_end<MB, END_NW>, END_NW * 32, smem_end, ntiles, &g_end);
         if (r) return r;
     });
     h->last_ctas_per_sm = (g_lu + h->sm_count - 1) / h->sm_count;
@@ -1144,7 +1145,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     h->rounds = 0;
     CU(h, cudaMemsetAsync(e.flags, 0, KB2_FLAG_SLOTS * sizeof(int), st));
     CU(h, cudaEventRecord(h->ev0, st));
-    DISPATCH_MB(e.MB, (k_solve_init<MB><<<g_init, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes)));
+    DISPATCH_MB(e.MB, (k_solve_init<MB, END_NW><<<g_init, END_NW * 32, smem_end, st>>>(h->dn, h->dp, e, ntiles)));
     h->launches++;
     CU(h, cudaGetLastError());
     // rounds are launched in batches; flags[j] of a batch = some member is still running after
@@ -1184,7 +1185,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
                     k_stage_sweep<MB><<<g_sweep, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, s);
                     if (tm) cudaEventRecord(h->phase_ev[evi++], st);
                 }
-                k_step_end<MB><<<g_end, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, j);
+                k_step_end<MB, END_NW><<<g_end, END_NW * 32, smem_end, st>>>(h->dn, h->dp, e, ntiles, j);
                 if (tm) cudaEventRecord(h->phase_ev[evi++], st);
             });
             h->launches += window ? 15 : 14;

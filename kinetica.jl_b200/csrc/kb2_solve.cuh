@@ -126,11 +126,30 @@ __global__ void k_profile(int B, int nt, const int *kind, const double *params, 
 // ---------------------------------------------------------------------------------------------
 enum { ST_RUNNING = -1 };
 constexpr int KB2_FLAG_SLOTS = 64;
+constexpr int END_NW = 4;          // warps per tile of k_solve_init / k_step_end
 
-template <int MB>
-__device__ void tile_process_stop(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, bool at_start)
+// Sum over all lanes of a member when NW warps of a CTA share the tile: warp butterfly, then the
+// warps' partial sums through shared memory in warp order (deterministic; every lane of the member
+// ends up with the same bits).  red: NW*MB doubles of shared memory.
+template <int MB, int NW>
+__device__ __forceinline__ double member_sum_cta(double v, double *red, int w, int m, int ln)
 {
-    constexpr int LN = 32 / MB;
+    v = member_sum<MB>(v);
+    if (NW == 1) return v;
+    if (ln == 0) red[w * MB + m] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) t += red[q * MB + m];
+    __syncthreads();
+    return t;
+}
+
+template <int MB, int NW>
+__device__ void tile_process_stop(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, bool at_start, int w)
+{
+    constexpr int LN = 32 / MB, VL = LN * NW;
+    const int vl = w * LN + tl.ln;
     c.upd = 0; c.sav = -1; c.chunk = 0;
     const size_t sb = (size_t)tl.b * en.nstops;
     const bool due = at_start ? (c.status == ST_RUNNING && c.si < c.ns && en.stop_t[sb + c.si] <= en.t0)
@@ -147,12 +166,12 @@ __device__ void tile_process_stop(const WTile<MB> &tl, const DevNet &net, const 
         c.si = s + 1;
         if (c.si >= c.ns) c.status = 0;   // reached the end of tspan
     }
-    if (__any_sync(FULL, c.upd)) tile_rates(tl, net, c.T, c.upd != 0, c.ridx);
+    if (__any_sync(FULL, c.upd)) tile_rates<MB, NW>(tl, net, c.T, c.upd != 0, c.ridx, w);
     const int sv = c.sav;
     if (__any_sync(FULL, sv >= 0)) {
         if (sv >= 0)
-            for (int i = tl.ln; i < net.S; i += LN) tl.out_u[((size_t)sv * net.S + i) * MB + tl.m] = tl.u[i * MB + tl.m];
-        __syncwarp();
+            for (int i = vl; i < net.S; i += VL) tl.out_u[((size_t)sv * net.S + i) * MB + tl.m] = tl.u[i * MB + tl.m];
+        tile_sync<NW>();
     }
     // a chunk starts here (reference chunkwise solves, methods.jl:185-303, 717-865: the integrator is
     // re-initialised at every multiple of solve_chunkstep): iteration count and tolerances start
@@ -165,45 +184,45 @@ __device__ void tile_process_stop(const WTile<MB> &tl, const DevNet &net, const 
     }
     if (en.chunk_retry && __any_sync(FULL, cstart)) {
         if (cstart)
-            for (int i = tl.ln; i < net.S; i += LN) tl.uc[i * MB + tl.m] = tl.u[i * MB + tl.m];
-        __syncwarp();
+            for (int i = vl; i < net.S; i += VL) tl.uc[i * MB + tl.m] = tl.u[i * MB + tl.m];
+        tile_sync<NW>();
     }
 }
 
 // Starting step size (Hairer-Nørsett-Wanner II.4, order 4).  Called once at t0 (`initial`) and
 // again after a discrete rate update, where the RHS jumps, for members that have no step-size
 // memory yet: they get h = min(h, 0.1 * estimate).  Uses rv, ua, y as scratch.
-template <int MB>
-__device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, bool initial, double *su)
+template <int MB, int NW>
+__device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, bool initial, double *su, double *red, int w)
 {
-    constexpr int LN = 32 / MB;
-    const int m = tl.m;
-    tile_rhs(tl, net, tl.u, tl.rv, false, su);
+    constexpr int LN = 32 / MB, VL = LN * NW;
+    const int m = tl.m, vl = w * LN + tl.ln;
+    tile_rhs<MB, NW>(tl, net, tl.u, tl.rv, false, su, w);
     double d0 = 0, d1 = 0;
-    for (int i = tl.ln; i < net.S; i += LN) {
+    for (int i = vl; i < net.S; i += VL) {
         const double ui = tl.u[i * MB + m], fi = tl.rv[i * MB + m];
         const double sc = c.atol + c.rtol * fabs(ui);
         d0 += (ui / sc) * (ui / sc); d1 += (fi / sc) * (fi / sc);
     }
-    d0 = sqrt(member_sum<MB>(d0) / net.S);
-    d1 = sqrt(member_sum<MB>(d1) / net.S);
+    d0 = sqrt(member_sum_cta<MB, NW>(d0, red, w, m, tl.ln) / net.S);
+    d1 = sqrt(member_sum_cta<MB, NW>(d1, red, w, m, tl.ln) / net.S);
     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-    for (int i = tl.ln; i < net.S; i += LN) tl.ua[i * MB + m] = tl.u[i * MB + m] + h0 * tl.rv[i * MB + m];
-    __syncwarp();
-    tile_rhs(tl, net, tl.ua, tl.y, false, su);
+    for (int i = vl; i < net.S; i += VL) tl.ua[i * MB + m] = tl.u[i * MB + m] + h0 * tl.rv[i * MB + m];
+    tile_sync<NW>();
+    tile_rhs<MB, NW>(tl, net, tl.ua, tl.y, false, su, w);
     double d2 = 0;
-    for (int i = tl.ln; i < net.S; i += LN) {
+    for (int i = vl; i < net.S; i += VL) {
         const double sc = c.atol + c.rtol * fabs(tl.u[i * MB + m]);
         const double q = (tl.y[i * MB + m] - tl.rv[i * MB + m]) / sc;
         d2 += q * q;
     }
-    d2 = sqrt(member_sum<MB>(d2) / net.S) / h0;
+    d2 = sqrt(member_sum_cta<MB, NW>(d2, red, w, m, tl.ln) / net.S) / h0;
     const double dm = fmax(d1, d2);
     const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
     const double hn = fmin(100.0 * h0, h1);
     if (initial) { c.h = hn; c.hold = hn; c.nrhs += 2; }
     else if ((c.upd || c.chunk) && c.status == ST_RUNNING && !(c.hfirst > 0.0)) { c.h = fmin(c.h, 0.1 * hn); c.nrhs += 2; }
-    __syncwarp();
+    tile_sync<NW>();
 }
 
 // Step size after a discrete rate update.  The jump in k throws the fast species off their
@@ -211,12 +230,12 @@ __device__ void tile_hinit(const WTile<MB> &tl, const DevNet &net, const DevEns 
 // a profile are alike, so the step size that the controller found optimal right after the
 // previous update (c.hfirst) is the prediction for this one.  Members without that memory fall
 // back to the starting-step estimate.
-template <int MB>
-__device__ void tile_restart_h(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, double *su)
+template <int MB, int NW>
+__device__ void tile_restart_h(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, double *su, double *red, int w)
 {
     const bool upd = (c.upd || c.chunk) && c.status == ST_RUNNING;      // a chunk boundary re-initialises the integrator as well
     if (upd) { c.fresh = 1; c.firstacc = 1; }
-    if (__any_sync(FULL, upd && !(c.hfirst > 0.0))) tile_hinit(tl, net, en, c, false, su);
+    if (__any_sync(FULL, upd && !(c.hfirst > 0.0))) tile_hinit<MB, NW>(tl, net, en, c, false, su, red, w);
     if (upd && c.hfirst > 0.0) c.h = fmin(c.h, c.hfirst);
 }
 
@@ -242,26 +261,26 @@ __device__ __forceinline__ void plan_attempt(const DevEns &en, Ctl &c, int b)
 // adaptive_solve! per chunk (solve_utils.jl:376-424 inside the chunk loops of methods.jl): a member
 // whose chunk failed (maxiters, dtmin) goes back to the start of the chunk with abstol / reltol x0.1,
 // at most five attempts and never below eps; then the failure stands.
-template <int MB>
-__device__ void tile_chunk_retry(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, double *su)
+template <int MB, int NW>
+__device__ void tile_chunk_retry(const WTile<MB> &tl, const DevNet &net, const DevEns &en, Ctl &c, double *su, double *red, int w)
 {
-    constexpr int LN = 32 / MB;
+    constexpr int LN = 32 / MB, VL = LN * NW;
     const double mintol = 2.220446049250313e-16;
     const bool redo = (c.status == 1 || c.status == 2 || c.status == 3) && c.retries < 4 && c.atol / 10 > mintol && c.rtol / 10 > mintol;
     if (!__any_sync(FULL, redo)) return;
     if (redo) {
-        for (int i = tl.ln; i < net.S; i += LN) tl.u[i * MB + tl.m] = tl.uc[i * MB + tl.m];
+        for (int i = w * LN + tl.ln; i < net.S; i += VL) tl.u[i * MB + tl.m] = tl.uc[i * MB + tl.m];
         c.t = c.tchunk; c.si = c.si_chunk; c.isave = c.isave_chunk; c.T = c.Tchunk; c.ridx = c.ridx_chunk;
         c.atol /= 10; c.rtol /= 10; c.retries++; c.nretry++;
         c.iters = 0; c.status = ST_RUNNING;
         c.rejlast = 0; c.firstacc = 1; c.fresh = 0; c.errold = 1.0; c.hfirst = 0.0;
     }
-    __syncwarp();
-    tile_rates(tl, net, c.T, redo, c.ridx);          // the rate constants the chunk started with
+    tile_sync<NW>();
+    tile_rates<MB, NW>(tl, net, c.T, redo, c.ridx, w);          // the rate constants the chunk started with
     {
         // fresh starting step for the repeated members only
         Ctl tmp = c;
-        tile_hinit(tl, net, en, tmp, true, su);
+        tile_hinit<MB, NW>(tl, net, en, tmp, true, su, red, w);
         if (redo) { c.h = tmp.h; c.hold = tmp.hold; c.nrhs += 2; }
     }
     if (redo) plan_attempt(en, c, tl.b);
@@ -270,8 +289,9 @@ __device__ void tile_chunk_retry(const WTile<MB> &tl, const DevNet &net, const D
 // end of a kernel that changes the control state: one lane per member writes it back, results of
 // finished members are published, and the tile reports whether it still has work
 template <int MB>
-__device__ __forceinline__ void store_ctl(const WTile<MB> &tl, const DevEns &en, const Ctl &c, int slot)
+__device__ __forceinline__ void store_ctl(const WTile<MB> &tl, const DevEns &en, const Ctl &c, int slot, int w = 0)
 {
+    if (w != 0) return;
     if (tl.ln == 0) {
         en.ctl[tl.b] = c;
         if (tl.b < en.B && c.status != ST_RUNNING) {
@@ -284,12 +304,14 @@ __device__ __forceinline__ void store_ctl(const WTile<MB> &tl, const DevEns &en,
     if (__any_sync(FULL, c.active) && tl.lane == 0) en.flags[slot] = 1;
 }
 
-template <int MB>
-__global__ void __launch_bounds__(32) k_solve_init(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes)
+template <int MB, int NW>
+__global__ void __launch_bounds__(NW * 32, KB2_RHS_MINB) k_solve_init(DevNet net, DevPlan pl, DevEns en, int ntiles)
 {
     extern __shared__ double smem[];
-    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    BulkChan ch; ch.bar = 0; ch.par = nullptr;
     double *su = en.u_smem ? smem : nullptr;
+    double *red = smem + (en.u_smem ? (size_t)net.S * MB : 0);
+    const int w = threadIdx.x >> 5;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en, ch);
         const int b = tl.b;
@@ -305,11 +327,12 @@ __global__ void __launch_bounds__(32) k_solve_init(DevNet net, DevPlan pl, DevEn
         // initial conditions: static -> value, variable -> X_start (condition_set.jl:111-121); both sit
         // in the profile's X(0) for every supported kind
         c.T = (net.calc_mode == 0) ? profile_eval(en.pkind[b], en.pparams + (size_t)b * 16, -1.0) : 0.0;
-        tile_rates(tl, net, c.T, true, -1);     // k(initial conditions), methods.jl:668
-        tile_process_stop(tl, net, en, c, true);
-        tile_hinit(tl, net, en, c, true, su);
+        tile_rates<MB, NW>(tl, net, c.T, true, -1, w);     // k(initial conditions), methods.jl:668
+        tile_process_stop<MB, NW>(tl, net, en, c, true, w);
+        tile_hinit<MB, NW>(tl, net, en, c, true, su, red, w);
         plan_attempt(en, c, b);
-        store_ctl(tl, en, c, 0);
+        store_ctl(tl, en, c, 0, w);
+        __syncthreads();
     }
 }
 
@@ -414,31 +437,33 @@ __global__ void __launch_bounds__(32) k_stage_sweep(DevNet net, DevPlan pl, DevE
 
 // error estimate (= K6), controller, commit, stop handling (rate update, saves), and the plan of
 // the next attempt
-template <int MB>
-__global__ void __launch_bounds__(32) k_step_end(DevNet net, DevPlan pl, DevEns en, int ntiles, int data_bytes, int slot)
+template <int MB, int NW>
+__global__ void __launch_bounds__(NW * 32, KB2_RHS_MINB) k_step_end(DevNet net, DevPlan pl, DevEns en, int ntiles, int slot)
 {
     extern __shared__ double smem[];
-    constexpr int LN = 32 / MB;
-    const BulkChan ch = chan_setup<MB>(smem, data_bytes);
+    constexpr int LN = 32 / MB, VL = LN * NW;
+    BulkChan ch; ch.bar = 0; ch.par = nullptr;
     double *su = en.u_smem ? smem : nullptr;
+    double *red = smem + (en.u_smem ? (size_t)net.S * MB : 0);
+    const int w = threadIdx.x >> 5;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         WTile<MB> tl(tile, net, pl, en, ch);
-        if (!__any_sync(FULL, en.ctl[tl.b].active)) continue;
+        if (!__syncthreads_or(en.ctl[tl.b].active)) continue;
         Ctl c = en.ctl[tl.b];
-        const int m = tl.m, ln = tl.ln;
+        const int m = tl.m, ln = tl.ln, vl = w * LN + ln;
         const double hs = c.hs;
         const size_t sb = (size_t)tl.b * en.nstops;
         double e2 = 0.0;
         int neg = 0;
-        for (int i = ln; i < net.S; i += LN) {
+        for (int i = vl; i < net.S; i += VL) {
             const int o = i * MB + m;
             const double k6 = tl.K[5][o], un = tl.ua[o] + k6;
             const double sc = c.atol + c.rtol * fmax(fabs(tl.u[o]), fabs(un));
             e2 += (k6 / sc) * (k6 / sc);
             neg |= (un < 0.0);
         }
-        double err = sqrt(member_sum<MB>(e2) / net.S);
-        const double nneg = en.ban_neg ? member_sum<MB>((double)neg) : 0.0;
+        double err = sqrt(member_sum_cta<MB, NW>(e2, red, w, m, ln) / net.S);
+        const double nneg = en.ban_neg ? member_sum_cta<MB, NW>((double)neg, red, w, m, ln) : 0.0;
         if (!(err < INFINITY)) err = INFINITY;          // NaN/Inf (singular pivot, overflow) -> reject
         if (nneg > 0.0) err = fmax(err, 1e4);            // isoutofdomain, methods.jl:169-171
         if (c.active) {
@@ -467,16 +492,17 @@ __global__ void __launch_bounds__(32) k_step_end(DevNet net, DevPlan pl, DevEns 
             }
         }
         if (c.accept)
-            for (int i = ln; i < net.S; i += LN) {
+            for (int i = vl; i < net.S; i += VL) {
                 const int o = i * MB + m;
                 tl.u[o] = tl.ua[o] + tl.K[5][o];
             }
-        __syncwarp();
-        tile_process_stop(tl, net, en, c, false);
-        if (__any_sync(FULL, c.upd || c.chunk)) tile_restart_h(tl, net, en, c, su);
+        tile_sync<NW>();
+        tile_process_stop<MB, NW>(tl, net, en, c, false, w);
+        if (__any_sync(FULL, c.upd || c.chunk)) tile_restart_h<MB, NW>(tl, net, en, c, su, red, w);
         plan_attempt(en, c, tl.b);
-        if (en.chunk_retry) tile_chunk_retry(tl, net, en, c, su);
-        store_ctl(tl, en, c, slot);
+        if (en.chunk_retry) tile_chunk_retry<MB, NW>(tl, net, en, c, su, red, w);
+        store_ctl(tl, en, c, slot, w);
+        __syncthreads();
     }
 }
 
