@@ -381,6 +381,11 @@ def main():
                 "whole_solve": {"achieved": sum(pb[k] * PHASE_LAUNCHES[k] for k in pb) * attempts / (float(np.mean(dev_ms)) * 1e-3) / 1e9,
                                 "note": "algorithmic bytes of all phase kernels x attempted steps / device time of the solve"}}
     roofline["whole_solve"]["frac"] = roofline["whole_solve"]["achieved"] / peak
+    if dom == "lu" and "frac_fp64" in kd:
+        roofline.update({"frac_fp64": kd["frac_fp64"], "fp64_tflops": kd["fp64_tflops"], "fp64_peak_tflops": kd["fp64_peak_tflops"],
+                         "note": "the factorisation keeps the active submatrix in shared memory: HBM sees the compact Jacobian values in and "
+                                 "the factors out once (traffic ~1.25x the algorithmic bytes); what bounds it is on-chip — the shared-memory "
+                                 "bandwidth of the rank-8 update and the latency of the strip / pivot phases with 8 warps per SM (DESIGN.md section 5 K4)"})
 
     # ---- parity spot check against the plain-C twin, outside the timed region (N = 1) ----
     parity = None

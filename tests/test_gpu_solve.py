@@ -268,3 +268,31 @@ def test_more_tiles_than_resident_warps(built, monkeypatch):
     ref = kb.solve_network(kb.B200EnsembleODESolve(pars, conds, calc), sd, rd)
     # another tile size only changes the order of the per-member reductions
     _check(np.array([np.array(o.sol.u) for o in ref]), U, rtol=1e-5)
+
+
+def test_batch_tiling_matches_one_shot(built):
+    """kb2_solve walks an ensemble in batch tiles when it does not fit the device memory (here forced:
+    40 members in tiles of 16, last tile ragged): every member's result is what the one-shot solve gives."""
+    import kinetica_b200 as kb
+    from kinetica_b200.synthetic import synthetic_crn, synthetic_u0, SEED_BASE
+    S, R, B = 48, 160, 40
+    sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + 47)
+    calc = kb.PrecalculatedArrheniusCalculator(Ea, A, k_max=1e12)
+    pars = kb.ODESimulationParams(tspan=(0.0, 0.5), u0=synthetic_u0(S), save_interval=0.125, low_k_cutoff="none", solve_chunks=False)
+    conds = [kb.ConditionSet({"T": kb.LinearDirectProfile(rate=100.0, X_start=650.0 + 10.0 * b, X_end=700.0 + 10.0 * b)},
+                             ts_update=0.05) for b in range(B)]
+    for cs in conds:
+        cs.solve_variable_conditions(pars)
+    es = kb.EnsembleSolver(sd, rd, calc)
+    plan = es.h.memory_plan(5)
+    assert plan["bytes_per_member"] > 8 * 12 * S and plan["b_tile"] >= B
+    es.h.set_tiling(1)
+    whole = es.solve(conds, pars, synthetic_u0(S))
+    assert es.h.last_batch_tiles == 1
+    es.h.set_batch_tile(16)
+    tiled = es.solve(conds, pars, synthetic_u0(S))
+    assert es.h.last_batch_tiles == 3
+    es.close()
+    for a, b in zip(whole[:4], tiled[:4]):
+        assert np.array_equal(a, b)
+    assert np.all(whole[2] == 0)
