@@ -1296,7 +1296,7 @@ extern "C" int32_t kb2_solve(kb2_handle h, int64_t B, const double *u0, int64_t 
     }
     int rc = kb2_memory_plan(h, Ns, &per, &tile, nullptr);
     if (rc) return rc;
-    if (h->ens_B == B) tile = std::max(tile, B);
+    if (h->ens_B == B && h->b_tile_user <= 0) tile = std::max(tile, B);      // resident already: it fits
     if (tile <= 0) FAIL(h, "not enough device memory for a single member of this network");
     h->last_tiles = (B + tile - 1) / tile;
     if (B <= tile) {
