@@ -427,11 +427,12 @@ def main():
         line["cpu_baseline"] = {"value": sps, "unit": "solves/s", "cores": used, "kind": "port", "per_core": sps / used,
                                 "sample": f"{n} members evenly spaced over the sweep, {used} of {ncores} host "
                                           f"threads busy, {sec:.1f} s; plain-C oracle (same Rodas4 + sparse LU), not the Julia reference"}
-    if rank == 0:
-        print(json.dumps(line))
     es.close()
     if dist is not None:
         dist.destroy_process_group()
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)      # the last line of stdout (NCCL may print its version line earlier)
 
 
 if __name__ == "__main__":
