@@ -55,9 +55,14 @@ def load_peaks():
 
 
 def kernel_source_hash():
+    """Hash of the kernel sources the ncu traffic capture belongs to: code only (comments and blank
+    lines do not count)."""
     h = hashlib.sha256()
     for f in ("kb2_kernels.cuh", "kb2_solve.cuh", "kb2_front.cuh"):
-        h.update(open(os.path.join(ROOT, "kinetica.jl_b200", "csrc", f), "rb").read())
+        for line in open(os.path.join(ROOT, "kinetica.jl_b200", "csrc", f), "r"):
+            code = line.split("//")[0].strip()
+            if code:
+                h.update(code.encode() + b"\n")
     return h.hexdigest()[:16]
 
 

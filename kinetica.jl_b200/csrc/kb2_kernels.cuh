@@ -1,14 +1,14 @@
-// CUDA kernels of the kinetic-solve hot path (sm_100a).
+// CUDA device code of the kinetic-solve hot path (sm_100a): data structures and tile primitives.
 //
-// Execution model: ONE WARP integrates one tile of MB consecutive ensemble members (MB in
-// {1,2,4}) from t0 to the end; lane = ln * MB + m with m the member inside the tile and ln one
-// of LN = 32/MB work lanes of that member.  A CTA is a single warp and the data path has no block
-// barrier, only __syncwarp and shuffles, so the scheduler can keep every tile of the ensemble
-// resident at once; the one place where warps wait for each other is the grid-wide phase
-// alignment in front of every attempted step (kb2_solve.cuh, grid_align).
+// Execution model: the ensemble is cut into TILES of MB consecutive members (MB in {1,2,4}); a
+// tile is worked on by one warp (lane = ln * MB + m with m the member inside the tile and ln one of
+// LN = 32/MB work lanes of that member) or, in the streaming phases, by NW warps of one CTA that
+// deal the reactions / rows / ELL groups among themselves (virtual lane = w * LN + ln).  The solve
+// is a sequence of phase kernels per attempted step (kb2_solve.cuh); the factorisation has its
+// own CTA-wide kernel (kb2_front.cuh).
 // Layout: every per-member array is tile-major [tile][index][MB] — species / reaction / LU-slot
-// major, member minor — so the lanes of a warp that work on the same index touch one MB*8-byte
-// segment (a full 32-byte sector for MB = 4) and consecutive indices are consecutive in memory.
+// major, member minor — so the threads that work on the same index touch one MB*8-byte segment
+// (a full 32-byte sector for MB = 4) and consecutive indices are consecutive in memory.
 // All index tables are shared by every member, control flow is uniform inside a warp.  No atomics
 // on the data path (gather tables), results are deterministic run to run.
 #pragma once

@@ -1,5 +1,6 @@
-// Kernels that compose the warp-tile primitives: stand-alone entry points and the fused solve.
-// Every kernel runs one warp per CTA; a warp owns one tile of MB members at a time.
+// Kernels that compose the tile primitives: stand-alone entry points (kernel-level C ABI, timing)
+// and the phase kernels of the solve.  A tile of MB members is worked on by one warp (sweeps,
+// block-plan LU) or by NW warps of one CTA (right-hand side, Jacobian values, step end).
 #pragma once
 #include "kb2_kernels.cuh"
 
@@ -112,7 +113,8 @@ __global__ void k_profile(int B, int nt, const int *kind, const double *params, 
 
 // ---------------------------------------------------------------------------------------------
 // The solve: Rodas4 with per-member adaptive h, as a sequence of PHASE KERNELS per attempted step
-//     k_step_lu | 6 x ( k_stage_rhs(s) | k_stage_sweep(s) ) | k_step_end
+//     k_step_jac | k_lu_window | 6 x ( k_stage_rhs(s) | k_stage_sweep(s) ) | k_step_end
+// (k_step_lu = block-plan assembly + LU instead of the first two when the window does not fit)
 // launched back to back on one stream by the host loop of kb2_solve_run.  Every kernel walks the
 // tiles of the ensemble (one warp-tile of MB members at a time); the control state of a member
 // (Ctl) lives in global memory between kernels and is replicated in the registers of the member's
