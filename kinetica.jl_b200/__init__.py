@@ -1,8 +1,8 @@
 """kinetica_b200 — B200-native kinetic-solve hot path of Kinetica.jl behind the reference's
 calculator / ODESimulationParams / ConditionSet API.  Sources live in `kinetica.jl_b200/`;
 import as `kinetica_b200`."""
-from .calculator import (AbstractKineticCalculator, DummyKineticCalculator,
-                         PrecalculatedArrheniusCalculator)
+from .calculator import (AbstractKineticCalculator, CollisionTheoryCalculator, DummyKineticCalculator,
+                         EyringCalculator, PrecalculatedArrheniusCalculator)
 from .conditions import (ConditionSet, DoubleRampGradientProfile, LinearDirectProfile,
                          LinearGradientProfile, NullDirectProfile, NullGradientProfile,
                          StaticConditionProfile, create_savepoints, tconvert)

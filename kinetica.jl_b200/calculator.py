@@ -110,3 +110,46 @@ class PrecalculatedArrheniusCalculator(AbstractKineticCalculator):
 
     def device_arrhenius(self):
         return dict(A=self.A, Ea=self.Ea, n=self.n, k_max=self.k_max, t_mult=self.t_mult)
+
+
+K_B = 1.380649e-23        # J/K
+H_PLANCK = 6.62607015e-34  # J s
+
+
+class _ModifiedArrheniusForm(PrecalculatedArrheniusCalculator):
+    """Calculators whose temperature dependence is A*T^n*exp(-E/RT): they run on the device through
+    the T^n factor of kb2_set_arrhenius.  The device multiplies by N_A*t_mult like the
+    reference's Arrhenius functor (calculator.jl:223-232), so prefactors are stored accordingly."""
+
+    def __call__(self, *, T, **_other_conditions):
+        return super().__call__(T=T)
+
+
+class CollisionTheoryCalculator(_ModifiedArrheniusForm):
+    """Rate law of the reference ecosystem's `KPMCollisionCalculator`
+    (docs/src/tutorials/kinetic-calculators.md:129-150):
+        k_i = 1 / (1/k_max + 1/(sigma_i rho_i N_A sqrt(8 k_B T / (pi mu_i)) exp(-E_i / RT)))
+    with the activation energies E_i [J/mol], reduced masses mu_i [kg], collision cross-sections
+    sigma_i [m^2] and steric factors rho_i supplied by the caller (in the reference they come from
+    the external KPM model and the species' geometries, which are outside the hot path)."""
+
+    def __init__(self, Ea, mu, sigma, rho=None, k_max=None, t_unit="s"):
+        mu, sigma = np.asarray(mu, dtype=np.float64), np.asarray(sigma, dtype=np.float64)
+        rho = np.ones_like(mu) if rho is None else np.asarray(rho, dtype=np.float64)
+        A = sigma * rho * np.sqrt(8.0 * K_B / (np.pi * mu))
+        super().__init__(Ea, A, k_max=k_max, t_unit=t_unit, n=np.full(len(A), 0.5))
+
+
+class EyringCalculator(_ModifiedArrheniusForm):
+    """Eyring equation of the reference's `ASENEBCalculator` (docs/src/tutorials/kinetic-calculators.md:73-77),
+        k = k_B T / h * exp(dS/R) * exp(-dH/RT),
+    for caller-supplied entropies [J/mol/K] and enthalpies [J/mol] of activation (in the reference
+    they come from NEB + vibrational analysis, outside the hot path; taken as temperature-independent)."""
+
+    def __init__(self, dH, dS, k_max=None, t_unit="s"):
+        dH, dS = np.asarray(dH, dtype=np.float64), np.asarray(dS, dtype=np.float64)
+        A = (K_B / H_PLANCK) * np.exp(dS / R_GAS) / N_A          # the device formula carries the N_A of the Arrhenius functor
+        super().__init__(dH, A, k_max=k_max, t_unit=t_unit, n=np.ones(len(A)))
+
+    def has_conditions(self, symbols):
+        return all(s in ("T", "P") for s in symbols)

@@ -228,3 +228,29 @@ def test_profiles_on_device(built):
         ref = np.array([profs[i].value_at(x) for x in t])
         assert np.max(np.abs(X[i] - ref)) < 1e-10
     assert X[5][-1] == pytest.approx(200.0, abs=1e-9)
+
+
+def test_modified_arrhenius_forms_on_device(built):
+    """k = A*T^n*exp(-Ea/RT)*N_A*t_mult with n = 1/2 (collision theory) and n = 1 (Eyring) on the device
+    against the host calculators, a few ulp (pow on the device)."""
+    import kinetica_b200 as kb
+    from kinetica_b200 import _lib
+    from kinetica_b200.synthetic import synthetic_crn, SEED_BASE
+    S, R = 40, 120
+    sd, rd, _, _ = synthetic_crn(S, R, SEED_BASE + 31)
+    rng = np.random.default_rng(9)
+    Ts = np.array([300.0, 512.5, 850.0, 1200.0, 2000.0])
+    calcs = [kb.CollisionTheoryCalculator(rng.uniform(0, 2e5, R), rng.uniform(1, 40, R) * 1.66054e-27, rng.uniform(1, 9, R) * 1e-19,
+                                          rng.uniform(0.01, 1, R), k_max=1e12),
+             kb.EyringCalculator(rng.uniform(2e4, 2e5, R), rng.uniform(-80, 40, R))]
+    for calc in calcs:
+        h = _lib.Handle(0)
+        h.set_network(S, *rd.flatten())
+        h.symbolic(4)
+        d = calc.device_arrhenius()
+        h.set_arrhenius(d["A"], d["Ea"], d["n"], d["k_max"], d["t_mult"])
+        k = h.eval_k(Ts)
+        h.close()
+        for b, T in enumerate(Ts):
+            ref = calc(T=T)
+            assert np.all(np.abs(k[:, b] - ref) <= 8 * np.spacing(np.abs(ref)) + 1e-300)

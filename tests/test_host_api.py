@@ -175,3 +175,26 @@ def test_chunk_grid_follows_the_reference_formula():
     st, fl = merge_stops([0.0, 0.5, 1.0], save, 0.0, 1.0, bounds)
     assert fl[list(st).index(0.5)] == (STOP_RATE | STOP_SAVE | STOP_CHUNK) and fl[list(st).index(0.25)] == (STOP_SAVE | STOP_CHUNK)
     assert fl[-1] & STOP_CHUNK == 0                      # tf is not the start of a chunk
+
+
+def test_modified_arrhenius_calculators_match_their_documented_rate_laws():
+    """Collision theory (docs/src/tutorials/kinetic-calculators.md:144-148) and Eyring (:73-77) written
+    out directly against the A*T^n*exp(-E/RT)*N_A*t_mult form the device evaluates."""
+    import kinetica_b200 as kb
+    from kinetica_b200.calculator import K_B, H_PLANCK, N_A, R_GAS
+    rng = np.random.default_rng(5)
+    R = 12
+    Ea = rng.uniform(0, 2e5, R); mu = rng.uniform(1, 40, R) * 1.66054e-27; sig = rng.uniform(1, 9, R) * 1e-19; rho = rng.uniform(0.01, 1, R)
+    calc = kb.CollisionTheoryCalculator(Ea, mu, sig, rho, k_max=1e12)
+    for T in (300.0, 850.0, 1500.0):
+        kr = sig * rho * N_A * np.sqrt(8 * K_B * T / (np.pi * mu)) * np.exp(-Ea / (R_GAS * T))
+        assert np.allclose(calc(T=T), 1.0 / (1.0 / 1e12 + 1.0 / kr), rtol=1e-13)
+    dev = calc.device_arrhenius()
+    assert np.all(dev["n"] == 0.5) and dev["k_max"] == 1e12 and calc.has_conditions(["T"]) and calc.allows_continuous()
+    dH = rng.uniform(2e4, 2e5, R); dS = rng.uniform(-80, 40, R)
+    ey = kb.EyringCalculator(dH, dS)
+    for T in (300.0, 1200.0):
+        assert np.allclose(ey(T=T, P=1e5), K_B * T / H_PLANCK * np.exp(dS / R_GAS) * np.exp(-dH / (R_GAS * T)), rtol=1e-13)
+    assert np.all(ey.device_arrhenius()["n"] == 1.0) and ey.has_conditions(["T", "P"])
+    ey.splice([0, 3])
+    assert len(ey.Ea) == R - 2 and len(ey.n) == R - 2
