@@ -69,8 +69,10 @@ int32_t kb2_set_network(kb2_handle h, int64_t S, int64_t R,
 
 /* ---- symbolic analysis: replaces MTK `jac=true, sparse=true` pattern detection
  * (methods.jl:157-158) and KLU's symbolic phase.  ordering: 0 = minimum degree,
- * 1 = natural, 2 = caller-supplied via kb2_set_ordering, 3 = natural with dense species last,
- * 4 = auto (whichever of 0 and 3 gives the smaller padded panel storage). ---- */
+ * 1 = natural, 2 = caller-supplied via kb2_set_ordering, 3 = natural with hub species last,
+ * 5 = reverse Cuthill-McKee and 6 / 7 = Sloan's profile reduction (weights 1:2 / 2:1) on the graph
+ * without the hub species, hubs last, 4 = auto (the candidate among 0, 3, 5, 6, 7 with the smallest
+ * modelled cost of the factorisation and the triangular sweeps, see kb2_symbolic in kb2_api.cu). ---- */
 int32_t kb2_set_ordering(kb2_handle h, const int64_t *perm);
 int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, int64_t *nnzLU, int64_t *n_fma);
 int32_t kb2_get_pattern(kb2_handle h, int64_t *colptr, int64_t *rowval);          /* CSC of P_J */
@@ -78,14 +80,16 @@ int32_t kb2_get_ordering(kb2_handle h, int64_t *perm);
 int32_t kb2_get_lu_pattern(kb2_handle h, int64_t *rowptr, int64_t *colidx, int64_t *diagpos);
 /* block plan of the numeric factorisation (replaces KLU's numeric phase bookkeeping):
  * out[8] = {padded storage slots, panels, units (panel x column chunk), source-block tasks,
- * FMAs incl. padding, widest panel, target-map entries, block barriers per LU (always 0)} */
+ * FMAs incl. padding, widest panel, target-map entries, the ordering in use (what `auto` chose)} */
 int32_t kb2_get_plan_stats(kb2_handle h, int64_t *out);
 /* raw plan tables for host-side verification; which: 0 p_row0, 1 p_nrows, 2 p_width, 3 p_next,
  * 4 p_base, 5 p_cptr, 6 cols, 7 u_info (12 per unit), 8 t_info (12 per task), 9 map, 10 slot_of,
  * 11 jslot, 12 diag_slot; gather tables of the right-hand side and the Jacobian: 13 rhs_ptr,
  * 14 rhs_rxn, 15 rhs_coef, 16 rhs_order, 17 rate_pos, 18 ell_ptr, 19 ell, 20 jt_ptr, 21 jt_rxn,
  * 22 jt_pack, 23 j_order, 24 drate_pos, 25 jell_ptr, 26 jell, 27 jt_pk,
- * 28 {rhs_nlong, j_nlong, jslots, ELL group size}.
+ * 28 {rhs_nlong, j_nlong, jslots, ELL group size}; front plan of the window LU: 29 f_info (12 per
+ * front), 30 lists, 31 init, 32 {fronts, window rows, window columns, max L rows, max U columns,
+ * max init entries}, 33 pb_init (original-value sources of look-ahead pivot blocks).
  * Returns the length (copies when cap is large enough), -1 on error. */
 int64_t kb2_get_plan_array(kb2_handle h, int32_t which, int32_t *out, int64_t cap);
 

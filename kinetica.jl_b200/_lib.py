@@ -164,7 +164,7 @@ class Handle:
     def get_plan_stats(self):
         out = np.zeros(8, dtype=np.int64)
         self._ck(self._lib.kb2_get_plan_stats(self._h, _i(out)))
-        return dict(zip(["padded", "panels", "units", "tasks", "fma_padded", "max_width", "map_entries", "barriers_per_lu"],
+        return dict(zip(["padded", "panels", "units", "tasks", "fma_padded", "max_width", "map_entries", "ordering"],
                         map(int, out)))
 
     PLAN_ARRAYS = ["p_row0", "p_nrows", "p_width", "p_next", "p_base", "p_cptr", "cols", "u_info", "t_info", "map",
@@ -206,7 +206,7 @@ class Handle:
     def get_front_plan(self):
         """The front plan of the window LU (host-side verification)."""
         out = {}
-        for which, name in ((29, "f_info"), (30, "lists"), (31, "init"), (32, "meta")):
+        for which, name in ((29, "f_info"), (30, "lists"), (31, "init"), (33, "pb_init"), (32, "meta")):
             n = int(self._lib.kb2_get_plan_array(self._h, which, None, 0))
             if n < 0:
                 raise Kb2Error("front plan table %s unavailable" % name)

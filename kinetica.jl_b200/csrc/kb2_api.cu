@@ -61,6 +61,7 @@ struct kb2_ctx {
     size_t ens_fixed = 0;
     int mb_user = 0, last_ctas_per_sm = 0;
     int ens_mb = 0;               // members per warp tile of the current ensemble allocation
+    int auto_ordering = -1;       // the ordering kb2_symbolic ended up with (its choice under `auto`)
     double *stage = nullptr;      // device staging for layout conversion (caller rows <-> tiles)
     size_t stage_cap = 0;
     double *scal = nullptr;       // [Bp] per-member scalars of the kernel-level entry points
@@ -276,6 +277,7 @@ static int upload_network(kb2_ctx *h)
         rc |= dev_upload(h, P, f.lists.data(), f.lists.size(), &q.lists);
         rc |= dev_upload(h, P, f.init.data(), f.init.size(), &ini);
         q.init = (const int2 *)ini;
+        rc |= dev_upload(h, P, f.pb_init.data(), f.pb_init.size(), &q.pb_init);
     }
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
@@ -291,23 +293,48 @@ extern "C" int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, i
     if (h->net.S <= 0) FAIL(h, "set the network first");
     std::string e;
     if (ordering == 4) {
-        // auto: the candidate whose padded panel storage is smallest (triangular solves stream it)
-        Symbolic a, b2;
-        e = build_symbolic(h->net, 0, a);
-        if (e.empty()) e = build_panels(a, h->net.S);
-        if (!e.empty()) FAIL(h, e);
-        e = build_symbolic(h->net, 3, b2);
-        if (e.empty()) e = build_panels(b2, h->net.S);
-        if (!e.empty()) FAIL(h, e);
-        h->sym = (b2.panels.padded < a.panels.padded) ? std::move(b2) : std::move(a);
+        // auto: the candidate ordering with the smallest modelled cost of the numeric phases that
+        // depend on it, per tile of four members in SM cycles (calibrated on C3):
+        // the window LU's update (8 x 4 register blocks), its strips (one task per L row / U column),
+        // the per-front overhead, and the six triangular sweeps of a step, which stream the padded
+        // panel storage.  A window that does not fit shared memory with four members per CTA costs
+        // the factorisation a factor (fewer members per CTA, or the left-looking block plan).
+        const size_t cap = h->smem_optin ? h->smem_optin : (size_t)227 * 1024;
+        auto cost = [&](const Symbolic &s) {
+            const FrontPlan &f = s.fronts;
+            double blocks = 0, tasks = 0;
+            for (int32_t P = 0; P < f.NF; ++P) {
+                const int32_t *r = f.f_info.data() + (size_t)P * FrontPlan::FREC;
+                blocks += (double)((r[3] + 7) / 8) * ((r[2] + WL_CB - 1) / WL_CB);
+                tasks += r[2] + r[3];
+            }
+            double lu = 66.3 * blocks + 38.9 * tasks + 4523.0 * f.NF;
+            int mw = 0;
+            for (int c = 4; c >= 1 && !mw; c >>= 1) if (wl_smem_bytes(c, f.Wr, f.Wc, f.max_nl, f.max_nu) <= cap) mw = c;
+            lu *= mw ? 4.0 / mw : 6.0;
+            return lu + 10.36 * (double)s.panels.padded;
+        };
+        Symbolic best;
+        double best_cost = 0.0;
+        for (int cand : {3, 5, 6, 7, 0}) {
+            Symbolic c;
+            e = build_symbolic(h->net, cand, c);
+            if (e.empty()) e = build_panels(c, h->net.S);
+            if (e.empty()) e = build_fronts(c, h->net.S);
+            if (!e.empty()) FAIL(h, e);
+            const double cc = cost(c);
+            if (!best.fronts.ready || cc < best_cost) { best = std::move(c); best_cost = cc; h->auto_ordering = cand; }
+        }
+        h->sym = std::move(best);
     } else {
         e = build_symbolic(h->net, ordering, h->sym);
         if (!e.empty()) FAIL(h, e);
         e = build_panels(h->sym, h->net.S);
         if (!e.empty()) FAIL(h, e);
+        e = build_fronts(h->sym, h->net.S);
+        if (!e.empty()) FAIL(h, e);
+        h->auto_ordering = ordering;
     }
-    e = build_fronts(h->sym, h->net.S);
-    if (!e.empty()) FAIL(h, e);
     if (nnzJ) *nnzJ = h->sym.nnzJ;
     if (nnzLU) *nnzLU = h->sym.nnzLU;
     if (n_fma) *n_fma = h->sym.n_fma;
@@ -322,7 +349,7 @@ extern "C" int32_t kb2_get_plan_stats(kb2_handle h, int64_t *out)
     const PanelPlan &pp = h->sym.panels;
     out[0] = pp.padded; out[1] = (int64_t)pp.p_row0.size(); out[2] = pp.n_units();
     out[3] = pp.n_tasks(); out[4] = pp.n_fma_padded; out[5] = pp.max_width;
-    out[6] = (int64_t)pp.map.size(); out[7] = 0;     // no block barriers: warps never synchronise with each other
+    out[6] = (int64_t)pp.map.size(); out[7] = h->auto_ordering;
     return 0;
 }
 
@@ -370,6 +397,7 @@ extern "C" int64_t kb2_get_plan_array(kb2_handle h, int32_t which, int32_t *out,
     case 29: v = &h->sym.fronts.f_info; break;
     case 30: v = &h->sym.fronts.lists; break;
     case 31: v = &h->sym.fronts.init; break;
+    case 33: v = &h->sym.fronts.pb_init; break;
     case 32: {
         const FrontPlan &f = h->sym.fronts;
         const int32_t meta[6] = {f.NF, f.Wr, f.Wc, f.max_nl, f.max_nu, f.max_init};

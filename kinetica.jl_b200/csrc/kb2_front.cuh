@@ -12,15 +12,16 @@
 //   B(P)      warp 0: Crout LU of the nr x nr pivot block with shuffles (pivots on L', unit U').  Look-
 //             ahead: B(P+1) runs on warp 0 DURING D(P), on a register copy of the block taken before
 //             the update and brought up to date with the same strip values in the same order, so
-//             the serial pivot chain is off the critical path (fronts whose pivot block has entries
-//             that only become live at that front factorise it in a phase of their own)
+//             the serial pivot chain is off the critical path (entries of the block whose row or
+//             column only becomes active at P+1 start from their original values: no earlier front
+//             has them as a target)
 //   C(P)      U strip  U'[:, j] = inv(L'_PP) w[:, j]   (one thread per column and member), and
 //             L strip  L'[i, :] = x inv(U'_PP)          (one thread per row and member), in place
 //             in the window and, once, to the panel storage in HBM that the sweeps read
 //   D(P)      W[i, j] -= sum_k L'[i, k] U'[k, j]  over Lrows x Ucols, 8 x 4 register blocks
 //   clear(P)  the slots of the pivot rows and columns are zeroed, then init(P+1) (behind one more
 //             barrier in the rare front that re-uses a slot given up by the front before it)
-// Three block barriers per front (four without look-ahead or with a re-used slot).  HBM traffic of a factorisation = the compact Jacobian values in,
+// Three block barriers per front (four with a re-used slot).  HBM traffic of a factorisation = the compact Jacobian values in,
 // the factors out; nothing is read twice.  Every entry receives the same updates in the same order
 // as in the left-looking block plan (tile_lu), so the two kernels agree bit for bit.
 #pragma once
@@ -33,6 +34,7 @@ struct DevFront {
     const int *f_info;      // FrontPlan::FREC ints per front
     const int *lists;
     const int2 *init;       // {window position, (J entry + 1) << 1 | is_diagonal}
+    const int *pb_init;     // 8 x 8 source words of the pivot-block entries that are new at a look-ahead front
 };
 
 constexpr int WL_NT = 256;          // threads per CTA
@@ -200,7 +202,10 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
             const bool has_next = P + 1 < fr.NF;
             const int *fn = f + (has_next ? FREC : 0);
             const int ni = has_next ? fn[8] : 0, ioff = fn[7], hot = has_next ? fn[9] : 0;
-            const bool la = has_next && fn[10];           // the next pivot block is factorised while this front updates
+            const int laword = has_next ? fn[10] : 0;
+            const bool la = laword & 1;                   // the next pivot block is factorised while this front updates
+            const bool la_rows_new = laword & 2;          // its rows / these of its columns only become active at the next front:
+            const int la_cmask = (laword >> 8) & 255;     // their entries start from the original values, not from the window
             // ---- look ahead: the lists of front P+2 go to the third buffer (cp.async); the original
             // values of front P+1 are fetched by the warps that have no pivot block to prepare ----
             if (P + 2 < fr.NF) {
@@ -219,9 +224,11 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
                 cp_async_commit();
                 if (la) {
                     const int ln = lane / MW, nr1 = fn[0];
+                    const int *pb = fr.pb_init + (fn[11] - 1) + ln * 8;      // dereferenced only when fn[11] > 0 (some entry is new)
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (ln < nr1 && j < nr1) Dn[j] = WinM[(L1[ln] * Wc + L1[8 + j]) * MW];
+                        if (ln < nr1 && j < nr1)
+                            Dn[j] = (la_rows_new || ((la_cmask >> j) & 1)) ? init_value(pb[j]) : WinM[(L1[ln] * Wc + L1[8 + j]) * MW];
                 }
             } else {
                 // the next front's new entries: positions and sources now (in flight during the strips) ...
@@ -299,14 +306,14 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
             // of the next pivot block up to date (same strip values, same order) and factorises it. ----
             if (la && warp == 0) {
                 const int ln = lane / MW, nr1 = fn[0];
-                if (ln < nr1) {
+                if (ln < nr1 && !la_rows_new) {      // (new rows and columns are no targets of this front)
                     const double *lrow = WinM + L1[ln] * Wc * MW;
                     for (int k = 0; k < nr; ++k) {
                         const double l = lrow[pcs[k] * MW];
                         const double *urow = WinM + prs[k] * Wc * MW;
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            if (j < nr1) Dn[j] -= l * urow[L1[8 + j] * MW];
+                            if (j < nr1 && !((la_cmask >> j) & 1)) Dn[j] -= l * urow[L1[8 + j] * MW];
                     }
                 }
                 wl_pivot_block<MB, MW>(Dn, lane, nr1, Dl2 + ((P + 1) & 1) * 64 * MW, dinv2 + ((P + 1) & 1) * 8 * MW,

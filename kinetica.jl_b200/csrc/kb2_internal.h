@@ -61,7 +61,9 @@ struct FrontPlan {
     // per front: {nr, first pivot row, nu, nl, base slot of the panel, position of the diagonal block,
     //             offset into `lists`, offset into `init` (entries), init entries,
     //             1 if a row/column of this front takes a slot that the previous front gave up,
-    //             1 if the pivot block may be factorised ahead (no entry of it is new at this front), 0}
+    //             look-ahead word: bit 0 the pivot block is factorised ahead (during the previous
+    //             front's update), bit 1 its rows are new at this front, bits 8..15 its new columns,
+    //             offset + 1 into pb_init of the block's original-value sources (0: no entry is new)}
     std::vector<int32_t> f_info;
     // per front, at its offset: prs[8] pcs[8] (window slots of the pivot rows / columns, -1 beyond nr),
     // ucs[nu] (column slots of Ucols, ascending), ujj[nu] (position of that column in the panel's U
@@ -71,6 +73,9 @@ struct FrontPlan {
     // window entries that become live when front P starts and have an original value (inactive
     // entries are zero): {window position rslot*Wc + cslot, (J entry + 1) << 1 | is_diagonal}
     std::vector<int32_t> init;
+    // per look-ahead front with new pivot-block entries: 8 x 8 source words (row-major, same coding
+    // as init, 0 = not new or no original value)
+    std::vector<int32_t> pb_init;
 };
 
 // Everything the kernels need that depends only on the network (shared by all members).
@@ -115,7 +120,8 @@ struct Symbolic {
 
 // Builds derived stoichiometry; returns "" or an error message.
 std::string build_network(Network &net);
-// ordering: 0 min degree, 1 natural, 2 user (sym.perm preset)
+// ordering: 0 min degree, 1 natural, 2 user (sym.perm preset), 3 natural with hub species last,
+// 5 reverse Cuthill-McKee / 6, 7 Sloan (weights 1:2, 2:1) on the graph without the hubs, hubs last
 std::string build_symbolic(const Network &net, int ordering, Symbolic &sym);
 std::string build_panels(Symbolic &sym, int64_t S);
 std::string build_fronts(Symbolic &sym, int64_t S);

@@ -99,6 +99,133 @@ static void min_degree(int64_t S, const std::vector<int64_t> &colptr, const std:
     }
 }
 
+// Orderings for networks with locality ("banded" networks: species react with species near them,
+// plus a few hub species that react with everything).  Hub species — symmetrised degree above
+// max(32, 8 * median) — go last, by ascending degree; the others are ordered on the graph without
+// the hubs by
+//   3  their natural order,
+//   5  reverse Cuthill-McKee (George-Liu pseudo-peripheral start per component),
+//   6  Sloan's profile reduction with weights (W1, W2) = (1, 2),
+//   7  Sloan's with (2, 1).
+// The panel factorisation pads least, and the window of the right-looking LU stays smallest, when
+// the envelope of the permuted pattern is small and smooth: natural order is as good as the
+// generator's locality, RCM minimises the bandwidth, Sloan's the profile (= the fill).
+// All choices are deterministic: ties go to the smaller (degree, index).
+static void banded_order(int64_t S, const std::vector<int64_t> &colptr, const std::vector<int64_t> &rowval, int kind,
+                         std::vector<int64_t> &perm)
+{
+    std::vector<std::vector<int32_t>> adj(S);
+    for (int64_t l = 0; l < S; ++l)
+        for (int64_t p = colptr[l]; p < colptr[l + 1]; ++p)
+            if (rowval[p] != l) { adj[l].push_back((int32_t)rowval[p]); adj[rowval[p]].push_back((int32_t)l); }
+    std::vector<int64_t> deg(S);
+    for (int64_t v = 0; v < S; ++v) {
+        std::sort(adj[v].begin(), adj[v].end());
+        adj[v].erase(std::unique(adj[v].begin(), adj[v].end()), adj[v].end());
+        deg[v] = (int64_t)adj[v].size();
+    }
+    std::vector<int64_t> srt(deg);
+    std::sort(srt.begin(), srt.end());
+    const int64_t thr = std::max<int64_t>(32, 8 * srt[S / 2]);
+    std::vector<char> hub(S, 0);
+    std::vector<std::pair<int64_t, int64_t>> dense;
+    for (int64_t v = 0; v < S; ++v) if (deg[v] > thr) { hub[v] = 1; dense.emplace_back(deg[v], v); }
+    std::sort(dense.begin(), dense.end());
+    perm.clear();
+    if (kind == 3) {
+        for (int64_t v = 0; v < S; ++v) if (!hub[v]) perm.push_back(v);
+    } else {
+        // the graph without the hubs; neighbours sorted by (degree in that graph, index)
+        std::vector<int32_t> sdeg(S, 0);
+        for (int64_t v = 0; v < S; ++v) {
+            if (hub[v]) { adj[v].clear(); continue; }
+            adj[v].erase(std::remove_if(adj[v].begin(), adj[v].end(), [&](int32_t w) { return hub[w] != 0; }), adj[v].end());
+            sdeg[v] = (int32_t)adj[v].size();
+        }
+        auto by_deg = [&](int32_t a, int32_t b) { return sdeg[a] != sdeg[b] ? sdeg[a] < sdeg[b] : a < b; };
+        for (int64_t v = 0; v < S; ++v) std::sort(adj[v].begin(), adj[v].end(), by_deg);
+        std::vector<char> done(S, 0);
+        std::vector<int32_t> lev(S, -1), order, touched;
+        // breadth-first levels from `start` over the vertices that are not done; neighbours in
+        // (degree, index) order: this IS the Cuthill-McKee numbering of the component
+        auto bfs = [&](int32_t start) {
+            for (int32_t v : touched) lev[v] = -1;
+            touched.clear(); order.clear();
+            lev[start] = 0; touched.push_back(start); order.push_back(start);
+            for (size_t q = 0; q < order.size(); ++q) {
+                const int32_t v = order[q];
+                for (int32_t w : adj[v])
+                    if (lev[w] < 0 && !done[w]) { lev[w] = lev[v] + 1; touched.push_back(w); order.push_back(w); }
+            }
+            return lev[order.back()];      // eccentricity of start
+        };
+        // vertex of the last level with the smallest (degree, index)
+        auto last_level_min = [&](int ecc) {
+            int32_t best = -1;
+            for (int32_t v : order) if (lev[v] == ecc && (best < 0 || by_deg(v, best))) best = v;
+            return best;
+        };
+        auto pseudo_peripheral = [&](int32_t start) {
+            int ecc = bfs(start);
+            for (;;) {
+                const int32_t cand = last_level_min(ecc);
+                const int e2 = bfs(cand);
+                if (e2 > ecc) { start = cand; ecc = e2; }
+                else { bfs(start); return start; }
+            }
+        };
+        std::vector<int32_t> roots;
+        for (int64_t v = 0; v < S; ++v) if (!hub[v]) roots.push_back((int32_t)v);
+        std::sort(roots.begin(), roots.end(), by_deg);
+        std::vector<int64_t> seq;
+        const int W1 = kind == 7 ? 2 : 1, W2 = kind == 7 ? 1 : 2;
+        std::vector<int32_t> status(S, 0), dist(S, 0);      // Sloan: 0 inactive, 1 preactive, 2 active, 3 numbered
+        std::vector<int64_t> prio(S, 0);
+        for (int32_t v0 : roots) {
+            if (done[v0]) continue;
+            const int32_t s = pseudo_peripheral(v0);       // leaves the levels / order of the search from s behind
+            if (kind == 5) {
+                for (int32_t v : order) { done[v] = 1; seq.push_back(v); }
+                continue;
+            }
+            // Sloan: number from s towards the far end e; priority = W2 * distance to e - W1 * (degree + 1),
+            // raised by W1 whenever a neighbour is numbered or becomes active (the vertex would add
+            // fewer new vertices to the front).  Highest priority first, ties to the smaller index.
+            const int ecc = lev[order.back()];
+            const int32_t e = last_level_min(ecc);
+            std::vector<int32_t> comp(order);
+            bfs(e);
+            for (int32_t v : comp) { dist[v] = lev[v]; status[v] = 0; prio[v] = (int64_t)W2 * dist[v] - (int64_t)W1 * (sdeg[v] + 1); }
+            std::set<std::pair<int64_t, int32_t>> heap;      // (-priority, vertex)
+            auto raise = [&](int32_t w) {
+                if (status[w] == 1 || status[w] == 2) heap.erase({-prio[w], w});
+                prio[w] += W1;
+                if (status[w] == 0) status[w] = 1;
+                heap.emplace(-prio[w], w);
+            };
+            status[s] = 1;
+            heap.emplace(-prio[s], s);
+            while (!heap.empty()) {
+                const int32_t v = heap.begin()->second;
+                heap.erase(heap.begin());
+                if (status[v] == 1)
+                    for (int32_t w : adj[v]) if (!done[w] && status[w] != 3) raise(w);
+                status[v] = 3; done[v] = 1; seq.push_back(v);
+                for (int32_t w : adj[v])
+                    if (status[w] == 1 && !done[w]) {
+                        heap.erase({-prio[w], w});
+                        status[w] = 2; prio[w] += W1;
+                        heap.emplace(-prio[w], w);
+                        for (int32_t x : adj[w]) if (!done[x] && status[x] != 3) raise(x);
+                    }
+            }
+        }
+        if (kind == 5) std::reverse(seq.begin(), seq.end());
+        perm = seq;
+    }
+    for (auto &d : dense) perm.push_back(d.second);
+}
+
 std::string build_symbolic(const Network &net, int ordering, Symbolic &sym)
 {
     const int64_t S = net.S, R = net.R;
@@ -123,27 +250,8 @@ std::string build_symbolic(const Network &net, int ordering, Symbolic &sym)
     // ---- ordering ----
     if (ordering == 0) min_degree(S, sym.colptr, sym.rowval, sym.perm);
     else if (ordering == 1) { sym.perm.resize(S); for (int64_t a = 0; a < S; ++a) sym.perm[a] = a; }
-    else if (ordering == 3) {
-        // natural order with dense ("hub") species last: keeps a banded network banded, which is what
-        // the panel factorisation pads least.  dense = symmetrised degree > max(32, 8 * median).
-        std::vector<std::vector<int32_t>> adj(S);
-        for (int64_t l = 0; l < S; ++l)
-            for (int64_t p = sym.colptr[l]; p < sym.colptr[l + 1]; ++p)
-                if (sym.rowval[p] != l) { adj[l].push_back((int32_t)sym.rowval[p]); adj[sym.rowval[p]].push_back((int32_t)l); }
-        std::vector<int64_t> deg(S);
-        for (int64_t v = 0; v < S; ++v) {
-            std::sort(adj[v].begin(), adj[v].end());
-            deg[v] = std::unique(adj[v].begin(), adj[v].end()) - adj[v].begin();
-        }
-        std::vector<int64_t> srt(deg);
-        std::sort(srt.begin(), srt.end());
-        const int64_t thr = std::max<int64_t>(32, 8 * srt[S / 2]);
-        sym.perm.clear();
-        std::vector<std::pair<int64_t, int64_t>> dense;
-        for (int64_t v = 0; v < S; ++v) { if (deg[v] > thr) dense.emplace_back(deg[v], v); else sym.perm.push_back(v); }
-        std::sort(dense.begin(), dense.end());
-        for (auto &d : dense) sym.perm.push_back(d.second);
-    }
+    else if (ordering == 3 || ordering == 5 || ordering == 6 || ordering == 7)
+        banded_order(S, sym.colptr, sym.rowval, ordering, sym.perm);
     else {
         if ((int64_t)sym.perm.size() != S) return "ordering 2 requested but kb2_set_ordering was not called";
         std::vector<char> seen(S, 0);

@@ -11,6 +11,8 @@ from kinetica_b200.synthetic import synthetic_crn, SEED_BASE
 from oracle import kinetica_oracle as ko
 from test_block_plan import run_plan
 
+LA_ALL = True       # kb2_front.cpp default: every front but the first factorises its pivot block ahead
+
 
 def run_fronts(fp, plan, jv, hg_inv, padded):
     """Window LU of one member: returns (lu storage, invd) like run_plan."""
@@ -18,23 +20,41 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
     win = np.zeros(Wr * Wc)                        # inactive entries are zero
     lu = np.full(padded, np.nan)
     invd = {}
-    lists, init = fp["lists"], fp["init"]
+    lists, init, pb_init = fp["lists"], fp["init"], fp["pb_init"]
     dead_prev, dead_prev_r, dead_prev_c = False, set(), set()
-    for (nr, p0, nu, nl, base, nxt, loff, ioff, icnt, hot, la, _c) in fp["f_info"]:
+    finfo = fp["f_info"]
+
+    def orig(src):
+        v = -jv[(src >> 1) - 1] if (src >> 1) else 0.0
+        return v + hg_inv if src & 1 else v
+
+    Dn = None                                      # look-ahead copy of this front's pivot block (made during the previous front)
+    for P, (nr, p0, nu, nl, base, nxt, loff, ioff, icnt, hot, laword, pboff) in enumerate(finfo):
+        la, rows_new, cmask = laword & 1, bool(laword & 2), (laword >> 8) & 255
+        assert la == (1 if P >= 1 else 0) or not LA_ALL
         # window entries that become live at this front and have an original value
         touches_prev = False
         for pos, src in init[ioff: ioff + icnt]:
             assert win[pos] == 0.0                 # nothing was there before
-            v = -jv[(src >> 1) - 1] if (src >> 1) else 0.0
-            if src & 1:
-                v += hg_inv
-            win[pos] = v
+            win[pos] = orig(src)
             touches_prev |= (pos // Wc in dead_prev_r) or (pos % Wc in dead_prev_c) if dead_prev else False
         assert hot or not touches_prev            # values land in a slot of the previous front only in flagged fronts
         prs, pcs = lists[loff: loff + 8], lists[loff + 8: loff + 16]
-        if la:      # look-ahead fronts: no entry of the pivot block is new at this front
-            blk = {int(r) * Wc + int(c) for r in prs[:nr] for c in pcs[:nr]}
-            assert not any(int(pos) in blk for pos, _ in init[ioff: ioff + icnt])
+        blk = {int(r) * Wc + int(c): (a, b) for a, r in enumerate(prs[:nr]) for b, c in enumerate(pcs[:nr])}
+        new_in_block = {blk[int(pos)]: src for pos, src in init[ioff: ioff + icnt] if int(pos) in blk}
+        if la:
+            # entries of the block that are new at this front: exactly those the look-ahead word flags,
+            # with the same original-value sources in pb_init
+            for (a, b), src in new_in_block.items():
+                assert rows_new or (cmask >> b) & 1
+                assert pboff > 0 and pb_init[pboff - 1 + a * 8 + b] == src
+            if pboff > 0:
+                for a in range(nr):
+                    for b in range(nr):
+                        if pb_init[pboff - 1 + a * 8 + b]:
+                            assert (a, b) in new_in_block
+            else:
+                assert not new_in_block and not rows_new and not cmask
         ucs = lists[loff + 16: loff + 16 + nu]
         ujj = lists[loff + 16 + nu: loff + 16 + 2 * nu]
         lrs = lists[loff + 16 + 2 * nu: loff + 16 + 2 * nu + nl]
@@ -43,6 +63,8 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
         assert np.all(prs[:nr] >= 0) and np.all(pcs[:nr] >= 0) and np.all(prs[nr:] < 0)
         # pivot block: Crout, pivots on L, unit diagonal on U (same operation order as tile_lu)
         D = np.array([[win[prs[r] * Wc + pcs[j]] for j in range(nr)] for r in range(nr)])
+        if la:      # the copy the kernel factorises was made ahead: it must be the block as it stands now, bit for bit
+            assert Dn is not None and Dn.shape == D.shape and np.array_equal(Dn, D)
         for j in range(nr):
             inv = 1.0 / D[j, j]
             invd[p0 + j] = inv
@@ -61,6 +83,8 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
                     w[r] -= D[r, a] * w[a]
                 w[r] *= invd[p0 + r]
             U12[:, jj] = w
+            for r in range(nr):
+                win[prs[r] * Wc + ucs[jj]] = w[r]          # strips are computed in place
             lu[base + (nxt + nr + ujj[jj]) * nr: base + (nxt + nr + ujj[jj] + 1) * nr] = w
         # L strip: L'[i, :] = x inv(U'_PP)
         L21 = np.zeros((nl, nr))
@@ -70,9 +94,30 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
                 for q in range(a + 1, nr):
                     X[q] -= X[a] * D[a, q]
             L21[ii] = X
+            for q in range(nr):
+                win[lrs[ii] * Wc + pcs[q]] = X[q]
             slot0, stride = lgs[ii] & 0x0fffffff, (lgs[ii] >> 28) + 1
             for q in range(nr):
                 lu[slot0 + q * stride] = X[q]
+        # look-ahead (k_lu_window, warp 0): the next front's pivot block, copied BEFORE this front's
+        # update — entries whose row or column is new at the next front from their original values,
+        # the others from the window — and brought up to date with this front's strips
+        Dn = None
+        if P + 1 < len(finfo) and finfo[P + 1][10] & 1:
+            nr1, lw, pb1, lo1 = int(finfo[P + 1][0]), int(finfo[P + 1][10]), int(finfo[P + 1][11]), int(finfo[P + 1][6])
+            rn1, cm1 = bool(lw & 2), (lw >> 8) & 255
+            r1, c1 = lists[lo1: lo1 + 8], lists[lo1 + 8: lo1 + 16]
+            Dn = np.zeros((nr1, nr1))
+            for a in range(nr1):
+                for b in range(nr1):
+                    Dn[a, b] = orig(int(pb_init[pb1 - 1 + a * 8 + b])) if (rn1 or (cm1 >> b) & 1) else win[r1[a] * Wc + c1[b]]
+            if not rn1:
+                for a in range(nr1):
+                    for q in range(nr):
+                        l = win[r1[a] * Wc + pcs[q]]
+                        for b in range(nr1):
+                            if not (cm1 >> b) & 1:
+                                Dn[a, b] -= l * win[prs[q] * Wc + c1[b]]
         # rank-nr update, pivots in ascending order
         for ii in range(nl):
             for jj in range(nu):
@@ -90,7 +135,8 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
     return lu, invd
 
 
-@pytest.mark.parametrize("S,R,ordering", [(96, 400, 0), (200, 1000, 3), (200, 1000, 0), (420, 2100, 3), (30, 60, 1), (64, 256, 4)])
+@pytest.mark.parametrize("S,R,ordering", [(96, 400, 0), (200, 1000, 3), (200, 1000, 0), (420, 2100, 3), (30, 60, 1), (64, 256, 4),
+                                          (200, 1000, 5), (420, 2100, 6), (200, 1000, 7), (96, 400, 6)])
 def test_front_plan_matches_block_plan(S, R, ordering):
     sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + 50 + S)
     h = _lib.Handle(-1)
