@@ -54,28 +54,50 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def kernel_source_hash():
-    """Hash of the kernel sources the ncu traffic capture belongs to: code only (comments and blank
-    lines do not count)."""
+KERNEL_FILES = ("kb2_kernels.cuh", "kb2_solve.cuh", "kb2_front.cuh")
+# what the DRAM traffic of a phase kernel depends on: the kernel sources it is compiled from and, for the
+# phases that stream the factors, the block plan (padded panel storage) of the ordering in use
+TRAFFIC_DEPENDS = {
+    "jacobian": (("kb2_kernels.cuh", "kb2_solve.cuh"), False),
+    "stage_rhs": (("kb2_kernels.cuh", "kb2_solve.cuh"), False),
+    "step_end": (("kb2_kernels.cuh", "kb2_solve.cuh"), False),
+    "stage_sweeps": (("kb2_kernels.cuh", "kb2_solve.cuh"), True),
+    "lu": (KERNEL_FILES, True),
+}
+
+
+def code_hash(text):
+    """Hash of a kernel source: code only (comments and blank lines do not count)."""
     h = hashlib.sha256()
-    for f in ("kb2_kernels.cuh", "kb2_solve.cuh", "kb2_front.cuh"):
-        for line in open(os.path.join(ROOT, "kinetica.jl_b200", "csrc", f), "r"):
-            code = line.split("//")[0].strip()
-            if code:
-                h.update(code.encode() + b"\n")
+    for line in text.splitlines():
+        code = line.split("//")[0].strip()
+        if code:
+            h.update(code.encode() + b"\n")
     return h.hexdigest()[:16]
 
 
-def load_traffic(workload, B):
+def kernel_source_hashes():
+    return {f: code_hash(open(os.path.join(ROOT, "kinetica.jl_b200", "csrc", f), "r").read()) for f in KERNEL_FILES}
+
+
+def load_traffic(workload, B, padded):
     """DRAM bytes per launch of the phase kernels from an ncu capture (profiles/r02_traffic.json,
-    written by scripts/ncu_traffic.py); only valid for the kernel sources it was captured on."""
+    written by scripts/ncu_traffic.py).  A phase's figure is only used while the kernel sources it was
+    captured on are unchanged and, for the factorisation and the sweeps, the plan has the same padded
+    storage (a different ordering moves different bytes); otherwise it is null."""
     p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if not os.path.exists(p):
         return {}
     d = json.load(open(p))
-    if d.get("source_hash") != kernel_source_hash() or d.get("workload") != workload or d.get("members") != B:
+    if d.get("workload") != workload or d.get("members") != B:
         return {}
-    return d.get("dram_bytes_per_launch", {})
+    now, then = kernel_source_hashes(), d.get("source_hashes", {})
+    out = {}
+    for ph, v in d.get("dram_bytes_per_launch", {}).items():
+        files, plan = TRAFFIC_DEPENDS.get(ph, (KERNEL_FILES, True))
+        if all(now[f] == then.get(f) for f in files) and (not plan or d.get("plan", {}).get("padded") == padded):
+            out[ph] = v
+    return out
 
 
 TOLS = {"default": (1e-10, 1e-8), "throughput": (1e-8, 1e-6)}
@@ -351,7 +373,7 @@ def main():
     # ---- per-kernel roofline, from the live phase timing of the timed solves ----
     peak, peak_src = load_peaks()
     pb = phase_bytes(S, R, es.nnzJ, es.nnzLU)
-    traffic = load_traffic(args.workload, B)
+    traffic = load_traffic(args.workload, B, es.h.get_plan_stats()["padded"])
     kern = {}
     round_ms = 0.0
     for nm, (tot, n) in phase_acc.items():

@@ -27,7 +27,7 @@ std::string build_fronts(Symbolic &sym, int64_t S)
     if (!pp.ready) return "block plan missing";
     const int PR = PanelPlan::PR;
     const int32_t NP = (int32_t)pp.p_row0.size();
-    const bool la_all = !(getenv("KB2_LA_ALL") && atoi(getenv("KB2_LA_ALL")) == 0);
+    const bool la_all = getenv("KB2_LA_ALL") && atoi(getenv("KB2_LA_ALL")) != 0;
     fp.NF = NP;
     // ---- Lrows: for every panel Q the later panels P that have Q as a (complete) source block,
     // with the position of Q's first column in P's pattern ----
@@ -156,14 +156,19 @@ std::string build_fronts(Symbolic &sym, int64_t S)
         }
         fp.max_nl = std::max(fp.max_nl, nl);
         fp.max_nu = std::max(fp.max_nu, nu);
-        // look-ahead: the pivot block of P is factorised while front P-1 is still updating the
-        // window, on a copy taken before that update.  Entries of the block whose row or column
-        // only becomes active at P are not in the window yet (their slot may still belong to a
-        // pivot of P-1): the copy takes their original value instead (pb_init) and they receive
-        // no update from P-1 (no earlier panel has them as a target).  word 10 of the record:
-        // bit 0 look-ahead, bit 1 the rows of the block are new at P, bits 8..15 its new columns;
-        // word 11: offset + 1 of the block's 64 original-value sources in pb_init (0: none new).
-        // KB2_LA_ALL=0 (A/B switch) keeps look-ahead to the fronts without new entries.
+        // look-ahead: the pivot block of P is factorised by warp 0 while front P-1 is still updating
+        // the window, on a copy taken before that update — by default only if no entry of the block
+        // is new at P (all of its rows and columns were active before).  KB2_LA_ALL=1 extends it to
+        // every front: entries whose row or column only becomes active at P are not in the window
+        // yet (their slot may still belong to a pivot of P-1), so the copy takes their original
+        // value instead (pb_init) and they receive no update from P-1 (no earlier panel has them
+        // as a target).  Measured on C3 (4096 members, scripts/time_orderings.py): slower, 7.98 ->
+        // 8.42 ms with the Sloan ordering, 8.93 -> 8.99 ms with the natural one — warp 0 is missing
+        // from the update of a look-ahead front, which costs more than the separate pivot phase it
+        // saves — so it stays an A/B switch.
+        // word 10 of the record: bit 0 look-ahead, bit 1 the rows of the block are new at P,
+        // bits 8..15 its new columns; word 11: offset + 1 of the block's 64 original-value sources
+        // in pb_init (0: none new).
         const bool rows_new = act_rowpanel[P] == P;
         int32_t cmask = 0;
         for (int r = 0; r < nr; ++r) if (act_col[p0 + r] == P) cmask |= 1 << r;

@@ -43,12 +43,19 @@ constexpr int WL_NT = 256;          // threads per CTA
 #endif
 constexpr int WL_CB = KB2_WL_CB;    // columns of a register block of the update (rows: 8)
 constexpr int WL_PF = 4;            // original values of the next front a thread fetches ahead
+#ifndef KB2_WL_NZ
+#define KB2_WL_NZ 2
+#endif
+constexpr int WL_NZ = KB2_WL_NZ;    // strip tasks (substitutions) a thread runs interleaved
+#ifndef KB2_WL_DYN
+#define KB2_WL_DYN 0                // 1: the blocks of the update are handed out dynamically (see the D phase)
+#endif
 
 __host__ __device__ inline int wl_list_cap(int max_nl, int max_nu) { return 16 + 2 * max_nu + 2 * max_nl; }
 // mw = members per CTA
 __host__ __device__ inline size_t wl_smem_bytes(int mw, int Wr, int Wc, int max_nl, int max_nu)
 {
-    return (size_t)8 * mw * ((size_t)Wr * Wc + 2 * (64 + 8)) + (size_t)8 * WL_PF * WL_NT + (size_t)3 * wl_list_cap(max_nl, max_nu) * 4;
+    return (size_t)8 * mw * ((size_t)Wr * Wc + 2 * (64 + 8)) + (size_t)8 * WL_PF * WL_NT + (size_t)3 * wl_list_cap(max_nl, max_nu) * 4 + 16;
 }
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
@@ -141,6 +148,7 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
     double *stage = dinv2 + 2 * 8 * MW;                   // [WL_PF][WL_NT]: Jacobian values of the next front's new entries
     const int LCAP = wl_list_cap(fr.max_nl, fr.max_nu);
     int *lst = reinterpret_cast<int *>(stage + WL_PF * WL_NT);   // [3][LCAP]: lists of this front and the next two
+    int *dctr = lst + 3 * LCAP;                           // next block of the update to hand out (KB2_WL_DYN)
     const int tid = threadIdx.x, mw = tid % MW, x = tid / MW, lane = tid & 31, warp = tid >> 5;
     const int xl = x - 32 / MW;                           // index among the x-threads outside warp 0 (negative in warp 0)
     if (stagger_ns > 0 && blockIdx.x >= gridDim.x / 2) __nanosleep(stagger_ns);
@@ -178,6 +186,7 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
         {
             const int n = Wr * Wc * MW;
             for (int i = tid; i < n; i += WL_NT) Win[i] = 0.0;
+            if (tid == 0) *dctr = 0;
             for (int q = 0; q < 2 && q < fr.NF; ++q) {
                 const int *f = fr.f_info + q * FREC;
                 const int len = 16 + 2 * f[2] + 2 * f[3];
@@ -249,14 +258,15 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
 #pragma unroll
                 for (int r = 0; r < 8; ++r) { offU[r] = r < nr ? prs[r] * Wc * MW : 0; offL[r] = r < nr ? pcs[r] * MW : 0; }
                 const int ntask = nu + nl;
-                for (int t = x; t < ntask; t += 2 * NX) {
-                    int tt[2] = {t, t + NX < ntask ? t + NX : t};
-                    const bool two = t + NX < ntask;
-                    bool isu[2];
-                    int wb[2], gst[2];
-                    double *g[2], v[2][8];
+                for (int t = x; t < ntask; t += WL_NZ * NX) {
+                    int tt[WL_NZ];
+                    bool live[WL_NZ], isu[WL_NZ];
+                    int wb[WL_NZ], gst[WL_NZ];
+                    double *g[WL_NZ], v[WL_NZ][8];
 #pragma unroll
-                    for (int z = 0; z < 2; ++z) {
+                    for (int z = 0; z < WL_NZ; ++z) {
+                        live[z] = t + z * NX < ntask;
+                        tt[z] = live[z] ? t + z * NX : t;
                         isu[z] = tt[z] < nu;
                         if (isu[z]) {
                             wb[z] = ucs[tt[z]] * MW;
@@ -277,15 +287,15 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
 #pragma unroll
                             for (int a = 0; a < r; ++a) {
 #pragma unroll
-                                for (int z = 0; z < 2; ++z) v[z][r] -= Dl[((isu[z] ? r * 8 + a : a * 8 + r)) * MW + mw] * v[z][a];
+                                for (int z = 0; z < WL_NZ; ++z) v[z][r] -= Dl[((isu[z] ? r * 8 + a : a * 8 + r)) * MW + mw] * v[z][a];
                             }
 #pragma unroll
-                            for (int z = 0; z < 2; ++z) v[z][r] *= isu[z] ? dinv[r * MW + mw] : 1.0;
+                            for (int z = 0; z < WL_NZ; ++z) v[z][r] *= isu[z] ? dinv[r * MW + mw] : 1.0;
                         }
                     }
 #pragma unroll
-                    for (int z = 0; z < 2; ++z) {
-                        if (z == 0 || two) {
+                    for (int z = 0; z < WL_NZ; ++z) {
+                        if (live[z]) {
 #pragma unroll
                             for (int r = 0; r < 8; ++r)
                                 if (r < nr) { WinM[wb[z] + (isu[z] ? offU[r] : offL[r])] = v[z][r]; g[z][(size_t)r * gst[z]] = v[z][r]; }
@@ -304,6 +314,48 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
             __syncthreads();
             // ---- D: rank-nr update of Lrows x Ucols.  With look-ahead, warp 0 instead brings its copy
             // of the next pivot block up to date (same strip values, same order) and factorises it. ----
+#if KB2_WL_DYN
+            // the blocks of the update are handed out a warp's worth at a time from a counter in shared
+            // memory: warp 0 joins after its pivot block, and no warp waits for a last partial pass
+            if (la && warp == 0) {
+                const int ln = lane / MW, nr1 = fn[0];
+                if (ln < nr1 && !la_rows_new) {
+                    const double *lrow = WinM + L1[ln] * Wc * MW;
+                    for (int k = 0; k < nr; ++k) {
+                        const double l = lrow[pcs[k] * MW];
+                        const double *urow = WinM + prs[k] * Wc * MW;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < nr1 && !((la_cmask >> j) & 1)) Dn[j] -= l * urow[L1[8 + j] * MW];
+                    }
+                }
+                wl_pivot_block<MB, MW>(Dn, lane, nr1, Dl2 + ((P + 1) & 1) * 64 * MW, dinv2 + ((P + 1) & 1) * 8 * MW,
+                                       invd + (size_t)fn[1] * MB, lu + ((size_t)fn[4] + (size_t)fn[5] * nr1) * MB);
+            }
+            if (nu > 0 && nl > 0) {
+                constexpr int XW = 32 / MW;
+                const int ncb = (nu + WL_CB - 1) / WL_CB, nrb = (nl + 7) / 8, nblk = nrb * ncb;
+                for (;;) {
+                    int b0 = 0;
+                    if (lane == 0) b0 = atomicAdd(dctr, XW);
+                    b0 = __shfl_sync(FULL, b0, 0);
+                    if (b0 >= nblk) break;
+                    const int t = b0 + lane / MW;
+                    if (t < nblk) {
+                        const int rb = t / ncb, cb = t - rb * ncb;
+                        int ro[8], co[WL_CB];
+                        bool rok[8], cok[WL_CB];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { rok[i] = rb * 8 + i < nl; ro[i] = lrs[min(rb * 8 + i, nl - 1)] * Wc * MW; }
+#pragma unroll
+                        for (int c = 0; c < WL_CB; ++c) { cok[c] = cb + c * ncb < nu; co[c] = ucs[min(cb + c * ncb, nu - 1)] * MW; }
+                        wl_update_block<MW>(WinM, prs, pcs, ro, co, rok, cok, nr, Wc);
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) *dctr = 0;
+#else
             if (la && warp == 0) {
                 const int ln = lane / MW, nr1 = fn[0];
                 if (ln < nr1 && !la_rows_new) {      // (new rows and columns are no targets of this front)
@@ -333,6 +385,7 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
                 }
             }
             __syncthreads();
+#endif
             // ---- the pivot rows and columns of P are dead: clear their slots (inactive entries stay
             // zero), then the next front's original values (which may land in those slots) ----
             // (warp r clears pivot r: its row slot is contiguous, its column slot strided)

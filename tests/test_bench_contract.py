@@ -33,3 +33,21 @@ def test_reference_arm_line():
 def test_reference_arm_other_ranks_do_nothing():
     r = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, "--gpus", "2")
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_traffic_capture_is_used_per_phase_only_while_sources_and_plan_match():
+    """bench.py copies the DRAM bytes of profiles/r02_traffic.json (an ncu capture) into a phase's
+    `traffic` only while the kernel sources that phase is compiled from are unchanged and — for the
+    factorisation and the sweeps, which stream the factors — the plan has the padded storage of the capture."""
+    sys.path.insert(0, ROOT)
+    import bench
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    now, padded = bench.kernel_source_hashes(), d["plan"]["padded"]
+    got = bench.load_traffic(d["workload"], d["members"], padded)
+    for ph, (files, _plan) in bench.TRAFFIC_DEPENDS.items():
+        assert (ph in got) == all(now[f] == d["source_hashes"][f] for f in files), ph
+    other = bench.load_traffic(d["workload"], d["members"], padded + 1)
+    assert "lu" not in other and "stage_sweeps" not in other
+    assert {k: v for k, v in got.items() if not bench.TRAFFIC_DEPENDS[k][1]} == other
+    assert bench.load_traffic("c4", d["members"], padded) == {} and bench.load_traffic(d["workload"], 1, padded) == {}
+    assert bench.code_hash("a = 1;  // note\n\n// only a comment\nb = 2;") == bench.code_hash("a = 1;\nb = 2;   // other note")

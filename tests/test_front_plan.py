@@ -11,7 +11,6 @@ from kinetica_b200.synthetic import synthetic_crn, SEED_BASE
 from oracle import kinetica_oracle as ko
 from test_block_plan import run_plan
 
-LA_ALL = True       # kb2_front.cpp default: every front but the first factorises its pivot block ahead
 
 
 def run_fronts(fp, plan, jv, hg_inv, padded):
@@ -31,7 +30,6 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
     Dn = None                                      # look-ahead copy of this front's pivot block (made during the previous front)
     for P, (nr, p0, nu, nl, base, nxt, loff, ioff, icnt, hot, laword, pboff) in enumerate(finfo):
         la, rows_new, cmask = laword & 1, bool(laword & 2), (laword >> 8) & 255
-        assert la == (1 if P >= 1 else 0) or not LA_ALL
         # window entries that become live at this front and have an original value
         touches_prev = False
         for pos, src in init[ioff: ioff + icnt]:
@@ -137,7 +135,11 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
 
 @pytest.mark.parametrize("S,R,ordering", [(96, 400, 0), (200, 1000, 3), (200, 1000, 0), (420, 2100, 3), (30, 60, 1), (64, 256, 4),
                                           (200, 1000, 5), (420, 2100, 6), (200, 1000, 7), (96, 400, 6)])
-def test_front_plan_matches_block_plan(S, R, ordering):
+@pytest.mark.parametrize("la_all", [0, 1])
+def test_front_plan_matches_block_plan(S, R, ordering, la_all, monkeypatch):
+    """la_all = 1: look-ahead pivot blocks for every front (KB2_LA_ALL, an A/B switch of kb2_front.cpp):
+    entries that are new at their front start from their original values."""
+    monkeypatch.setenv("KB2_LA_ALL", str(la_all))
     sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + 50 + S)
     h = _lib.Handle(-1)
     h.set_network(S, *rd.flatten())
@@ -161,6 +163,10 @@ def test_front_plan_matches_block_plan(S, R, ordering):
             ref[plan["slot_of"][p]] = Wp[i, colidx[p]]
     ref_invd = run_plan(plan, ref)
     assert fp["NF"] == st["panels"] and fp["Wr"] > 0 and fp["Wc"] > 0
+    la = fp["f_info"][:, 10] & 1
+    assert la[0] == 0 and (not la_all or np.all(la[1:] == 1))
+    if not la_all:
+        assert np.all(fp["f_info"][:, 11] == 0) and len(fp["pb_init"]) == 0
     lu, invd = run_fronts(fp, plan, jv, hg, st["padded"])
     assert not np.any(np.isnan(lu))                # every storage slot is written (exactly once)
     # same updates in the same order (the interpreters differ in how they round a block product;

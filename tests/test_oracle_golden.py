@@ -214,3 +214,29 @@ def test_c_oracle_known_answers(built):
     ref = ko.solve_trajectory(net, [1.0, 0.0], np.array([[1.0], [3.0]]), np.array([0.0, 0.5]), (0.0, 1.0), np.array([0.5, 1.0]),
                               rtol=1e-12, atol=1e-15)
     assert ref[0, 0] == pytest.approx(math.exp(-0.5), rel=1e-9) and ref[1, 0] == pytest.approx(math.exp(-0.5 - 1.5), rel=1e-9)
+
+
+def test_c3_radau_fixture_agrees_with_the_c_twin(built):
+    """tests/golden/c3_radau.npz (scipy Radau on two members of the C3 sweep, full horizon; written by
+    tests/golden/make_c3_radau.py) against the plain-C Rodas4 twin at the bench tolerances: two
+    independent integrators of the oracle on the bench network, bound 1e-4 relative + 1e-9 (the
+    Rodas4 global error level at abstol 1e-10 / reltol 1e-8).  The GPU test
+    (tests/test_gpu_baseline_configs.py) checks the CUDA path against the same fixture."""
+    from kinetica_b200.synthetic import synthetic_crn, synthetic_u0, SEED_BASE
+    from oracle import c_oracle as co, kinetica_oracle as ko
+    gold = np.load(os.path.join(HERE, "golden", "c3_radau.npz"))
+    S, R = 1000, 5000
+    sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + 3)
+    net = ko.Network(S, rd.id_reacs, rd.id_prods, rd.stoic_reacs, rd.stoic_prods)
+    Ts = [float(t) for t in gold["T0"]]
+    assert gold["u"].shape == (len(Ts), 11, S) and list(gold["members"]) == [4, 7]
+    ts = ko.create_savepoints(0.0, 1.0, 1e-2)
+    ref, st, stats, _ = co.solve_rodas4(net, A, Ea, 1e12, 1.0, Ts, ts, lambda b, t: Ts[b] + 100.0 * min(t, 1.0),
+                                        synthetic_u0(S), (0.0, 1.0), gold["save_t"], nthreads=len(Ts),
+                                        abstol=1e-10, reltol=1e-8)
+    assert np.all(st == 0)
+    worst = np.max(np.abs(ref - gold["u"]) / (1e-4 * np.abs(gold["u"]) + 1e-9))
+    assert worst < 1.0, worst
+    # conservation of the synthetic networks' mass balance is not needed here: positivity and the initial state
+    assert np.array_equal(gold["u"][:, 0, :], np.tile(synthetic_u0(S), (len(Ts), 1)))
+    assert gold["u"].min() > -1e-12
