@@ -316,15 +316,20 @@ extern "C" int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, i
         };
         Symbolic best;
         double best_cost = 0.0;
+        std::string first_error;
         for (int cand : {3, 5, 6, 7, 0}) {
             Symbolic c;
             e = build_symbolic(h->net, cand, c);
             if (e.empty()) e = build_panels(c, h->net.S);
             if (e.empty()) e = build_fronts(c, h->net.S);
-            if (!e.empty()) FAIL(h, e);
+            if (!e.empty()) {       // a candidate may be out of reach (e.g. the fill of a banded order on a network without locality)
+                if (first_error.empty()) first_error = e;
+                continue;
+            }
             const double cc = cost(c);
             if (!best.fronts.ready || cc < best_cost) { best = std::move(c); best_cost = cc; h->auto_ordering = cand; }
         }
+        if (!best.fronts.ready) FAIL(h, first_error);
         h->sym = std::move(best);
     } else {
         e = build_symbolic(h->net, ordering, h->sym);

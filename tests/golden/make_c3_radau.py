@@ -12,6 +12,9 @@ import os
 import sys
 from concurrent.futures import ProcessPoolExecutor
 
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):      # the vectors are short: BLAS threads only spin
+    os.environ.setdefault(_v, "1")
+
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))

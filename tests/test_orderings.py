@@ -1,0 +1,92 @@
+"""Host-side tests of the elimination orderings of kb2_symbolic (kb2_symbolic.cpp `banded_order`,
+`auto` in kb2_api.cu) against the restatement in oracle/orderings.py and scipy's Cuthill-McKee, and of the
+cost model `auto` chooses by.  Needs no GPU (host-only handles)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.sparse.csgraph import reverse_cuthill_mckee
+
+from kinetica_b200 import _lib
+from kinetica_b200.synthetic import synthetic_crn, SEED_BASE
+from oracle import orderings as oo
+
+NETS = [(1000, 5000, 3), (200, 1000, 250), (420, 2100, 470), (64, 256, 100), (30, 60, 80)]
+
+
+def _handle(S, R, seed):
+    sd, rd, _, _ = synthetic_crn(S, R, SEED_BASE + seed)
+    h = _lib.Handle(-1)
+    h.set_network(S, *rd.flatten())
+    return h
+
+
+@pytest.mark.parametrize("S,R,seed", NETS)
+def test_banded_orderings_match_the_restatement(S, R, seed):
+    h = _handle(S, R, seed)
+    h.symbolic(1)
+    colptr, rowval = h.get_pattern()
+    for code, kind, w in ((3, "natural", None), (5, "rcm", None), (6, "sloan", (1, 2)), (7, "sloan", (2, 1))):
+        h.symbolic(code)
+        perm = h.get_ordering()
+        assert sorted(perm.tolist()) == list(range(S))
+        ref = oo.banded_order(S, colptr, rowval, kind, w) if w else oo.banded_order(S, colptr, rowval, kind)
+        assert np.array_equal(perm, ref), (code, kind)
+        assert h.get_plan_stats()["ordering"] == code
+    h.close()
+
+
+def test_rcm_is_scipys_on_the_graph_without_the_hubs():
+    S, R, seed = 1000, 5000, 3
+    h = _handle(S, R, seed)
+    h.symbolic(5)
+    perm = h.get_ordering()
+    colptr, rowval = h.get_pattern()
+    h.close()
+    adj, sdeg, hub, hubs = oo.hubless_graph(S, colptr, rowval)
+    assert len(hubs) == 8 and sorted(hubs) == list(range(8))      # the generator's hub species
+    keep = np.where(~hub)[0]
+    pos = -np.ones(S, dtype=int); pos[keep] = np.arange(len(keep))
+    rows = [pos[v] for v in keep for _ in adj[v]]
+    cols = [pos[w] for v in keep for w in adj[v]]
+    G = sp.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(len(keep), len(keep))).tocsr()
+    r = reverse_cuthill_mckee(G, symmetric_mode=True)
+    assert np.array_equal(perm[:len(keep)], keep[r]) and perm[len(keep):].tolist() == hubs
+
+
+def _cost(h, cap=227 * 1024):
+    ps, fp = h.get_plan_stats(), h.get_front_plan()
+    f = fp["f_info"]
+    blocks = float(np.sum(((f[:, 3] + 7) // 8) * ((f[:, 2] + 3) // 4)))
+    lu = 66.3 * blocks + 38.9 * float(np.sum(f[:, 2] + f[:, 3])) + 4523.0 * fp["NF"]
+    lcap = 16 + 2 * fp["max_nu"] + 2 * fp["max_nl"]
+    fits = [mw for mw in (4, 2, 1) if 8 * mw * (fp["Wr"] * fp["Wc"] + 144) + 8 * 4 * 256 + 3 * lcap * 4 + 16 <= cap]
+    lu *= 4.0 / fits[0] if fits else 6.0
+    return lu + 10.36 * ps["padded"]
+
+
+@pytest.mark.parametrize("S,R,seed", NETS)
+def test_auto_keeps_the_candidate_with_the_smallest_modelled_cost(S, R, seed):
+    h = _handle(S, R, seed)
+    costs = {}
+    for code in (3, 5, 6, 7, 0):
+        h.symbolic(code)
+        costs[code] = _cost(h)
+    h.symbolic(4)
+    chosen = h.get_plan_stats()["ordering"]
+    assert chosen in costs and costs[chosen] == min(costs.values())
+    assert abs(_cost(h) - costs[chosen]) < 1e-6 * costs[chosen]
+    h.close()
+
+
+def test_bench_network_gets_the_profile_ordering():
+    """C3: Sloan's ordering (1:2) — a tenth less padded storage and a fifth fewer padded FMAs than the
+    natural order with hubs last, and a window that fits shared memory with four members per CTA."""
+    h = _handle(1000, 5000, 3)
+    h.symbolic(3)
+    nat = h.get_plan_stats()
+    h.symbolic(4)
+    st, fp = h.get_plan_stats(), h.get_front_plan()
+    assert st["ordering"] == 6
+    assert st["padded"] < 0.92 * nat["padded"] and st["fma_padded"] < 0.82 * nat["fma_padded"]
+    assert 8 * 4 * (fp["Wr"] * fp["Wc"] + 144) < 200 * 1024
+    h.close()
