@@ -26,13 +26,10 @@ def _sweep(kb, Ts, ts_update):
             for T in Ts]
 
 
-def test_c3_network_at_bench_tolerances(built, monkeypatch):
-    """S = 1000 / R = 5000, seed 20261018 + 3, auto ordering, four members per tile (the bench layout:
-    window LU with the 96 x 63 window, staged state vector), 8 members spread over the sweep."""
+def _c3_solve(monkeypatch, B=8):
     import kinetica_b200 as kb
     from kinetica_b200.synthetic import synthetic_crn, synthetic_u0, SEED_BASE
-    from oracle import c_oracle as co, kinetica_oracle as ko
-    S, R, B = 1000, 5000, 8
+    S, R = 1000, 5000
     sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + 3)
     calc = kb.PrecalculatedArrheniusCalculator(Ea, A, k_max=1e12)
     pars = kb.ODESimulationParams(tspan=(0.0, 1.0), u0=synthetic_u0(S), save_interval=0.1, low_k_cutoff="none",
@@ -41,6 +38,15 @@ def test_c3_network_at_bench_tolerances(built, monkeypatch):
     conds = _sweep(kb, Ts, 1e-2)
     monkeypatch.setenv("KB2_MB", "4")
     outs = kb.solve_network(kb.B200EnsembleODESolve(pars, conds, calc), sd, rd)
+    return S, R, rd, Ea, A, pars, Ts, conds, outs
+
+
+def test_c3_network_at_bench_tolerances(built, monkeypatch):
+    """S = 1000 / R = 5000, seed 20261018 + 3, auto ordering, four members per tile (the bench layout:
+    window LU, staged state vector), 8 members spread over the sweep, against the plain-C twin."""
+    from kinetica_b200.synthetic import synthetic_u0
+    from oracle import c_oracle as co, kinetica_oracle as ko
+    S, R, rd, Ea, A, pars, Ts, conds, outs = _c3_solve(monkeypatch)
     net = ko.Network(S, rd.id_reacs, rd.id_prods, rd.stoic_reacs, rd.stoic_prods)
     ts = conds[0].get_tstops()
     assert len(ts) == 101
@@ -55,17 +61,24 @@ def test_c3_network_at_bench_tolerances(built, monkeypatch):
         _check(o.umax, ref[b].max(axis=0), rtol=1e-4)                     # per-species maxima vs the ORACLE's
         assert abs(int(o.sol.stats[0]) - int(stats[b, 0])) <= 0.05 * stats[b, 0]
         assert o.sol_k is not None and o.sol_k.u.shape == (101, R) and o.sol_vcs is None
-    b = B // 2
+
+
+def test_c3_network_against_radau_fixture(built, monkeypatch):
+    """The same solve against the INDEPENDENT integrator of the oracle (scipy Radau, rtol 1e-8, restarted at
+    every rate update) over the full horizon, two members: ten minutes of CPU per member, so the
+    trajectories are a committed fixture (tests/golden/c3_radau.npz, written by
+    tests/golden/make_c3_radau.py, pinned against the C twin in tests/test_oracle_golden.py)."""
+    from oracle import kinetica_oracle as ko
+    S, R, rd, Ea, A, pars, Ts, conds, outs = _c3_solve(monkeypatch)
+    ts = conds[0].get_tstops()
+    b = len(Ts) // 2
     ocalc = ko.PrecalculatedArrheniusCalculator(Ea, A, k_max=1e12)
     ktab = np.array([ocalc(Ts[b] + 100.0 * min(t, 1.0)) for t in ts])
     assert np.allclose(outs[b].sol_k.u, ktab, rtol=1e-14, atol=0)         # res.sol_k = the reference's k_precalc table
-    # two members against the independent integrator (scipy Radau, rtol 1e-8, restarted at every rate
-    # update) over the FULL horizon: ten minutes of CPU per member, so the trajectories are a committed
-    # fixture (tests/golden/c3_radau.npz, written by tests/golden/make_c3_radau.py)
     gold = np.load(os.path.join(HERE, "golden", "c3_radau.npz"))
     assert np.allclose(outs[0].sol.t, gold["save_t"], rtol=0, atol=1e-15)
     for q, bm in enumerate(gold["members"]):
-        assert gold["T0"][q] == Ts[bm]
+        assert gold["T0"][q] == Ts[bm] and outs[bm].sol.retcode == "Success"
         _check(np.array(outs[bm].sol.u), gold["u"][q], rtol=1e-4)
 
 
