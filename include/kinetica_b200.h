@@ -89,7 +89,7 @@ int32_t kb2_get_plan_stats(kb2_handle h, int64_t *out);
  * 22 jt_pack, 23 j_order, 24 drate_pos, 25 jell_ptr, 26 jell, 27 jt_pk,
  * 28 {rhs_nlong, j_nlong, jslots, ELL group size}; front plan of the window LU: 29 f_info (12 per
  * front), 30 lists, 31 init, 32 {fronts, window rows, window columns, max L rows, max U columns,
- * max init entries}, 33 pb_init (original-value sources of look-ahead pivot blocks).
+ * max init entries}.
  * Returns the length (copies when cap is large enough), -1 on error. */
 int64_t kb2_get_plan_array(kb2_handle h, int32_t which, int32_t *out, int64_t cap);
 

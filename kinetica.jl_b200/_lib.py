@@ -206,7 +206,7 @@ class Handle:
     def get_front_plan(self):
         """The front plan of the window LU (host-side verification)."""
         out = {}
-        for which, name in ((29, "f_info"), (30, "lists"), (31, "init"), (33, "pb_init"), (32, "meta")):
+        for which, name in ((29, "f_info"), (30, "lists"), (31, "init"), (32, "meta")):
             n = int(self._lib.kb2_get_plan_array(self._h, which, None, 0))
             if n < 0:
                 raise Kb2Error("front plan table %s unavailable" % name)

@@ -277,7 +277,6 @@ static int upload_network(kb2_ctx *h)
         rc |= dev_upload(h, P, f.lists.data(), f.lists.size(), &q.lists);
         rc |= dev_upload(h, P, f.init.data(), f.init.size(), &ini);
         q.init = (const int2 *)ini;
-        rc |= dev_upload(h, P, f.pb_init.data(), f.pb_init.size(), &q.pb_init);
     }
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
@@ -402,7 +401,6 @@ extern "C" int64_t kb2_get_plan_array(kb2_handle h, int32_t which, int32_t *out,
     case 29: v = &h->sym.fronts.f_info; break;
     case 30: v = &h->sym.fronts.lists; break;
     case 31: v = &h->sym.fronts.init; break;
-    case 33: v = &h->sym.fronts.pb_init; break;
     case 32: {
         const FrontPlan &f = h->sym.fronts;
         const int32_t meta[6] = {f.NF, f.Wr, f.Wc, f.max_nl, f.max_nu, f.max_init};

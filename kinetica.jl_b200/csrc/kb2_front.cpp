@@ -15,7 +15,6 @@
 #include "kb2_internal.h"
 
 #include <algorithm>
-#include <cstdlib>
 
 namespace kb2 {
 
@@ -27,7 +26,6 @@ std::string build_fronts(Symbolic &sym, int64_t S)
     if (!pp.ready) return "block plan missing";
     const int PR = PanelPlan::PR;
     const int32_t NP = (int32_t)pp.p_row0.size();
-    const bool la_all = getenv("KB2_LA_ALL") && atoi(getenv("KB2_LA_ALL")) != 0;
     fp.NF = NP;
     // ---- Lrows: for every panel Q the later panels P that have Q as a (complete) source block,
     // with the position of Q's first column in P's pattern ----
@@ -156,37 +154,13 @@ std::string build_fronts(Symbolic &sym, int64_t S)
         }
         fp.max_nl = std::max(fp.max_nl, nl);
         fp.max_nu = std::max(fp.max_nu, nu);
-        // look-ahead: the pivot block of P is factorised by warp 0 while front P-1 is still updating
-        // the window, on a copy taken before that update — by default only if no entry of the block
-        // is new at P (all of its rows and columns were active before).  KB2_LA_ALL=1 extends it to
-        // every front: entries whose row or column only becomes active at P are not in the window
-        // yet (their slot may still belong to a pivot of P-1), so the copy takes their original
-        // value instead (pb_init) and they receive no update from P-1 (no earlier panel has them
-        // as a target).  Measured on C3 (4096 members, scripts/time_orderings.py): slower, 7.98 ->
-        // 8.42 ms with the Sloan ordering, 8.93 -> 8.99 ms with the natural one — warp 0 is missing
-        // from the update of a look-ahead front, which costs more than the separate pivot phase it
-        // saves — so it stays an A/B switch.
-        // word 10 of the record: bit 0 look-ahead, bit 1 the rows of the block are new at P,
-        // bits 8..15 its new columns; word 11: offset + 1 of the block's 64 original-value sources
-        // in pb_init (0: none new).
-        const bool rows_new = act_rowpanel[P] == P;
-        int32_t cmask = 0;
-        for (int r = 0; r < nr; ++r) if (act_col[p0 + r] == P) cmask |= 1 << r;
-        const bool any_new = rows_new || cmask != 0;
-        int32_t la = P >= 1 && (la_all || !any_new);
-        int32_t pboff = 0;
-        if (la && any_new) {
-            la |= (rows_new ? 2 : 0) | (cmask << 8);
-            pboff = (int32_t)fp.pb_init.size() + 1;
-            fp.pb_init.resize(fp.pb_init.size() + PR * PR, 0);
-            int32_t *pb = fp.pb_init.data() + (pboff - 1);
-            for (int r = 0; r < nr; ++r)
-                for (int64_t q = sym.rowptr[p0 + r]; q < sym.rowptr[p0 + r + 1]; ++q) {
-                    const int64_t j = sym.colidx[q] - p0;
-                    if (j >= 0 && j < nr && (rows_new || ((cmask >> j) & 1))) pb[r * PR + j] = sym.slot_src[q];
-                }
-        }
-        const int32_t rec[FrontPlan::FREC] = {nr, p0, nu, nl, pp.p_base[P], next, loff, 0, (int32_t)init_of[P].size(), hot[P], la, pboff};
+        // look-ahead: the pivot block of P can be factorised while front P-1 is still updating the
+        // window if all of its rows and columns were active before P (none of its entries is new).
+        // (Extending it to every front — new entries taken from their original values — was measured
+        // slower: warp 0 is missing from the update of a look-ahead front)
+        int32_t la = P >= 1 && act_rowpanel[P] < P;
+        for (int r = 0; r < nr && la; ++r) la = act_col[p0 + r] < P;
+        const int32_t rec[FrontPlan::FREC] = {nr, p0, nu, nl, pp.p_base[P], next, loff, 0, (int32_t)init_of[P].size(), hot[P], la, 0};
         fp.f_info.insert(fp.f_info.end(), rec, rec + FrontPlan::FREC);
         // ---- eliminate: the pivot rows and columns leave the window ----
         for (int r = 0; r < nr; ++r) {

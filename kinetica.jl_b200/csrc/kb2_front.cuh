@@ -12,16 +12,15 @@
 //   B(P)      warp 0: Crout LU of the nr x nr pivot block with shuffles (pivots on L', unit U').  Look-
 //             ahead: B(P+1) runs on warp 0 DURING D(P), on a register copy of the block taken before
 //             the update and brought up to date with the same strip values in the same order, so
-//             the serial pivot chain is off the critical path (entries of the block whose row or
-//             column only becomes active at P+1 start from their original values: no earlier front
-//             has them as a target)
+//             the serial pivot chain is off the critical path (fronts whose pivot block has entries
+//             that only become live at that front factorise it in a phase of their own)
 //   C(P)      U strip  U'[:, j] = inv(L'_PP) w[:, j]   (one thread per column and member), and
 //             L strip  L'[i, :] = x inv(U'_PP)          (one thread per row and member), in place
 //             in the window and, once, to the panel storage in HBM that the sweeps read
 //   D(P)      W[i, j] -= sum_k L'[i, k] U'[k, j]  over Lrows x Ucols, 8 x 4 register blocks
 //   clear(P)  the slots of the pivot rows and columns are zeroed, then init(P+1) (behind one more
 //             barrier in the rare front that re-uses a slot given up by the front before it)
-// Three block barriers per front (four with a re-used slot).  HBM traffic of a factorisation = the compact Jacobian values in,
+// Three block barriers per front (four without look-ahead or with a re-used slot).  HBM traffic of a factorisation = the compact Jacobian values in,
 // the factors out; nothing is read twice.  Every entry receives the same updates in the same order
 // as in the left-looking block plan (tile_lu), so the two kernels agree bit for bit.
 #pragma once
@@ -34,7 +33,6 @@ struct DevFront {
     const int *f_info;      // FrontPlan::FREC ints per front
     const int *lists;
     const int2 *init;       // {window position, (J entry + 1) << 1 | is_diagonal}
-    const int *pb_init;     // 8 x 8 source words of the pivot-block entries that are new at a look-ahead front
 };
 
 constexpr int WL_NT = 256;          // threads per CTA
@@ -43,19 +41,12 @@ constexpr int WL_NT = 256;          // threads per CTA
 #endif
 constexpr int WL_CB = KB2_WL_CB;    // columns of a register block of the update (rows: 8)
 constexpr int WL_PF = 4;            // original values of the next front a thread fetches ahead
-#ifndef KB2_WL_NZ
-#define KB2_WL_NZ 2
-#endif
-constexpr int WL_NZ = KB2_WL_NZ;    // strip tasks (substitutions) a thread runs interleaved
-#ifndef KB2_WL_DYN
-#define KB2_WL_DYN 0                // 1: the blocks of the update are handed out dynamically (see the D phase)
-#endif
 
 __host__ __device__ inline int wl_list_cap(int max_nl, int max_nu) { return 16 + 2 * max_nu + 2 * max_nl; }
 // mw = members per CTA
 __host__ __device__ inline size_t wl_smem_bytes(int mw, int Wr, int Wc, int max_nl, int max_nu)
 {
-    return (size_t)8 * mw * ((size_t)Wr * Wc + 2 * (64 + 8)) + (size_t)8 * WL_PF * WL_NT + (size_t)3 * wl_list_cap(max_nl, max_nu) * 4 + 16;
+    return (size_t)8 * mw * ((size_t)Wr * Wc + 2 * (64 + 8)) + (size_t)8 * WL_PF * WL_NT + (size_t)3 * wl_list_cap(max_nl, max_nu) * 4;
 }
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
@@ -148,7 +139,6 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
     double *stage = dinv2 + 2 * 8 * MW;                   // [WL_PF][WL_NT]: Jacobian values of the next front's new entries
     const int LCAP = wl_list_cap(fr.max_nl, fr.max_nu);
     int *lst = reinterpret_cast<int *>(stage + WL_PF * WL_NT);   // [3][LCAP]: lists of this front and the next two
-    int *dctr = lst + 3 * LCAP;                           // next block of the update to hand out (KB2_WL_DYN)
     const int tid = threadIdx.x, mw = tid % MW, x = tid / MW, lane = tid & 31, warp = tid >> 5;
     const int xl = x - 32 / MW;                           // index among the x-threads outside warp 0 (negative in warp 0)
     if (stagger_ns > 0 && blockIdx.x >= gridDim.x / 2) __nanosleep(stagger_ns);
@@ -186,7 +176,6 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
         {
             const int n = Wr * Wc * MW;
             for (int i = tid; i < n; i += WL_NT) Win[i] = 0.0;
-            if (tid == 0) *dctr = 0;
             for (int q = 0; q < 2 && q < fr.NF; ++q) {
                 const int *f = fr.f_info + q * FREC;
                 const int len = 16 + 2 * f[2] + 2 * f[3];
@@ -211,10 +200,7 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
             const bool has_next = P + 1 < fr.NF;
             const int *fn = f + (has_next ? FREC : 0);
             const int ni = has_next ? fn[8] : 0, ioff = fn[7], hot = has_next ? fn[9] : 0;
-            const int laword = has_next ? fn[10] : 0;
-            const bool la = laword & 1;                   // the next pivot block is factorised while this front updates
-            const bool la_rows_new = laword & 2;          // its rows / these of its columns only become active at the next front:
-            const int la_cmask = (laword >> 8) & 255;     // their entries start from the original values, not from the window
+            const bool la = has_next && fn[10];           // the next pivot block is factorised while this front updates
             // ---- look ahead: the lists of front P+2 go to the third buffer (cp.async); the original
             // values of front P+1 are fetched by the warps that have no pivot block to prepare ----
             if (P + 2 < fr.NF) {
@@ -233,11 +219,9 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
                 cp_async_commit();
                 if (la) {
                     const int ln = lane / MW, nr1 = fn[0];
-                    const int *pb = fr.pb_init + (fn[11] - 1) + ln * 8;      // dereferenced only when fn[11] > 0 (some entry is new)
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (ln < nr1 && j < nr1)
-                            Dn[j] = (la_rows_new || ((la_cmask >> j) & 1)) ? init_value(pb[j]) : WinM[(L1[ln] * Wc + L1[8 + j]) * MW];
+                        if (ln < nr1 && j < nr1) Dn[j] = WinM[(L1[ln] * Wc + L1[8 + j]) * MW];
                 }
             } else {
                 // the next front's new entries: positions and sources now (in flight during the strips) ...
@@ -258,15 +242,14 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
 #pragma unroll
                 for (int r = 0; r < 8; ++r) { offU[r] = r < nr ? prs[r] * Wc * MW : 0; offL[r] = r < nr ? pcs[r] * MW : 0; }
                 const int ntask = nu + nl;
-                for (int t = x; t < ntask; t += WL_NZ * NX) {
-                    int tt[WL_NZ];
-                    bool live[WL_NZ], isu[WL_NZ];
-                    int wb[WL_NZ], gst[WL_NZ];
-                    double *g[WL_NZ], v[WL_NZ][8];
+                for (int t = x; t < ntask; t += 2 * NX) {
+                    int tt[2] = {t, t + NX < ntask ? t + NX : t};
+                    const bool two = t + NX < ntask;
+                    bool isu[2];
+                    int wb[2], gst[2];
+                    double *g[2], v[2][8];
 #pragma unroll
-                    for (int z = 0; z < WL_NZ; ++z) {
-                        live[z] = t + z * NX < ntask;
-                        tt[z] = live[z] ? t + z * NX : t;
+                    for (int z = 0; z < 2; ++z) {
                         isu[z] = tt[z] < nu;
                         if (isu[z]) {
                             wb[z] = ucs[tt[z]] * MW;
@@ -287,15 +270,15 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
 #pragma unroll
                             for (int a = 0; a < r; ++a) {
 #pragma unroll
-                                for (int z = 0; z < WL_NZ; ++z) v[z][r] -= Dl[((isu[z] ? r * 8 + a : a * 8 + r)) * MW + mw] * v[z][a];
+                                for (int z = 0; z < 2; ++z) v[z][r] -= Dl[((isu[z] ? r * 8 + a : a * 8 + r)) * MW + mw] * v[z][a];
                             }
 #pragma unroll
-                            for (int z = 0; z < WL_NZ; ++z) v[z][r] *= isu[z] ? dinv[r * MW + mw] : 1.0;
+                            for (int z = 0; z < 2; ++z) v[z][r] *= isu[z] ? dinv[r * MW + mw] : 1.0;
                         }
                     }
 #pragma unroll
-                    for (int z = 0; z < WL_NZ; ++z) {
-                        if (live[z]) {
+                    for (int z = 0; z < 2; ++z) {
+                        if (z == 0 || two) {
 #pragma unroll
                             for (int r = 0; r < 8; ++r)
                                 if (r < nr) { WinM[wb[z] + (isu[z] ? offU[r] : offL[r])] = v[z][r]; g[z][(size_t)r * gst[z]] = v[z][r]; }
@@ -314,58 +297,16 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
             __syncthreads();
             // ---- D: rank-nr update of Lrows x Ucols.  With look-ahead, warp 0 instead brings its copy
             // of the next pivot block up to date (same strip values, same order) and factorises it. ----
-#if KB2_WL_DYN
-            // the blocks of the update are handed out a warp's worth at a time from a counter in shared
-            // memory: warp 0 joins after its pivot block, and no warp waits for a last partial pass
             if (la && warp == 0) {
                 const int ln = lane / MW, nr1 = fn[0];
-                if (ln < nr1 && !la_rows_new) {
+                if (ln < nr1) {
                     const double *lrow = WinM + L1[ln] * Wc * MW;
                     for (int k = 0; k < nr; ++k) {
                         const double l = lrow[pcs[k] * MW];
                         const double *urow = WinM + prs[k] * Wc * MW;
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            if (j < nr1 && !((la_cmask >> j) & 1)) Dn[j] -= l * urow[L1[8 + j] * MW];
-                    }
-                }
-                wl_pivot_block<MB, MW>(Dn, lane, nr1, Dl2 + ((P + 1) & 1) * 64 * MW, dinv2 + ((P + 1) & 1) * 8 * MW,
-                                       invd + (size_t)fn[1] * MB, lu + ((size_t)fn[4] + (size_t)fn[5] * nr1) * MB);
-            }
-            if (nu > 0 && nl > 0) {
-                constexpr int XW = 32 / MW;
-                const int ncb = (nu + WL_CB - 1) / WL_CB, nrb = (nl + 7) / 8, nblk = nrb * ncb;
-                for (;;) {
-                    int b0 = 0;
-                    if (lane == 0) b0 = atomicAdd(dctr, XW);
-                    b0 = __shfl_sync(FULL, b0, 0);
-                    if (b0 >= nblk) break;
-                    const int t = b0 + lane / MW;
-                    if (t < nblk) {
-                        const int rb = t / ncb, cb = t - rb * ncb;
-                        int ro[8], co[WL_CB];
-                        bool rok[8], cok[WL_CB];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { rok[i] = rb * 8 + i < nl; ro[i] = lrs[min(rb * 8 + i, nl - 1)] * Wc * MW; }
-#pragma unroll
-                        for (int c = 0; c < WL_CB; ++c) { cok[c] = cb + c * ncb < nu; co[c] = ucs[min(cb + c * ncb, nu - 1)] * MW; }
-                        wl_update_block<MW>(WinM, prs, pcs, ro, co, rok, cok, nr, Wc);
-                    }
-                }
-            }
-            __syncthreads();
-            if (tid == 0) *dctr = 0;
-#else
-            if (la && warp == 0) {
-                const int ln = lane / MW, nr1 = fn[0];
-                if (ln < nr1 && !la_rows_new) {      // (new rows and columns are no targets of this front)
-                    const double *lrow = WinM + L1[ln] * Wc * MW;
-                    for (int k = 0; k < nr; ++k) {
-                        const double l = lrow[pcs[k] * MW];
-                        const double *urow = WinM + prs[k] * Wc * MW;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (j < nr1 && !((la_cmask >> j) & 1)) Dn[j] -= l * urow[L1[8 + j] * MW];
+                            if (j < nr1) Dn[j] -= l * urow[L1[8 + j] * MW];
                     }
                 }
                 wl_pivot_block<MB, MW>(Dn, lane, nr1, Dl2 + ((P + 1) & 1) * 64 * MW, dinv2 + ((P + 1) & 1) * 8 * MW,
@@ -385,7 +326,6 @@ __global__ void __launch_bounds__(WL_NT, 1) k_lu_window(DevNet net, DevPlan pl, 
                 }
             }
             __syncthreads();
-#endif
             // ---- the pivot rows and columns of P are dead: clear their slots (inactive entries stay
             // zero), then the next front's original values (which may land in those slots) ----
             // (warp r clears pivot r: its row slot is contiguous, its column slot strided)

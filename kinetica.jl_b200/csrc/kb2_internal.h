@@ -61,9 +61,7 @@ struct FrontPlan {
     // per front: {nr, first pivot row, nu, nl, base slot of the panel, position of the diagonal block,
     //             offset into `lists`, offset into `init` (entries), init entries,
     //             1 if a row/column of this front takes a slot that the previous front gave up,
-    //             look-ahead word: bit 0 the pivot block is factorised ahead (during the previous
-    //             front's update), bit 1 its rows are new at this front, bits 8..15 its new columns,
-    //             offset + 1 into pb_init of the block's original-value sources (0: no entry is new)}
+    //             1 if the pivot block may be factorised ahead (no entry of it is new at this front), 0}
     std::vector<int32_t> f_info;
     // per front, at its offset: prs[8] pcs[8] (window slots of the pivot rows / columns, -1 beyond nr),
     // ucs[nu] (column slots of Ucols, ascending), ujj[nu] (position of that column in the panel's U
@@ -73,9 +71,6 @@ struct FrontPlan {
     // window entries that become live when front P starts and have an original value (inactive
     // entries are zero): {window position rslot*Wc + cslot, (J entry + 1) << 1 | is_diagonal}
     std::vector<int32_t> init;
-    // per look-ahead front with new pivot-block entries: 8 x 8 source words (row-major, same coding
-    // as init, 0 = not new or no original value)
-    std::vector<int32_t> pb_init;
 };
 
 // Everything the kernels need that depends only on the network (shared by all members).

@@ -1,6 +1,5 @@
 """Stand-alone timing of the window LU and the triangular sweeps on a C3-shaped ensemble for the
-candidate orderings of `auto` (kb2_symbolic), with and without look-ahead for every front
-(KB2_LA_ALL).  Usage: python scripts/time_orderings.py [S] [B] [config id]"""
+candidate orderings of `auto` (kb2_symbolic).  Usage: python scripts/time_orderings.py [S] [B] [config id]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -14,8 +13,7 @@ sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + cid)
 rng = np.random.default_rng(1)
 u = rng.uniform(0, 1e-2, (S, B)); k = 10 ** rng.uniform(-3, 3, (R, B)); hg = np.full(B, 1e4)
 names = {3: "natural, hubs last", 5: "RCM", 6: "Sloan 1:2", 7: "Sloan 2:1", 4: "auto"}
-for ordering, la_all in ((3, 0), (3, 1), (5, 1), (6, 0), (6, 1), (7, 1), (4, 1)):
-    os.environ["KB2_LA_ALL"] = str(la_all)
+for ordering in (3, 5, 6, 7, 4):
     h = _lib.Handle(0)
     h.set_network(S, *rd.flatten())
     nnzJ, nnzLU, nfma = h.symbolic(ordering)
@@ -23,6 +21,6 @@ for ordering, la_all in ((3, 0), (3, 1), (5, 1), (6, 0), (6, 1), (7, 1), (4, 1))
     h.factor(u, k, hg, want_lu=False)
     t_lu = h.time_kernel(7, B, 5)
     t_tri = h.time_kernel(4, B, 5)
-    print("%-20s la_all %d | nnzLU %6d padded %6d fma_pad %8d window %3dx%3d fronts %4d | window LU %.3f ms  trisolve %.3f ms  (LU + 6 sweeps %.3f ms)"
-          % (names[ordering], la_all, nnzLU, ps["padded"], ps["fma_padded"], fp["Wr"], fp["Wc"], fp["NF"], t_lu, t_tri, t_lu + 6 * t_tri), flush=True)
+    print("%-20s | nnzLU %6d padded %6d fma_pad %8d window %3dx%3d fronts %4d | window LU %.3f ms  trisolve %.3f ms  (LU + 6 sweeps %.3f ms)"
+          % (names[ordering], nnzLU, ps["padded"], ps["fma_padded"], fp["Wr"], fp["Wc"], fp["NF"], t_lu, t_tri, t_lu + 6 * t_tri), flush=True)
     h.close()

@@ -19,7 +19,7 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
     win = np.zeros(Wr * Wc)                        # inactive entries are zero
     lu = np.full(padded, np.nan)
     invd = {}
-    lists, init, pb_init = fp["lists"], fp["init"], fp["pb_init"]
+    lists, init = fp["lists"], fp["init"]
     dead_prev, dead_prev_r, dead_prev_c = False, set(), set()
     finfo = fp["f_info"]
 
@@ -28,8 +28,7 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
         return v + hg_inv if src & 1 else v
 
     Dn = None                                      # look-ahead copy of this front's pivot block (made during the previous front)
-    for P, (nr, p0, nu, nl, base, nxt, loff, ioff, icnt, hot, laword, pboff) in enumerate(finfo):
-        la, rows_new, cmask = laword & 1, bool(laword & 2), (laword >> 8) & 255
+    for P, (nr, p0, nu, nl, base, nxt, loff, ioff, icnt, hot, la, _c) in enumerate(finfo):
         # window entries that become live at this front and have an original value
         touches_prev = False
         for pos, src in init[ioff: ioff + icnt]:
@@ -38,21 +37,9 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
             touches_prev |= (pos // Wc in dead_prev_r) or (pos % Wc in dead_prev_c) if dead_prev else False
         assert hot or not touches_prev            # values land in a slot of the previous front only in flagged fronts
         prs, pcs = lists[loff: loff + 8], lists[loff + 8: loff + 16]
-        blk = {int(r) * Wc + int(c): (a, b) for a, r in enumerate(prs[:nr]) for b, c in enumerate(pcs[:nr])}
-        new_in_block = {blk[int(pos)]: src for pos, src in init[ioff: ioff + icnt] if int(pos) in blk}
-        if la:
-            # entries of the block that are new at this front: exactly those the look-ahead word flags,
-            # with the same original-value sources in pb_init
-            for (a, b), src in new_in_block.items():
-                assert rows_new or (cmask >> b) & 1
-                assert pboff > 0 and pb_init[pboff - 1 + a * 8 + b] == src
-            if pboff > 0:
-                for a in range(nr):
-                    for b in range(nr):
-                        if pb_init[pboff - 1 + a * 8 + b]:
-                            assert (a, b) in new_in_block
-            else:
-                assert not new_in_block and not rows_new and not cmask
+        if la:      # look-ahead fronts: no entry of the pivot block is new at this front
+            blk = {int(r) * Wc + int(c) for r in prs[:nr] for c in pcs[:nr]}
+            assert P >= 1 and not any(int(pos) in blk for pos, _ in init[ioff: ioff + icnt])
         ucs = lists[loff + 16: loff + 16 + nu]
         ujj = lists[loff + 16 + nu: loff + 16 + 2 * nu]
         lrs = lists[loff + 16 + 2 * nu: loff + 16 + 2 * nu + nl]
@@ -97,25 +84,18 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
             slot0, stride = lgs[ii] & 0x0fffffff, (lgs[ii] >> 28) + 1
             for q in range(nr):
                 lu[slot0 + q * stride] = X[q]
-        # look-ahead (k_lu_window, warp 0): the next front's pivot block, copied BEFORE this front's
-        # update — entries whose row or column is new at the next front from their original values,
-        # the others from the window — and brought up to date with this front's strips
+        # look-ahead (k_lu_window, warp 0): the next front's pivot block, copied from the window BEFORE
+        # this front's update and brought up to date with this front's strips
         Dn = None
-        if P + 1 < len(finfo) and finfo[P + 1][10] & 1:
-            nr1, lw, pb1, lo1 = int(finfo[P + 1][0]), int(finfo[P + 1][10]), int(finfo[P + 1][11]), int(finfo[P + 1][6])
-            rn1, cm1 = bool(lw & 2), (lw >> 8) & 255
+        if P + 1 < len(finfo) and finfo[P + 1][10]:
+            nr1, lo1 = int(finfo[P + 1][0]), int(finfo[P + 1][6])
             r1, c1 = lists[lo1: lo1 + 8], lists[lo1 + 8: lo1 + 16]
-            Dn = np.zeros((nr1, nr1))
+            Dn = np.array([[win[r1[a] * Wc + c1[b]] for b in range(nr1)] for a in range(nr1)])
             for a in range(nr1):
-                for b in range(nr1):
-                    Dn[a, b] = orig(int(pb_init[pb1 - 1 + a * 8 + b])) if (rn1 or (cm1 >> b) & 1) else win[r1[a] * Wc + c1[b]]
-            if not rn1:
-                for a in range(nr1):
-                    for q in range(nr):
-                        l = win[r1[a] * Wc + pcs[q]]
-                        for b in range(nr1):
-                            if not (cm1 >> b) & 1:
-                                Dn[a, b] -= l * win[prs[q] * Wc + c1[b]]
+                for q in range(nr):
+                    l = win[r1[a] * Wc + pcs[q]]
+                    for b in range(nr1):
+                        Dn[a, b] -= l * win[prs[q] * Wc + c1[b]]
         # rank-nr update, pivots in ascending order
         for ii in range(nl):
             for jj in range(nu):
@@ -135,11 +115,7 @@ def run_fronts(fp, plan, jv, hg_inv, padded):
 
 @pytest.mark.parametrize("S,R,ordering", [(96, 400, 0), (200, 1000, 3), (200, 1000, 0), (420, 2100, 3), (30, 60, 1), (64, 256, 4),
                                           (200, 1000, 5), (420, 2100, 6), (200, 1000, 7), (96, 400, 6)])
-@pytest.mark.parametrize("la_all", [0, 1])
-def test_front_plan_matches_block_plan(S, R, ordering, la_all, monkeypatch):
-    """la_all = 1: look-ahead pivot blocks for every front (KB2_LA_ALL, an A/B switch of kb2_front.cpp):
-    entries that are new at their front start from their original values."""
-    monkeypatch.setenv("KB2_LA_ALL", str(la_all))
+def test_front_plan_matches_block_plan(S, R, ordering):
     sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + 50 + S)
     h = _lib.Handle(-1)
     h.set_network(S, *rd.flatten())
@@ -163,10 +139,7 @@ def test_front_plan_matches_block_plan(S, R, ordering, la_all, monkeypatch):
             ref[plan["slot_of"][p]] = Wp[i, colidx[p]]
     ref_invd = run_plan(plan, ref)
     assert fp["NF"] == st["panels"] and fp["Wr"] > 0 and fp["Wc"] > 0
-    la = fp["f_info"][:, 10] & 1
-    assert la[0] == 0 and (not la_all or np.all(la[1:] == 1))
-    if not la_all:
-        assert np.all(fp["f_info"][:, 11] == 0) and len(fp["pb_init"]) == 0
+    assert fp["f_info"][0, 10] == 0 and set(np.unique(fp["f_info"][:, 10])) <= {0, 1}
     lu, invd = run_fronts(fp, plan, jv, hg, st["padded"])
     assert not np.any(np.isnan(lu))                # every storage slot is written (exactly once)
     # same updates in the same order (the interpreters differ in how they round a block product;

@@ -174,13 +174,10 @@ def _factor_trisolve_check(h, net, B, seed):
                                                (1000, 5000, 4, 8, 4), (1000, 5000, 3, 8, 4), (1000, 5000, 5, 12, 4), (1000, 5000, 7, 6, 2),
                                                (200, 1000, 7, 37, 4), (200, 1000, 6, 9, 2), (200, 1000, 5, 5, 1), (420, 2100, 7, 16, 4),
                                                (96, 400, 6, 19, 4), (64, 256, 4, 8, 4)])
-@pytest.mark.parametrize("la_all", [0, 1])
-def test_window_lu_matches_block_plan_lu_bitwise(built, monkeypatch, S, R, ordering, B, mb, la_all):
+def test_window_lu_matches_block_plan_lu_bitwise(built, monkeypatch, S, R, ordering, B, mb):
     """The window LU (right-looking, active submatrix in shared memory, built from the compact
     Jacobian values) and the block-plan LU (left-looking over the assembled padded storage) apply the
-    same updates to every entry in the same order: factors and solutions must be identical bits.
-    la_all: look-ahead pivot blocks for every front (KB2_LA_ALL, kb2_front.cpp)."""
-    monkeypatch.setenv("KB2_LA_ALL", str(la_all))
+    same updates to every entry in the same order: factors and solutions must be identical bits."""
     from kinetica_b200 import _lib
     from kinetica_b200.synthetic import synthetic_crn, SEED_BASE
     sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + (3 if S == 1000 else 50 + S))
