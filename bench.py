@@ -138,6 +138,8 @@ def phase_bytes(S, R, nnzJ, nnzLU):
     }
 
 
+ORDERING_NAMES = {0: "minimum degree", 1: "natural", 2: "caller-supplied", 3: "natural, hub species last",
+                  5: "reverse Cuthill-McKee, hub species last", 6: "Sloan 1:2, hub species last", 7: "Sloan 2:1, hub species last"}
 PHASE_LAUNCHES = {"jacobian": 1, "lu": 1, "stage_rhs": 6, "stage_sweeps": 6, "step_end": 1}
 
 
@@ -373,7 +375,8 @@ def main():
     # ---- per-kernel roofline, from the live phase timing of the timed solves ----
     peak, peak_src = load_peaks()
     pb = phase_bytes(S, R, es.nnzJ, es.nnzLU)
-    traffic = load_traffic(args.workload, B, es.h.get_plan_stats()["padded"])
+    plan = es.h.get_plan_stats()
+    traffic = load_traffic(args.workload, B, plan["padded"])
     kern = {}
     round_ms = 0.0
     for nm, (tot, n) in phase_acc.items():
@@ -434,7 +437,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "S": S, "R": R, "members_per_gpu": B, "tspan": [0.0, 1.0], "ts_update": 1e-2,
                    "saves": Ns, "abstol": pars.abstol, "reltol": pars.reltol, "integrator": "Rodas4",
-                   "nnzJ": es.nnzJ, "nnzLU": es.nnzLU, "lu_fma_per_member": es.n_fma, "lu_padded_slots": es.h.get_plan_stats()["padded"],
+                   "nnzJ": es.nnzJ, "nnzLU": es.nnzLU, "lu_fma_per_member": es.n_fma, "lu_padded_slots": plan["padded"],
+                   "ordering": ORDERING_NAMES.get(plan["ordering"], str(plan["ordering"])) + " (chosen by `auto`)",
                    "l2": "inputs larger than L2 (LU values %.1f GB per launch)" % (8 * es.nnzLU * Bp / 1e9),
                    "symbolic_s": t_sym, "members_ok": ok_all, "attempted_steps_per_member": attempts / B,
                    "rounds": rounds, "requested": {"steps": args.steps, "warmup": args.warmup, "budget_s": args.budget_s},
