@@ -57,7 +57,7 @@ def _cost(h, cap=227 * 1024):
     ps, fp = h.get_plan_stats(), h.get_front_plan()
     f = fp["f_info"]
     blocks = float(np.sum(((f[:, 3] + 7) // 8) * ((f[:, 2] + 3) // 4)))
-    lu = 66.3 * blocks + 38.9 * float(np.sum(f[:, 2] + f[:, 3])) + 4523.0 * fp["NF"]
+    lu = 66.3 * blocks + 38.9 * float(np.sum(f[:, 2] + f[:, 3])) + 4523.0 * fp["NF"] + 2000.0 * float(np.sum(f[:, 10] == 0))
     lcap = 16 + 2 * fp["max_nu"] + 2 * fp["max_nl"]
     fits = [mw for mw in (4, 2, 1) if 8 * mw * (fp["Wr"] * fp["Wc"] + 144) + 8 * 4 * 256 + 3 * lcap * 4 + 16 <= cap]
     lu *= 4.0 / fits[0] if fits else 6.0
@@ -66,6 +66,8 @@ def _cost(h, cap=227 * 1024):
 
 @pytest.mark.parametrize("S,R,seed", NETS)
 def test_auto_keeps_the_candidate_with_the_smallest_modelled_cost(S, R, seed):
+    """... unless that is less than 3 % ahead of the natural order with hub species last (the baseline every
+    full-size run was first made with; 3 % is within the model's error)."""
     h = _handle(S, R, seed)
     costs = {}
     for code in (3, 5, 6, 7, 0):
@@ -73,9 +75,20 @@ def test_auto_keeps_the_candidate_with_the_smallest_modelled_cost(S, R, seed):
         costs[code] = _cost(h)
     h.symbolic(4)
     chosen = h.get_plan_stats()["ordering"]
-    assert chosen in costs and costs[chosen] == min(costs.values())
+    others = {c: v for c, v in costs.items() if c != 3}
+    best = min(others, key=lambda c: (others[c], (5, 6, 7, 0).index(c)))
+    assert chosen == (best if others[best] < 0.97 * costs[3] else 3)
     assert abs(_cost(h) - costs[chosen]) < 1e-6 * costs[chosen]
     h.close()
+
+
+def test_auto_choices_on_the_baseline_networks():
+    """C3 and C5 leave the natural order (modelled 12 % / 6 % ahead), C4 keeps it (2 %)."""
+    for S, seed, want in ((1000, 3, 6), (5000, 5, 7), (10000, 4, 3)):
+        h = _handle(S, 5 * S, seed)
+        h.symbolic(4)
+        assert h.get_plan_stats()["ordering"] == want, (S, h.get_plan_stats())
+        h.close()
 
 
 def test_bench_network_gets_the_profile_ordering():
