@@ -71,8 +71,8 @@ int32_t kb2_set_network(kb2_handle h, int64_t S, int64_t R,
  * (methods.jl:157-158) and KLU's symbolic phase.  ordering: 0 = minimum degree,
  * 1 = natural, 2 = caller-supplied via kb2_set_ordering, 3 = natural with hub species last,
  * 5 = reverse Cuthill-McKee and 6 / 7 = Sloan's profile reduction (weights 1:2 / 2:1) on the graph
- * without the hub species, hubs last, 4 = auto (the candidate among 0, 3, 5, 6, 7 with the smallest
- * modelled cost of the factorisation and the triangular sweeps, see kb2_symbolic in kb2_api.cu). ---- */
+ * without the hub species, hubs last, 4 = auto (3, unless one of 0, 5, 6, 7 has a modelled cost of the
+ * factorisation and the triangular sweeps more than 3 % below it; see kb2_symbolic in kb2_api.cu). ---- */
 int32_t kb2_set_ordering(kb2_handle h, const int64_t *perm);
 int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, int64_t *nnzLU, int64_t *n_fma);
 int32_t kb2_get_pattern(kb2_handle h, int64_t *colptr, int64_t *rowval);          /* CSC of P_J */
