@@ -165,3 +165,51 @@ def test_front_window_of_the_bench_network_fits_shared_memory():
     need = 8 * MB * (fp["Wr"] * fp["Wc"] + 64 + 8) + 8 * (16 + 2 * fp["max_nu"] + 2 * fp["max_nl"]) + 8 * 4 * 256
     assert need <= 227 * 1024, (fp["Wr"], fp["Wc"], fp["max_nl"], fp["max_nu"], need)
     h.close()
+
+
+@pytest.mark.parametrize("S,seed", [(1000, 3), (5000, 5)])
+def test_plans_of_the_baseline_networks_factorise_correctly(S, seed):
+    """C3 and C5 (BASELINE configs 3 and 5) with the ordering `auto` chooses for them (Sloan 1:2 / 2:1): the
+    front plan and the block plan, interpreted in numpy, give the same factors, L U = P W P^T and a linear
+    system solved through the factors agrees with numpy's — at the networks' full size, on the host."""
+    import scipy.linalg as sl
+    R = 5 * S
+    sd, rd, Ea, A = synthetic_crn(S, R, SEED_BASE + seed)
+    h = _lib.Handle(-1)
+    h.set_network(S, *rd.flatten())
+    h.symbolic(4)
+    plan, fp, st = h.get_plan(), h.get_front_plan(), h.get_plan_stats()
+    assert st["ordering"] in (6, 7) and fp["Wr"] * fp["Wc"] * 4 * 8 < 200 * 1024
+    rowptr, colidx, diagpos = h.get_lu_pattern()
+    colptr, rowval = h.get_pattern()
+    perm = h.get_ordering()
+    h.close()
+    net = ko.Network(S, rd.id_reacs, rd.id_prods, rd.stoic_reacs, rd.stoic_prods)
+    rng = np.random.default_rng(S)
+    u = rng.uniform(0, 1, S)
+    k = 10 ** rng.uniform(-3, 3, R)
+    J = net.jac_sparse(u, k).toarray()
+    hg = 5000.0
+    jv = np.array([J[rowval[p], l] for l in range(S) for p in range(colptr[l], colptr[l + 1])])
+    Wp = (np.eye(S) * hg - J)[np.ix_(perm, perm)]
+    ref = np.zeros(st["padded"])
+    for i in range(S):
+        for p in range(rowptr[i], rowptr[i + 1]):
+            ref[plan["slot_of"][p]] = Wp[i, colidx[p]]
+    run_plan(plan, ref)
+    lu, invd = run_fronts(fp, plan, jv, hg, st["padded"])
+    scale = np.max(np.abs(ref))
+    assert not np.any(np.isnan(lu)) and np.max(np.abs(lu - ref)) <= 1e-12 * scale
+    L, U = np.zeros((S, S)), np.eye(S)
+    for i in range(S):
+        for p in range(rowptr[i], rowptr[i + 1]):
+            j, v = colidx[p], lu[plan["slot_of"][p]]
+            if j <= i:
+                L[i, j] = v
+            else:
+                U[i, j] = v
+    assert np.max(np.abs(L @ U - Wp)) <= 1e-12 * scale
+    b = rng.normal(size=S)
+    x = sl.solve_triangular(U, sl.solve_triangular(L, b, lower=True), lower=False)
+    x_ref = np.linalg.solve(Wp, b)
+    assert np.max(np.abs(x - x_ref)) <= 1e-10 * np.max(np.abs(x_ref))
