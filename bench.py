@@ -409,7 +409,10 @@ def main():
                 "algorithmic_bytes_per_launch": kd["alg_bytes_per_launch"], "avg_launch_ms": kd["ms"],
                 "share_of_step": kd["share"],
                 "whole_solve": {"achieved": sum(pb[k] * PHASE_LAUNCHES[k] for k in pb) * attempts / (float(np.mean(dev_ms)) * 1e-3) / 1e9,
-                                "note": "algorithmic bytes of all phase kernels x attempted steps / device time of the solve"}}
+                                "algorithmic_bytes_per_member_attempt": sum(pb[k] * PHASE_LAUNCHES[k] for k in pb),
+                                "note": "algorithmic bytes of all phase kernels x attempted steps / device time of the solve; the bytes "
+                                        "follow nnzLU of the ordering in use (SURVEY 8d: 8(nnzJ+nnzLU) for the LU, 8(nnzLU+2S) per sweep): "
+                                        "an ordering with less fill lowers them, so this fraction is only comparable at equal nnzLU"}}
     roofline["whole_solve"]["frac"] = roofline["whole_solve"]["achieved"] / peak
     if dom == "lu" and "frac_fp64" in kd:
         roofline.update({"frac_fp64": kd["frac_fp64"], "fp64_tflops": kd["fp64_tflops"], "fp64_peak_tflops": kd["fp64_peak_tflops"],
