@@ -296,8 +296,9 @@ extern "C" int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, i
         // depend on it, per tile of four members in SM cycles (calibrated on C3):
         // the window LU's update (8 x 4 register blocks), its strips (one task per L row / U column),
         // the per-front overhead (more for a front whose pivot block cannot be factorised ahead), and
-        // the six triangular sweeps of a step, which stream the padded panel storage.  A window that does not fit shared memory with four members per CTA costs
-        // the factorisation a factor (fewer members per CTA, or the left-looking block plan).
+        // the six triangular sweeps of a step, which stream the padded panel storage.  A window that
+        // does not fit shared memory with four members per CTA costs the factorisation a factor
+        // (fewer members per CTA, or the left-looking block plan).
         const size_t cap = h->smem_optin ? h->smem_optin : (size_t)227 * 1024;
         auto cost = [&](const Symbolic &s) {
             const FrontPlan &f = s.fronts;
@@ -316,7 +317,7 @@ extern "C" int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, i
         };
         // The natural order with hub species last is the baseline (every full-size run of configs 3-5
         // was first made with it); another candidate replaces it only if the model puts it more than
-        // 3 % ahead — the model's error: it promised 12 % on C3 where the solve gained 5 %.
+        // 3 % ahead — the model's error: it promised 10 % on C3 where the solve gained 5 %.
         Symbolic best, base;
         double best_cost = 0.0, base_cost = 0.0;
         int best_cand = -1;
