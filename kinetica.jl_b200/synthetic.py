@@ -46,7 +46,12 @@ def synthetic_crn(S: int, R: int, seed: int, w: float = 16.0, n_hubs: int = 8,
     # positive conservation law: concentrations stay bounded (random unbalanced A -> B + C networks
     # are autocatalytic and blow up, which no real CRN does)
     mass = rng.integers(1, 5, S)
+    attempts = 0
     while len(fwd) < nf:
+        attempts += 1
+        if attempts > 2000 * nf + 20000:
+            raise ValueError(f"synthetic_crn: no {nf} distinct mass-balanced forward reactions among {S} species "
+                             f"(window {w}, {n_hubs} hubs): ask for fewer reactions")
         kind = rng.random()
         c = int(rng.integers(0, S))
 

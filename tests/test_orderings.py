@@ -103,3 +103,50 @@ def test_bench_network_gets_the_profile_ordering():
     assert st["padded"] < 0.92 * nat["padded"] and st["fma_padded"] < 0.82 * nat["fma_padded"]
     assert 8 * 4 * (fp["Wr"] * fp["Wc"] + 144) < 200 * 1024
     h.close()
+
+
+def test_random_small_networks_every_ordering():
+    """Forty random networks (4 to 70 species, with and without locality or hubs): every ordering is a
+    permutation, equals the restatement, and its block and front plans factorise W correctly (numpy
+    interpreters of tests/test_block_plan.py and tests/test_front_plan.py)."""
+    from oracle import kinetica_oracle as ko
+    from test_block_plan import run_plan
+    from test_front_plan import run_fronts
+    rng = np.random.default_rng(7)
+    done = 0
+    for trial in range(40):
+        S = int(rng.integers(4, 70))
+        R = 2 * int(rng.integers(1, 2 * S))
+        try:
+            sd, rd, _, _ = synthetic_crn(S, R, 1000 + trial, w=float(rng.choice([1.5, 4, 16, 60])),
+                                         n_hubs=int(min(S, rng.integers(1, 9))), p_hub=float(rng.choice([0.0, 0.1, 0.5])))
+        except ValueError:          # more reactions asked for than the tiny network has
+            continue
+        net = ko.Network(S, rd.id_reacs, rd.id_prods, rd.stoic_reacs, rd.stoic_prods)
+        u = rng.uniform(0, 1, S)
+        k = 10 ** rng.uniform(-2, 2, R)
+        J = net.jac_dense(u, k)
+        for code in (3, 5, 6, 7, 4, 0):
+            h = _lib.Handle(-1)
+            h.set_network(S, *rd.flatten())
+            h.symbolic(code)
+            perm = h.get_ordering()
+            assert sorted(perm.tolist()) == list(range(S))
+            plan, fp, st = h.get_plan(), h.get_front_plan(), h.get_plan_stats()
+            rowptr, colidx, _ = h.get_lu_pattern()
+            colptr, rowval = h.get_pattern()
+            h.close()
+            if code in (5, 6, 7):
+                ref = oo.banded_order(S, colptr, rowval, "rcm" if code == 5 else "sloan", (1, 2) if code == 6 else (2, 1))
+                assert np.array_equal(ref, perm), (trial, code)
+            jv = np.array([J[rowval[p], l] for l in range(S) for p in range(colptr[l], colptr[l + 1])])
+            Wp = (np.eye(S) * 1e4 - J)[np.ix_(perm, perm)]
+            ref = np.zeros(st["padded"])
+            for i in range(S):
+                for p in range(rowptr[i], rowptr[i + 1]):
+                    ref[plan["slot_of"][p]] = Wp[i, colidx[p]]
+            run_plan(plan, ref)
+            lu, _ = run_fronts(fp, plan, jv, 1e4, st["padded"])
+            assert not np.any(np.isnan(lu)) and np.max(np.abs(lu - ref)) <= 1e-11 * np.max(np.abs(ref)), (trial, code)
+            done += 1
+    assert done >= 150
