@@ -313,11 +313,11 @@ extern "C" int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, i
             int mw = 0;
             for (int c = 4; c >= 1 && !mw; c >>= 1) if (wl_smem_bytes(c, f.Wr, f.Wc, f.max_nl, f.max_nu) <= cap) mw = c;
             lu *= mw ? 4.0 / mw : 6.0;
-            return lu + 10.36 * (double)s.panels.padded;
+            return lu + 5.25 * (double)s.panels.padded;       // slope of the sweeps in the same-box A/B: 0.772 -> 0.732 ms for 120 620 -> 107 787 slots
         };
         // The natural order with hub species last is the baseline (every full-size run of configs 3-5
         // was first made with it); another candidate replaces it only if the model puts it more than
-        // 3 % ahead — the model's error: it promised 10 % on C3 where the solve gained 5 %.
+        // 3 % ahead (the model's error: for the LU of C3 it says -9 % where the same-box A/B measured -7 %).
         Symbolic best, base;
         double best_cost = 0.0, base_cost = 0.0;
         int best_cand = -1;

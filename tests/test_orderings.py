@@ -61,7 +61,7 @@ def _cost(h, cap=227 * 1024):
     lcap = 16 + 2 * fp["max_nu"] + 2 * fp["max_nl"]
     fits = [mw for mw in (4, 2, 1) if 8 * mw * (fp["Wr"] * fp["Wc"] + 144) + 8 * 4 * 256 + 3 * lcap * 4 + 16 <= cap]
     lu *= 4.0 / fits[0] if fits else 6.0
-    return lu + 10.36 * ps["padded"]
+    return lu + 5.25 * ps["padded"]
 
 
 @pytest.mark.parametrize("S,R,seed", NETS)
