@@ -322,9 +322,15 @@ extern "C" int32_t kb2_symbolic(kb2_handle h, int32_t ordering, int64_t *nnzJ, i
         double best_cost = 0.0, base_cost = 0.0;
         int best_cand = -1;
         std::string first_error;
-        for (int cand : {3, 5, 6, 7, 0}) {
+        // minimum degree goes first: it is the robust one, and its fill bounds what the banded
+        // candidates may spend — on a network without locality their fill explodes: a candidate whose
+        // envelope (an upper bound of a banded order's fill) is beyond 2 x the minimum-degree nnzLU is
+        // dropped before its symbolic LU, and a symbolic LU is abandoned at 16 x the minimum-degree FMAs
+        int64_t fma_limit = INT64_MAX, env_limit = INT64_MAX;
+        for (int cand : {0, 3, 5, 6, 7}) {
             Symbolic c;
-            e = build_symbolic(h->net, cand, c);
+            e = build_symbolic(h->net, cand, c, fma_limit, env_limit);
+            if (e.empty() && cand == 0) { fma_limit = 16 * c.n_fma + 1000000; env_limit = 2 * c.nnzLU + 100000; }
             if (e.empty()) e = build_panels(c, h->net.S);
             if (e.empty()) e = build_fronts(c, h->net.S);
             if (!e.empty()) {       // a candidate may be out of reach (e.g. the fill of a banded order on a network without locality)

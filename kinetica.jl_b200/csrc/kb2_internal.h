@@ -117,7 +117,12 @@ struct Symbolic {
 std::string build_network(Network &net);
 // ordering: 0 min degree, 1 natural, 2 user (sym.perm preset), 3 natural with hub species last,
 // 5 reverse Cuthill-McKee / 6, 7 Sloan (weights 1:2, 2:1) on the graph without the hubs, hubs last
-std::string build_symbolic(const Network &net, int ordering, Symbolic &sym);
+// env_limit / fma_limit let `auto` drop a candidate whose fill explodes (a banded order on a network without
+// locality) at bounded cost: give up ("profile beyond the limit") before the symbolic LU when the envelope of
+// the permuted symmetrised pattern (an upper bound of the fill of a banded order) exceeds env_limit, and
+// ("fill beyond the limit") as soon as the symbolic LU has counted more than fma_limit FMAs
+std::string build_symbolic(const Network &net, int ordering, Symbolic &sym, int64_t fma_limit = INT64_MAX,
+                           int64_t env_limit = INT64_MAX);
 std::string build_panels(Symbolic &sym, int64_t S);
 std::string build_fronts(Symbolic &sym, int64_t S);
 

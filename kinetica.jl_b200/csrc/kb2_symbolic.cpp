@@ -226,7 +226,7 @@ static void banded_order(int64_t S, const std::vector<int64_t> &colptr, const st
     for (auto &d : dense) perm.push_back(d.second);
 }
 
-std::string build_symbolic(const Network &net, int ordering, Symbolic &sym)
+std::string build_symbolic(const Network &net, int ordering, Symbolic &sym, int64_t fma_limit, int64_t env_limit)
 {
     const int64_t S = net.S, R = net.R;
     // ---- Jacobian pattern P_J = {(i,l): exists j, net[i,j] != 0 and nu_lj > 0}, CSC ----
@@ -262,6 +262,19 @@ std::string build_symbolic(const Network &net, int ordering, Symbolic &sym)
     }
     sym.iperm.assign(S, 0);
     for (int64_t a = 0; a < S; ++a) sym.iperm[sym.perm[a]] = a;
+    if (env_limit != INT64_MAX) {
+        // envelope of the permuted symmetrised pattern: sum over rows of (row - first column) on both sides
+        std::vector<int64_t> first(S);
+        for (int64_t a = 0; a < S; ++a) first[a] = a;
+        for (int64_t l = 0; l < S; ++l)
+            for (int64_t p = sym.colptr[l]; p < sym.colptr[l + 1]; ++p) {
+                const int64_t a = sym.iperm[sym.rowval[p]], b = sym.iperm[l];
+                first[std::max(a, b)] = std::min(first[std::max(a, b)], std::min(a, b));
+            }
+        int64_t env = 0;
+        for (int64_t a = 0; a < S; ++a) env += 2 * (a - first[a]);
+        if (env > env_limit) return "profile beyond the limit";
+    }
     // ---- row-wise symbolic LU of P (P_J U diag) P^T without pivoting ----
     {
         std::vector<std::vector<int32_t>> rows(S);
@@ -285,6 +298,7 @@ std::string build_symbolic(const Network &net, int ordering, Symbolic &sym)
                 int32_t k = *lower.begin();
                 lower.erase(lower.begin());
                 sym.n_fma += (int64_t)upper[k].size();
+                if (sym.n_fma > fma_limit) return "fill beyond the limit";
                 for (int32_t j : upper[k])
                     if (mark[j] != (int32_t)i) { mark[j] = (int32_t)i; pat.push_back(j); if (j < i) lower.insert(j); }
             }

@@ -76,7 +76,7 @@ def test_auto_keeps_the_candidate_with_the_smallest_modelled_cost(S, R, seed):
     h.symbolic(4)
     chosen = h.get_plan_stats()["ordering"]
     others = {c: v for c, v in costs.items() if c != 3}
-    best = min(others, key=lambda c: (others[c], (5, 6, 7, 0).index(c)))
+    best = min(others, key=lambda c: (others[c], (0, 5, 6, 7).index(c)))
     assert chosen == (best if others[best] < 0.97 * costs[3] else 3)
     assert abs(_cost(h) - costs[chosen]) < 1e-6 * costs[chosen]
     h.close()
@@ -150,3 +150,25 @@ def test_random_small_networks_every_ordering():
             assert not np.any(np.isnan(lu)) and np.max(np.abs(lu - ref)) <= 1e-11 * np.max(np.abs(ref)), (trial, code)
             done += 1
     assert done >= 150
+
+
+def test_auto_on_a_network_without_locality_falls_back_to_minimum_degree():
+    """Reactions between species drawn from the whole network (window = S / 3): the banded candidates' fill is
+    several times the minimum-degree fill; `auto` drops them by their envelope before running their symbolic LU."""
+    import time
+    S = 1500
+    sd, rd, _, _ = synthetic_crn(S, 5 * S, SEED_BASE + 77, w=S / 3.0)
+    h = _lib.Handle(-1)
+    h.set_network(S, *rd.flatten())
+    t = time.perf_counter()
+    h.symbolic(0)
+    t_md = time.perf_counter() - t
+    nnz_md = h.nnzLU
+    h.symbolic(3)
+    assert h.nnzLU > 2 * nnz_md
+    t = time.perf_counter()
+    h.symbolic(4)
+    t_auto = time.perf_counter() - t
+    assert h.get_plan_stats()["ordering"] == 0 and h.nnzLU == nnz_md
+    assert t_auto < 3 * t_md + 1.0          # one full analysis plus four cheap rejections
+    h.close()
